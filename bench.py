@@ -1,0 +1,315 @@
+#!/usr/bin/env python
+"""Headline benchmark: agent-steps/sec of the lockstep env step (+ fused random-access policy).
+
+    python bench.py --gpus N --steps K --warmup W            # this repo, N GPUs (torchrun for N > 1)
+    python bench.py --impl reference --gpus N --steps K ...  # the reference's CPU path (oracle port), host cores
+
+Workload (BASELINE.json configs c3/c5): CombinatorialEnv, setup_8_channels.p, N = 6 devices,
+C = 8 channels, deadlines [7,14]x3, heterogeneous traffic at load 1/3, homogeneous_size=True (30 f32 per
+observation), 1,048,576 lockstep envs PER GPU (weak scaling; c5's 1M envs on one GPU so the per-step working set,
+~1.06 GB, is far larger than the 126 MB L2).  One "step" = one env step of all envs, observations emitted,
+actions from the fused CombinatorialRandomAccess policy (algorithms/baselines.py:181-183), reset after every
+episode_length = 200 steps inside the timed region.
+
+One JSON line on stdout (rank 0).  See DESIGN.md "Measurement" for every field.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+N_AGENTS, N_CHANNELS, MAX_DEADLINE = 6, 8, 14
+OBS_DIM = MAX_DEADLINE + 2 * N_CHANNELS
+# Algorithmic bytes per agent-step of the env-step kernel:
+#   read  buffers D + channel mask 1 + counters 8                      (the action mask is NOT read: fused policy)
+#   write buffers D + channel mask 1 + counters 8 + obs 4(D+2C) + (reward 4 + done 1 + ack C) / N
+ALG_BYTES = (MAX_DEADLINE + 1 + 8) + (MAX_DEADLINE + 1 + 8 + 4 * OBS_DIM + (5 + N_CHANNELS) / N_AGENTS)
+TP = 0.2          # transmission probability of the random-access policy
+LOAD = 1 / 3      # xp_load.py:53 first load level
+FALLBACK_HBM = 6650.0
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=400)
+    ap.add_argument("--warmup", type=int, default=20)
+    ap.add_argument("--impl", default="native", choices=["native", "reference"])
+    ap.add_argument("--envs", type=int, default=1 << 20, help="lockstep envs per GPU")
+    ap.add_argument("--cpu-envs", type=int, default=4096, help="envs per process of the CPU arm")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+# ------------------------------------------------------------------------------------------------
+# clocks sampled DURING the timed region
+# ------------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                 "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except OSError:
+            self.proc = None
+            return
+        threading.Thread(target=self._read, daemon=True).start()
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])), mx.append(float(r[1]))
+            except (ValueError, IndexError):
+                continue
+            for n, v in zip(names, r[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU arm: the oracle port of the reference's numpy path
+# ------------------------------------------------------------------------------------------------
+def _cpu_worker(args):
+    """Run `steps` env steps (+ random-access policy) of the oracle on `n_envs` envs; returns seconds."""
+    n_envs, steps, warmup, seed = args
+    os.environ.setdefault("OMP_NUM_THREADS", "1")
+    import numpy as np
+
+    from d2d_ppo_b200 import presets
+    from oracle.envs_np import CombinatorialOracle, NumpySource
+    kw = presets.combinatorial_kwargs("setup_8_channels", load=LOAD)
+    env = CombinatorialOracle(n_envs=n_envs, source=NumpySource(n_envs, seed), **kw)
+    rng = np.random.default_rng(seed + 1)
+    env.reset()
+
+    def one():
+        a = rng.binomial(1, TP, (n_envs, N_AGENTS, N_CHANNELS))      # baselines.py:182
+        _, _, _, done, _ = env.step(a)
+        if done:
+            env.reset()
+    for _ in range(warmup):
+        one()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        one()
+    return time.perf_counter() - t0
+
+
+def cpu_throughput(n_envs, steps, warmup, procs):
+    """agent-steps/s of `procs` independent oracle processes (max time over processes)."""
+    if procs == 1:
+        dt = _cpu_worker((n_envs, steps, warmup, 0))
+    else:
+        import multiprocessing as mp
+        with mp.get_context("spawn").Pool(procs) as pool:
+            dt = max(pool.map(_cpu_worker, [(n_envs, steps, warmup, i) for i in range(procs)]))
+    return procs * n_envs * N_AGENTS * steps / dt, dt
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    steps, warmup = args.steps, args.warmup
+    # bound the sample: one step of 4096 envs costs ~5 ms per process; keep the whole run to ~a minute
+    steps_eff = min(steps, 2000)
+    value, dt = cpu_throughput(args.cpu_envs, steps_eff, min(warmup, 50), cores)
+    sample = (f"{cores} processes x {args.cpu_envs} envs x {steps_eff} steps of oracle/envs_np.CombinatorialOracle "
+              f"(numpy restatement, vectorised over envs) + numpy random-access policy")
+    line = {
+        "impl": "reference", "metric": "agent-steps/sec (env step + random-access policy)", "value": value,
+        "unit": "agent-steps/s", "n_gpus": args.gpus, "steps": steps_eff, "warmup": min(warmup, 50),
+        "ms_per_step": dt / steps_eff * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "u8", "data": "synthetic", "config": workload_config(args.cpu_envs * cores, cpu=True),
+        "cpu_baseline": {"value": value, "unit": "agent-steps/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": "agent-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(envs_total, cpu=False):
+    return {"workload": "c5/c3: CombinatorialEnv setup_8_channels.p (N=6, C=8, deadlines [7,14]x3, heterogeneous "
+                        "traffic, load 1/3, homogeneous_size=True), fused random-access policy tp=0.2, "
+                        "obs f32 emitted, reset every 200 steps",
+            "envs_total": envs_total, "n_agents": N_AGENTS, "n_channels": N_CHANNELS, "episode_length": 200,
+            "rng": "numpy Generator" if cpu else "philox4x32-10",
+            "l2": "n/a" if cpu else "per-step working set ~1.06 GB per GPU >> 126 MB L2 (no flush needed)"}
+
+
+# ------------------------------------------------------------------------------------------------
+# native arm
+# ------------------------------------------------------------------------------------------------
+def run_native(args):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    from d2d_ppo_b200 import _lib, presets
+    from d2d_ppo_b200.envs import CombinatorialEnv
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus and world > 1:
+        raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}")
+    if args.gpus > 1 and world == 1:
+        raise SystemExit("for --gpus N > 1 launch with torch.distributed.run (one rank per GPU)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    B, K, W = args.envs, args.steps, args.warmup
+    kw = presets.combinatorial_kwargs("setup_8_channels", load=LOAD)
+    T = kw["episode_length"]
+    # shards are contiguous blocks of the global env index space; no data-path collective
+    env = CombinatorialEnv(n_envs=B, device=dev, seed=42, env_offset=rank * B, **kw)
+    obs_buf = torch.empty((N_AGENTS * OBS_DIM, B), dtype=torch.float32, device=dev)
+
+    def step():
+        if env.timestep >= T:
+            env.reset(with_state=False)
+        return env.step_random_access(TP, with_state=False, out_obs=obs_buf)
+
+    env.reset(with_state=False)
+    for _ in range(max(W, 3)):
+        step()
+
+    # ---- device-resident throughput: K steps, CUDA events on the launching stream --------------
+    sampler = ClockSampler(local)
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(K + 1)]
+    launches0 = _lib.launch_count()
+    barrier()
+    sampler.start()
+    ev[0].record()
+    n_resets = 0
+    for i in range(K):
+        if env.timestep >= T:
+            n_resets += 1
+        step()
+        ev[i + 1].record()
+    barrier()
+    clocks = sampler.stop()
+    launches = _lib.launch_count() - launches0
+    total_ms = max_over_ranks(ev[0].elapsed_time(ev[K]))
+    per = np.array([ev[i].elapsed_time(ev[i + 1]) for i in range(K)])
+    # per-launch duration of the step kernel: gaps that contain a reset launch are excluded from the average
+    kernel_ms = float(np.median(per))
+    value = world * B * N_AGENTS * K / (total_ms * 1e-3)
+
+    # ---- end to end through the public API with HOST buffers ------------------------------------
+    n_host = 4
+    host_actions = [torch.from_numpy(np.random.default_rng(i).binomial(1, TP, (B, N_AGENTS, N_CHANNELS))
+                                     .astype(np.uint8)).pin_memory() for i in range(n_host)]
+    host_reward = torch.empty(B, dtype=torch.int32).pin_memory()
+    Ke = max(10, min(K, 100))
+
+    def e2e_step(i):
+        if env.timestep >= T:
+            env.reset(with_state=False)
+        _, _, rew, done, _ = env.step(host_actions[i % n_host], with_state=False, out_obs=obs_buf)   # H2D inside
+        host_reward.copy_(rew[:, 0], non_blocking=True)                                            # D2H result
+        torch.cuda.current_stream().synchronize()
+        return int(host_reward[0])
+
+    for i in range(3):
+        e2e_step(i)
+    barrier()
+    t0 = time.perf_counter()
+    for i in range(Ke):
+        e2e_step(i)
+    barrier()
+    e2e_s = max_over_ranks(time.perf_counter() - t0)
+    e2e_value = world * B * N_AGENTS * Ke / e2e_s
+
+    # ---- roofline of the dominant kernel ---------------------------------------------------------
+    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(peaks_path):
+        peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "of measured (MEASURED_PEAKS.json hbm_gbs)"
+    else:
+        peak, peak_src = FALLBACK_HBM, "of fallback (B200_PROFILING.md 6.65 TB/s)"
+    achieved = B * N_AGENTS * ALG_BYTES / (kernel_ms * 1e-3) / 1e9
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "env_step_traffic.json")
+    if os.path.exists(tpath):
+        traffic = json.load(open(tpath)).get("dram_bytes_per_launch")
+
+    line = {
+        "metric": "agent-steps/sec (env step + random-access policy)", "value": value, "unit": "agent-steps/s",
+        "n_gpus": world, "steps": K, "warmup": max(W, 3), "ms_per_step": total_ms / K, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+        "config": workload_config(world * B),
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                     "traffic": traffic, "kernel": "comb_step_kernel<4,uint8_t,6>", "kernel_ms": kernel_ms,
+                     "alg_bytes_per_agent_step": ALG_BYTES, "agent_steps_per_launch": B * N_AGENTS,
+                     "peak_source": peak_src},
+        "e2e": {"value": e2e_value, "unit": "agent-steps/s",
+                "h2d_bytes_per_step": B * N_AGENTS * N_CHANNELS, "d2h_bytes_per_step": B * 4, "steps": Ke,
+                "api": "CombinatorialEnv.step(actions u8 [B,N,C] in pinned host memory) -> rewards read on host"},
+        "gpu_launches": int(launches), "resets_in_timed_region": n_resets, "clocks": clocks,
+    }
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        steps_cpu = 600
+        v, dt = cpu_throughput(args.cpu_envs, steps_cpu, 20, 1)
+        v1, dt1 = cpu_throughput(1, 3000, 50, 1)
+        line["cpu_baseline"] = {
+            "value": v, "unit": "agent-steps/s", "cores": 1, "kind": "port",
+            "sample": f"{args.cpu_envs} envs x {steps_cpu} steps of oracle/envs_np.CombinatorialOracle (numpy, "
+                      f"vectorised over envs) + numpy random-access policy, {dt:.1f} s",
+            "single_env_value": v1,
+            "single_env_sample": f"1 env x 3000 steps (the reference's own shape: one instance per process), {dt1:.1f} s"}
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    a = parse()
+    if a.impl == "reference":
+        run_reference(a)
+    else:
+        run_native(a)

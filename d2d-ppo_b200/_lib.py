@@ -1,0 +1,106 @@
+"""ctypes binding of the C ABI in include/d2d_b200.h (libd2d_b200.so, built in-tree for sm_100a).
+
+Loading fails loudly: there is no CPU or PyTorch fallback for any entry point.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libd2d_b200.so")
+
+OK, ERR_INVALID, ERR_CUDA, ERR_STATE = 0, -1, -2, -3
+ENV_COMBINATORIAL, ENV_SINGLE_CHANNEL, ENV_CHANNEL_SELECTION = 0, 1, 2
+RNG_PHILOX, RNG_REPLAY = 0, 1
+ARRIVAL_POISSON, ARRIVAL_BERNOULLI = 0, 1
+MAX_AGENTS, MAX_CHANNELS, MAX_DEADLINE, POISSON_KMAX = 64, 32, 32, 16
+
+
+class D2DError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__(f"libd2d_b200 error {code}: {msg}")
+        self.code = code
+
+
+class EnvConfig(C.Structure):
+    _fields_ = [
+        ("kind", C.c_int32), ("n_envs", C.c_int32), ("n_agents", C.c_int32), ("n_channels", C.c_int32),
+        ("episode_length", C.c_int32), ("homogeneous_size", C.c_int32), ("rng_mode", C.c_int32),
+        ("reserved0", C.c_int32), ("seed", C.c_uint64), ("env_offset", C.c_uint64),
+        ("deadlines", C.POINTER(C.c_int32)), ("arrival_kind", C.POINTER(C.c_int32)),
+        ("arrival_active", C.POINTER(C.c_uint64)), ("poisson_cdf", C.POINTER(C.c_uint32)),
+        ("bernoulli_thr", C.POINTER(C.c_uint64)), ("switch_thr", C.POINTER(C.c_uint32)),
+        ("nbr_offset", C.POINTER(C.c_int32)), ("nbr_index", C.POINTER(C.c_int32)),
+    ]
+
+
+_lib = None
+
+_P = C.c_void_p
+_SIGNATURES = {
+    # name: (restype, argtypes)
+    "d2d_last_error": (C.c_char_p, []),
+    "d2d_abi_version": (C.c_int, []),
+    "d2d_launch_count": (C.c_uint64, []),
+    "d2d_env_create": (C.c_int, [C.POINTER(EnvConfig), C.POINTER(_P)]),
+    "d2d_env_destroy": (C.c_int, [_P]),
+    "d2d_env_obs_rows": (C.c_int, [_P]),
+    "d2d_env_obs_offset": (C.c_int, [_P, C.c_int]),
+    "d2d_env_obs_dim": (C.c_int, [_P, C.c_int]),
+    "d2d_env_state_rows": (C.c_int, [_P]),
+    "d2d_env_timestep": (C.c_int, [_P]),
+    "d2d_env_record_bytes": (C.c_int, [_P]),
+    "d2d_env_mask_bytes": (C.c_int, [_P]),
+    "d2d_env_set_replay": (C.c_int, [_P, _P, _P, C.c_int]),
+    "d2d_env_reset": (C.c_int, [_P, _P, _P, _P]),
+    "d2d_env_step": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, _P]),
+    "d2d_env_step_random_access": (C.c_int, [_P, C.c_double, _P, _P, _P, _P, _P, _P, _P]),
+    "d2d_pack_actions": (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_int, _P]),
+    "d2d_env_export_state": (C.c_int, [_P, _P, _P, _P, _P, _P, _P]),
+    "d2d_env_import_state": (C.c_int, [_P, _P, _P, _P, _P, _P, C.c_int, _P]),
+    "d2d_env_scores": (C.c_int, [_P, _P, _P, _P, _P]),
+}
+
+
+def exported_symbols():
+    """Names declared in include/d2d_b200.h that this binding expects (checked by the CPU tests)."""
+    return sorted(_SIGNATURES)
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise ImportError(
+                f"{LIB_PATH} is missing: the CUDA library has not been built. Run "
+                "`python -c 'import __graft_entry__ as g; g.build()'` from the repo root. "
+                "There is no CPU fallback for this path.")
+        handle = C.CDLL(LIB_PATH)
+        for name, (res, args) in _SIGNATURES.items():
+            fn = getattr(handle, name)  # AttributeError if the symbol is not exported
+            fn.restype, fn.argtypes = res, args
+        if handle.d2d_abi_version() != 1:
+            raise ImportError("libd2d_b200.so ABI version mismatch; rebuild")
+        _lib = handle
+    return _lib
+
+
+def check(code):
+    if code != OK:
+        raise D2DError(code, lib().d2d_last_error().decode("utf-8", "replace"))
+    return code
+
+
+def launch_count() -> int:
+    return int(lib().d2d_launch_count())
+
+
+def ptr(t):
+    """Device (or host) address of a torch tensor, or NULL."""
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+def current_stream():
+    import torch
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)

@@ -1,0 +1,1020 @@
+// Lockstep step/reset of the three channel-access environments for B envs x N devices on one B200.
+//
+// Replaces (file:line under /root/reference):
+//   envs/combinatorial_env.py:61-114 reset, :127-242 step     -> comb_reset_kernel / comb_step_kernel
+//   envs/env.py:51-101 reset, :118-217 step                   -> sc_reset_kernel / sc_step_kernel
+//   envs/channel_selection_env.py:49-98 reset, :116-214 step  -> sel_reset_kernel / sel_step_kernel
+//   algorithms/baselines.py:181-183 CombinatorialRandomAccess.act (fused, act_mode = 1)
+//
+// Design (sm_100a, HBM-bound integer/byte work -- no tensor cores on purpose):
+//   * one THREAD per env, devices looped in-thread.  Per-channel collision / success resolution is then pure
+//     bitmask arithmetic in registers (once / twice accumulators over the devices' channel masks): no
+//     shuffles, no idle lanes for N = 6, and every per-device parameter (deadline, switch thresholds,
+//     arrival law) is warp-uniform, so there is no divergence on heterogeneous devices.
+//   * env-minor structure of arrays: record k of env b lives at X[k][b]; a warp of 32 consecutive envs
+//     issues one fully coalesced 128..512-byte request per row.  Packet buffers are one 8/16/32-byte record
+//     per (device, env) (byte d = packets with d slots to the deadline), moved with one vector load/store.
+//   * observations are emitted as f32 rows obs[row][b]: each warp store writes one full 128-byte line.
+//   * grid-stride persistent launch sized in whole waves of the SM count; per-env parameters are staged
+//     once per block in shared memory and read by broadcast.
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <new>
+#include <vector>
+
+#include "common.cuh"
+#include "philox.cuh"
+
+namespace d2d {
+
+// ------------------------------------------------------------------------------------------------
+// parameter blob (device global -> shared memory at block start)
+// ------------------------------------------------------------------------------------------------
+struct EnvParamsHdr {
+  int32_t N, C, D, T, homog, kind, sum_dl, obs_rows, state_rows;
+  int32_t off_cdf, off_sw, off_nbr_off, off_nbr_idx, total_bytes;
+  uint8_t deadline[D2D_MAX_AGENTS];
+  uint8_t arrival_kind[D2D_MAX_AGENTS];
+  uint16_t obs_off[D2D_MAX_AGENTS];
+  uint16_t obs_dim[D2D_MAX_AGENTS];
+  uint16_t sbuf_off[D2D_MAX_AGENTS];  // first row of device k's buffer inside `state`
+  uint64_t bern_thr[D2D_MAX_AGENTS];
+  float inv_count[D2D_MAX_AGENTS + 1];  // (float)(1.0 / count) -- channel_selection_env.py:137
+};
+
+struct StepArgs {
+  uint32_t* buf;
+  void* chan;
+  uint32_t* disc;
+  uint32_t* recv;
+  uint32_t* stats;
+  const uint8_t* params;
+  int params_bytes;
+  const void* actions;
+  void* actions_out;
+  float* obs;
+  float* state;
+  int32_t* reward;
+  uint8_t* done;
+  void* ack;
+  const uint8_t* rp_arr;  // replay arrivals of this timestep, u8 [N][B]
+  const void* rp_sw;      // replay switch draws of this timestep
+  int B;
+  uint32_t t;  // timestep being produced (0 = reset)
+  uint32_t k0, k1;
+  uint32_t env_offset;
+  uint64_t active;  // bit k: device k draws an arrival at timestep t
+  int rng_mode;
+  int act_mode;  // 0 = actions from memory, 1 = fused random-access policy
+  uint32_t tp_thr;
+  int done_flag;
+};
+
+__device__ __forceinline__ const EnvParamsHdr* stage_params(const StepArgs& a, uint8_t* smem) {
+  const uint32_t* src = reinterpret_cast<const uint32_t*>(a.params);
+  uint32_t* dst = reinterpret_cast<uint32_t*>(smem);
+  for (int i = threadIdx.x; i < a.params_bytes / 4; i += blockDim.x) dst[i] = src[i];
+  __syncthreads();
+  return reinterpret_cast<const EnvParamsHdr*>(smem);
+}
+
+// ------------------------------------------------------------------------------------------------
+// packet-buffer records: W 32-bit words, byte d (little endian) = packets with d slots left
+// ------------------------------------------------------------------------------------------------
+template <int W>
+struct Rec {
+  uint32_t w[W];
+};
+
+template <int W>
+__device__ __forceinline__ Rec<W> rec_load(const uint32_t* base, size_t idx) {
+  Rec<W> r;
+  if constexpr (W == 2) {
+    const uint2 v = reinterpret_cast<const uint2*>(base)[idx];
+    r.w[0] = v.x, r.w[1] = v.y;
+  } else {
+#pragma unroll
+    for (int q = 0; q < W / 4; ++q) {
+      const uint4 v = reinterpret_cast<const uint4*>(base)[idx * (W / 4) + q];
+      r.w[4 * q] = v.x, r.w[4 * q + 1] = v.y, r.w[4 * q + 2] = v.z, r.w[4 * q + 3] = v.w;
+    }
+  }
+  return r;
+}
+
+template <int W>
+__device__ __forceinline__ void rec_store(uint32_t* base, size_t idx, const Rec<W>& r) {
+  if constexpr (W == 2) {
+    reinterpret_cast<uint2*>(base)[idx] = make_uint2(r.w[0], r.w[1]);
+  } else {
+#pragma unroll
+    for (int q = 0; q < W / 4; ++q)
+      reinterpret_cast<uint4*>(base)[idx * (W / 4) + q] =
+          make_uint4(r.w[4 * q], r.w[4 * q + 1], r.w[4 * q + 2], r.w[4 * q + 3]);
+  }
+}
+
+template <int W>
+__device__ __forceinline__ bool rec_any(const Rec<W>& r) {
+  uint32_t o = 0;
+#pragma unroll
+  for (int j = 0; j < W; ++j) o |= r.w[j];
+  return o != 0;
+}
+
+// remove one packet from the earliest non-empty slot (combinatorial_env.py:169-170)
+template <int W>
+__device__ __forceinline__ void rec_pop_earliest(Rec<W>& r, bool enable) {
+  bool done = !enable;
+#pragma unroll
+  for (int j = 0; j < W; ++j) {
+    const uint32_t w = r.w[j];
+    const bool hit = !done && w != 0;
+    const int pos = (__ffs((int)w) - 1) & 24;  // bit offset of the lowest non-zero byte
+    r.w[j] = hit ? w - (1u << pos) : w;
+    done |= hit;
+  }
+}
+
+// age by one slot (combinatorial_env.py:120-124); returns the expired count (old slot 0)
+template <int W>
+__device__ __forceinline__ uint32_t rec_age(Rec<W>& r) {
+  const uint32_t expired = r.w[0] & 0xFFu;
+#pragma unroll
+  for (int j = 0; j + 1 < W; ++j) r.w[j] = __funnelshift_r(r.w[j], r.w[j + 1], 8);
+  r.w[W - 1] >>= 8;
+  return expired;
+}
+
+template <int W>
+__device__ __forceinline__ void rec_set_byte(Rec<W>& r, int idx, uint32_t val) {
+  const int s = (idx & 3) * 8;
+#pragma unroll
+  for (int j = 0; j < W; ++j)
+    if (j == (idx >> 2)) r.w[j] = (r.w[j] & ~(0xFFu << s)) | (val << s);
+}
+
+template <int W>
+__device__ __forceinline__ uint32_t rec_sum(const Rec<W>& r) {
+  uint32_t s = 0;
+#pragma unroll
+  for (int j = 0; j < W; ++j) s += __vsadu4(r.w[j], 0u);
+  return s;
+}
+
+// write the first `n` slots of a record as f32 rows p[0], p[B], p[2B], ...
+template <int W>
+__device__ __forceinline__ void rec_emit(const Rec<W>& r, int n, float* p, size_t B) {
+#pragma unroll
+  for (int d = 0; d < 4 * W; ++d) {
+    if (d < n) {
+      *p = (float)((r.w[d >> 2] >> (8 * (d & 3))) & 0xFFu);
+      p += B;
+    }
+  }
+}
+
+// arrival of device k at timestep a.t (only called when the device is active)
+__device__ __forceinline__ uint32_t draw_arrival(const StepArgs& a, const EnvParamsHdr* P, const uint32_t* cdf, int k,
+                                                 int b) {
+  if (a.rng_mode == D2D_RNG_REPLAY) return a.rp_arr[(size_t)k * a.B + b];
+  const uint32_t u =
+      philox4x32_10(a.env_offset + (uint32_t)b, a.t, (uint32_t)k | (kPurposeArrival << 16), 0u, a.k0, a.k1).x;
+  if (P->arrival_kind[k] == D2D_ARRIVAL_BERNOULLI) return (uint64_t)u < P->bern_thr[k] ? 1u : 0u;
+  const uint32_t* c = cdf + k * D2D_POISSON_KMAX;
+  uint32_t n = 0;
+#pragma unroll 1
+  for (int m = 0; m < D2D_POISSON_KMAX; ++m) {
+    if (u < c[m]) break;  // thresholds are non-decreasing
+    ++n;
+  }
+  return n;
+}
+
+// ================================================================================================
+// CombinatorialEnv
+// ================================================================================================
+template <int W, typename MaskT, int NFIX>
+__global__ void __launch_bounds__(256) comb_step_kernel(const StepArgs a) {
+  extern __shared__ __align__(16) uint8_t smem[];
+  const EnvParamsHdr* P = stage_params(a, smem);
+  const uint32_t* cdf = reinterpret_cast<const uint32_t*>(smem + P->off_cdf);
+  const uint32_t* swthr = reinterpret_cast<const uint32_t*>(smem + P->off_sw);
+  const int N = NFIX ? NFIX : P->N;
+  const int C = P->C;
+  const size_t B = (size_t)a.B;
+  constexpr int NMAX = NFIX ? NFIX : D2D_MAX_AGENTS;
+  MaskT* chan = reinterpret_cast<MaskT*>(a.chan);
+  const MaskT* act = reinterpret_cast<const MaskT*>(a.actions);
+  MaskT* act_out = reinterpret_cast<MaskT*>(a.actions_out);
+  const MaskT* rp_sw = reinterpret_cast<const MaskT*>(a.rp_sw);
+  const uint32_t cmask = C >= 32 ? 0xFFFFFFFFu : ((1u << C) - 1u);
+
+  for (int b = blockIdx.x * blockDim.x + threadIdx.x; b < a.B; b += gridDim.x * blockDim.x) {
+    const uint32_t env = a.env_offset + (uint32_t)b;
+    MaskT att[NMAX];
+    Rec<W> recs[NFIX ? NFIX : 1];
+    MaskT chn[NFIX ? NFIX : 1];
+
+    // ---- pass 1: who transmits where (combinatorial_env.py:135-148) ----
+    uint32_t once = 0, twice = 0, good_any = 0;
+#pragma unroll
+    for (int k = 0; k < N; ++k) {
+      const Rec<W> r = rec_load<W>(a.buf, (size_t)k * B + b);
+      const uint32_t ch = chan[(size_t)k * B + b];
+      uint32_t want;
+      if (a.act_mode == 0) {
+        want = act[(size_t)k * B + b];
+      } else {
+        const uint32_t thr = a.tp_thr;
+        want = philox_lane_mask(env, a.t, (uint32_t)k | (kPurposePolicy << 16), C, a.k0, a.k1,
+                                [thr](int) { return thr; });
+        if (act_out) act_out[(size_t)k * B + b] = (MaskT)want;
+      }
+      const uint32_t at = rec_any<W>(r) ? (want & cmask) : 0u;
+      twice |= once & at;
+      once |= at;
+      good_any |= at & ch;
+      att[k] = (MaskT)at;
+      if constexpr (NFIX != 0) recs[k] = r, chn[k] = (MaskT)ch;
+    }
+    // ack/nack per channel (combinatorial_env.py:155-157): +1 iff exactly one user and its channel is good
+    const uint32_t acked = once & ~twice & good_any;
+    const uint32_t nacked = once & ~acked;
+
+    // ---- pass 2: serve, age, switch, arrive, observe ----
+    int n_success = 0;
+#pragma unroll
+    for (int k = 0; k < N; ++k) {
+      const size_t idx = (size_t)k * B + b;
+      Rec<W> r;
+      uint32_t ch;
+      if constexpr (NFIX != 0) {
+        r = recs[k], ch = chn[k];
+      } else {
+        r = rec_load<W>(a.buf, idx), ch = chan[idx];
+      }
+      const bool success = ((uint32_t)att[k] & ch & acked) != 0;  // :160-161
+      n_success += success;
+      rec_pop_earliest<W>(r, success);                            // :164-170
+      const uint32_t expired = rec_age<W>(r);                     // :173
+      if (expired) a.disc[idx] += expired;                        // :174
+      uint32_t sw;                                                // :175, :116-118
+      if (a.rng_mode == D2D_RNG_REPLAY) {
+        sw = rp_sw[idx];
+      } else {
+        const uint32_t* thr = swthr + k * C;
+        sw = philox_lane_mask(env, a.t, (uint32_t)k | (kPurposeSwitch << 16), C, a.k0, a.k1,
+                              [thr](int c) { return thr[c]; });
+      }
+      const uint32_t ch_new = (ch ^ sw) & cmask;
+      chan[idx] = (MaskT)ch_new;
+      const int dl = P->deadline[k];
+      if ((a.active >> k) & 1ull) {                               // :178-196
+        const uint32_t arrived = draw_arrival(a, P, cdf, k, b);
+        rec_set_byte<W>(r, dl - 1, arrived);
+        if (arrived) a.recv[idx] += arrived;
+      }
+      rec_store<W>(a.buf, idx, r);
+      if (a.obs) {                                                // :199-206
+        float* o = a.obs + (size_t)P->obs_off[k] * B + b;
+        const int nb = P->homog ? P->D : dl;
+        rec_emit<W>(r, nb, o, B);
+        o += (size_t)nb * B;
+        for (int c = 0; c < C; ++c) o[(size_t)c * B] = (float)((ch >> c) & 1u);  // pre-switch copy (:145)
+        o += (size_t)C * B;
+        for (int c = 0; c < C; ++c) o[(size_t)c * B] = (float)((acked >> c) & 1u) - (float)((nacked >> c) & 1u);
+      }
+      if (a.state) {                                              // :207-209
+        rec_emit<W>(r, dl, a.state + (size_t)P->sbuf_off[k] * B + b, B);
+        float* s = a.state + ((size_t)P->sum_dl + (size_t)k * C) * B + b;
+        for (int c = 0; c < C; ++c) s[(size_t)c * B] = (float)((ch_new >> c) & 1u);
+      }
+    }
+    if (a.state) {
+      float* s = a.state + ((size_t)P->sum_dl + (size_t)N * C) * B + b;
+      for (int c = 0; c < C; ++c) s[(size_t)c * B] = (float)((acked >> c) & 1u) - (float)((nacked >> c) & 1u);
+    }
+    if (a.ack) {
+      int8_t* q = reinterpret_cast<int8_t*>(a.ack) + b;
+      for (int c = 0; c < C; ++c) q[(size_t)c * B] = (int8_t)((int)((acked >> c) & 1u) - (int)((nacked >> c) & 1u));
+    }
+    a.reward[b] = n_success;                                      // :211
+    if (a.done) a.done[b] = (uint8_t)a.done_flag;                 // :233-236
+  }
+}
+
+template <int W, typename MaskT>
+__global__ void __launch_bounds__(256) comb_reset_kernel(const StepArgs a) {
+  extern __shared__ __align__(16) uint8_t smem[];
+  const EnvParamsHdr* P = stage_params(a, smem);
+  const uint32_t* cdf = reinterpret_cast<const uint32_t*>(smem + P->off_cdf);
+  const int N = P->N, C = P->C;
+  const size_t B = (size_t)a.B;
+  MaskT* chan = reinterpret_cast<MaskT*>(a.chan);
+  const uint32_t cmask = C >= 32 ? 0xFFFFFFFFu : ((1u << C) - 1u);
+  for (int b = blockIdx.x * blockDim.x + threadIdx.x; b < a.B; b += gridDim.x * blockDim.x) {
+    for (int k = 0; k < N; ++k) {
+      const size_t idx = (size_t)k * B + b;
+      Rec<W> r;
+#pragma unroll
+      for (int j = 0; j < W; ++j) r.w[j] = 0;
+      uint32_t arrived = 0;
+      const int dl = P->deadline[k];
+      if ((a.active >> k) & 1ull) {
+        arrived = draw_arrival(a, P, cdf, k, b);
+        rec_set_byte<W>(r, dl - 1, arrived);
+      }
+      rec_store<W>(a.buf, idx, r);
+      chan[idx] = (MaskT)cmask;          // combinatorial_env.py:88
+      a.disc[idx] = 0;                   // :91
+      a.recv[idx] = arrived;             // :92
+      if (a.obs) {                       // :102-109 -- channel and ack/nack slots are ones at reset
+        float* o = a.obs + (size_t)P->obs_off[k] * B + b;
+        const int nb = P->homog ? P->D : dl;
+        rec_emit<W>(r, nb, o, B);
+        o += (size_t)nb * B;
+        for (int c = 0; c < 2 * C; ++c) o[(size_t)c * B] = 1.0f;
+      }
+      if (a.state) rec_emit<W>(r, dl, a.state + (size_t)P->sbuf_off[k] * B + b, B);
+    }
+    if (a.state) {                       // :110-112
+      float* s = a.state + (size_t)P->sum_dl * B + b;
+      for (int c = 0; c < (N + 1) * C; ++c) s[(size_t)c * B] = 1.0f;
+    }
+  }
+}
+
+// ================================================================================================
+// D2DEnv (single channel)
+// ================================================================================================
+template <int W>
+__global__ void __launch_bounds__(256) sc_step_kernel(const StepArgs a) {
+  extern __shared__ __align__(16) uint8_t smem[];
+  const EnvParamsHdr* P = stage_params(a, smem);
+  const uint32_t* cdf = reinterpret_cast<const uint32_t*>(smem + P->off_cdf);
+  const uint32_t* swthr = reinterpret_cast<const uint32_t*>(smem + P->off_sw);
+  const int32_t* nbr_off = reinterpret_cast<const int32_t*>(smem + P->off_nbr_off);
+  const uint8_t* nbr_idx = smem + P->off_nbr_idx;
+  const int N = P->N;
+  const size_t B = (size_t)a.B;
+  uint8_t* chan = reinterpret_cast<uint8_t*>(a.chan);
+  const uint8_t* act = reinterpret_cast<const uint8_t*>(a.actions);
+  uint8_t* act_out = reinterpret_cast<uint8_t*>(a.actions_out);
+  const uint8_t* rp_sw = reinterpret_cast<const uint8_t*>(a.rp_sw);
+
+  for (int b = blockIdx.x * blockDim.x + threadIdx.x; b < a.B; b += gridDim.x * blockDim.x) {
+    const uint32_t env = a.env_offset + (uint32_t)b;
+    // ---- pass 1 (env.py:125-127): attempts and the lone transmitter's channel ----
+    uint64_t att = 0, good = 0;
+    for (int k = 0; k < N; ++k) {
+      const size_t idx = (size_t)k * B + b;
+      const Rec<W> r = rec_load<W>(a.buf, idx);
+      uint32_t want;
+      if (a.act_mode == 0) {
+        want = act[idx] != 0;
+      } else {
+        const uint32_t thr = a.tp_thr;
+        want = philox_lane_mask(env, a.t, (uint32_t)k | (kPurposePolicy << 16), 1, a.k0, a.k1,
+                                [thr](int) { return thr; });
+        if (act_out) act_out[idx] = (uint8_t)want;
+      }
+      const uint64_t at = (want && rec_any<W>(r)) ? 1ull : 0ull;
+      att |= at << k;
+      good |= (at & (uint64_t)(chan[idx] & 1u)) << k;
+    }
+    const int n_att = __popcll(att);
+    // env.py:130-152: exactly one attempt is decoded iff its channel is good (binomial(1, state) is deterministic)
+    const bool lone = n_att == 1;
+    const bool decoded = lone && good != 0;
+    const int ack = n_att > 1 ? -1 : (decoded ? 1 : 0);
+    if (lone && !decoded) a.stats[b] += 1;          // channel_errors (:147)
+    if (n_att > 1) a.stats[B + b] += 1;             // n_collisions   (:150)
+
+    // ---- pass 2: serve, age, switch, arrive ----
+    for (int k = 0; k < N; ++k) {
+      const size_t idx = (size_t)k * B + b;
+      Rec<W> r = rec_load<W>(a.buf, idx);
+      rec_pop_earliest<W>(r, decoded && ((att >> k) & 1ull));   // :137-144
+      const uint32_t expired = rec_age<W>(r);                   // :157
+      if (expired) a.disc[idx] += expired;                      // :158
+      uint32_t sw;                                              // :107-109
+      if (a.rng_mode == D2D_RNG_REPLAY) {
+        sw = rp_sw[idx] & 1u;
+      } else {
+        const uint32_t thr = swthr[k];
+        sw = philox_lane_mask(env, a.t, (uint32_t)k | (kPurposeSwitch << 16), 1, a.k0, a.k1,
+                              [thr](int) { return thr; });
+      }
+      chan[idx] = (uint8_t)((chan[idx] ^ sw) & 1u);
+      if ((a.active >> k) & 1ull) {                             // :162-180
+        const uint32_t arrived = draw_arrival(a, P, cdf, k, b);
+        rec_set_byte<W>(r, P->deadline[k] - 1, arrived);
+        if (arrived) a.recv[idx] += arrived;
+      }
+      rec_store<W>(a.buf, idx, r);
+      if (a.state) {                                            // :189-190
+        rec_emit<W>(r, P->deadline[k], a.state + (size_t)P->sbuf_off[k] * B + b, B);
+        a.state[((size_t)P->sum_dl + k) * B + b] = (float)chan[idx];
+      }
+    }
+    if (a.state) a.state[((size_t)P->sum_dl + N) * B + b] = (float)ack;
+    // ---- pass 3: neighbourhood observations (env.py:183-187), channel is the post-switch state ----
+    if (a.obs) {
+      for (int k = 0; k < N; ++k) {
+        float* o = a.obs + (size_t)P->obs_off[k] * B + b;
+        for (int j = nbr_off[k]; j < nbr_off[k + 1]; ++j) {
+          const int i = nbr_idx[j];
+          const Rec<W> r = rec_load<W>(a.buf, (size_t)i * B + b);
+          rec_emit<W>(r, P->deadline[i], o, B);
+          o += (size_t)P->deadline[i] * B;
+        }
+        for (int j = nbr_off[k]; j < nbr_off[k + 1]; ++j, o += B) *o = (float)chan[(size_t)nbr_idx[j] * B + b];
+        *o = (float)ack;
+      }
+    }
+    a.reward[b] = ack;                                          // :191 rewards = zeros(N) + ack
+    if (a.done) a.done[b] = (uint8_t)a.done_flag;
+  }
+}
+
+template <int W>
+__global__ void __launch_bounds__(256) sc_reset_kernel(const StepArgs a) {
+  extern __shared__ __align__(16) uint8_t smem[];
+  const EnvParamsHdr* P = stage_params(a, smem);
+  const uint32_t* cdf = reinterpret_cast<const uint32_t*>(smem + P->off_cdf);
+  const int32_t* nbr_off = reinterpret_cast<const int32_t*>(smem + P->off_nbr_off);
+  const uint8_t* nbr_idx = smem + P->off_nbr_idx;
+  const int N = P->N;
+  const size_t B = (size_t)a.B;
+  uint8_t* chan = reinterpret_cast<uint8_t*>(a.chan);
+  for (int b = blockIdx.x * blockDim.x + threadIdx.x; b < a.B; b += gridDim.x * blockDim.x) {
+    for (int k = 0; k < N; ++k) {
+      const size_t idx = (size_t)k * B + b;
+      Rec<W> r;
+#pragma unroll
+      for (int j = 0; j < W; ++j) r.w[j] = 0;
+      uint32_t arrived = 0;
+      if ((a.active >> k) & 1ull) {
+        arrived = draw_arrival(a, P, cdf, k, b);
+        rec_set_byte<W>(r, P->deadline[k] - 1, arrived);
+      }
+      rec_store<W>(a.buf, idx, r);
+      chan[idx] = 1;                     // env.py:79
+      a.disc[idx] = 0;
+      a.recv[idx] = arrived;
+      if (a.state) {
+        rec_emit<W>(r, P->deadline[k], a.state + (size_t)P->sbuf_off[k] * B + b, B);
+        a.state[((size_t)P->sum_dl + k) * B + b] = 1.0f;
+      }
+    }
+    a.stats[b] = 0;
+    a.stats[B + b] = 0;
+    if (a.state) a.state[((size_t)P->sum_dl + N) * B + b] = 0.0f;   // last_feedback = 0 (env.py:87,99)
+    if (a.obs) {                                                    // env.py:92-96
+      for (int k = 0; k < N; ++k) {
+        float* o = a.obs + (size_t)P->obs_off[k] * B + b;
+        for (int j = nbr_off[k]; j < nbr_off[k + 1]; ++j) {
+          const int i = nbr_idx[j];
+          const Rec<W> r = rec_load<W>(a.buf, (size_t)i * B + b);
+          rec_emit<W>(r, P->deadline[i], o, B);
+          o += (size_t)P->deadline[i] * B;
+        }
+        for (int j = nbr_off[k]; j < nbr_off[k + 1]; ++j, o += B) *o = 1.0f;
+        *o = 0.0f;
+      }
+    }
+  }
+}
+
+// ================================================================================================
+// ChannelSelectionEnv
+// ================================================================================================
+constexpr int kCountPlanes = 7;  // bit-sliced per-channel attempt counters, counts up to 127 >= N
+
+template <int W>
+__global__ void __launch_bounds__(256) sel_step_kernel(const StepArgs a) {
+  extern __shared__ __align__(16) uint8_t smem[];
+  const EnvParamsHdr* P = stage_params(a, smem);
+  const uint32_t* cdf = reinterpret_cast<const uint32_t*>(smem + P->off_cdf);
+  const uint32_t* swthr = reinterpret_cast<const uint32_t*>(smem + P->off_sw);
+  const int N = P->N, C1 = P->C + 1;
+  const size_t B = (size_t)a.B;
+  uint32_t* chan = reinterpret_cast<uint32_t*>(a.chan);
+  const uint8_t* act = reinterpret_cast<const uint8_t*>(a.actions);
+  const uint32_t* rp_sw = reinterpret_cast<const uint32_t*>(a.rp_sw);
+  const uint32_t cmask = C1 >= 32 ? 0xFFFFFFFFu : ((1u << C1) - 1u);
+
+  for (int b = blockIdx.x * blockDim.x + threadIdx.x; b < a.B; b += gridDim.x * blockDim.x) {
+    const uint32_t env = a.env_offset + (uint32_t)b;
+    const uint32_t ch = chan[b];
+    // ---- pass 1 (channel_selection_env.py:124-128): per-channel attempt counts, bit-sliced ----
+    uint32_t plane[kCountPlanes];
+#pragma unroll
+    for (int j = 0; j < kCountPlanes; ++j) plane[j] = 0;
+    for (int k = 0; k < N; ++k) {
+      const size_t idx = (size_t)k * B + b;
+      const Rec<W> r = rec_load<W>(a.buf, idx);
+      const uint32_t sel = act[idx];
+      uint32_t carry = (sel != 0 && rec_any<W>(r)) ? (1u << sel) : 0u;
+#pragma unroll
+      for (int j = 0; j < kCountPlanes; ++j) {
+        const uint32_t s = plane[j] ^ carry;
+        carry &= plane[j];
+        plane[j] = s;
+      }
+    }
+    uint32_t selected = 0, multi = 0;
+#pragma unroll
+    for (int j = 0; j < kCountPlanes; ++j) {
+      selected |= plane[j];
+      if (j > 0) multi |= plane[j];
+    }
+    const uint32_t win = plane[0] & ~multi & ch;                 // :140-141 one attempt on a good channel
+    a.stats[b] += __popc(selected & ch);                         // :132 selected_channel_qualities
+    a.stats[B + b] += __popc(selected);                          // :133 number_selected_channel
+
+    // ---- pass 2 ----
+    int n_success = 0;
+    for (int k = 0; k < N; ++k) {
+      const size_t idx = (size_t)k * B + b;
+      Rec<W> r = rec_load<W>(a.buf, idx);
+      const uint32_t sel = act[idx];
+      const bool success = sel != 0 && rec_any<W>(r) && ((win >> sel) & 1u);   // :142
+      n_success += success;
+      rec_pop_earliest<W>(r, success);
+      const uint32_t expired = rec_age<W>(r);
+      if (expired) a.disc[idx] += expired;
+      if ((a.active >> k) & 1ull) {
+        const uint32_t arrived = draw_arrival(a, P, cdf, k, b);
+        rec_set_byte<W>(r, P->deadline[k] - 1, arrived);
+        if (arrived) a.recv[idx] += arrived;
+      }
+      rec_store<W>(a.buf, idx, r);
+      if (a.obs) rec_emit<W>(r, P->deadline[k], a.obs + (size_t)P->obs_off[k] * B + b, B);
+      if (a.state) rec_emit<W>(r, P->deadline[k], a.state + (size_t)P->sbuf_off[k] * B + b, B);
+    }
+    uint32_t sw;                                                 // :104-107 C+1 scalar draws
+    if (a.rng_mode == D2D_RNG_REPLAY) {
+      sw = rp_sw[b];
+    } else {
+      sw = philox_lane_mask(env, a.t, kEnvLevelDevice | (kPurposeSwitch << 16), C1, a.k0, a.k1,
+                            [swthr](int c) { return swthr[c]; });
+    }
+    const uint32_t ch_new = (ch ^ sw) & cmask;
+    chan[b] = ch_new;
+    // ack/nack vector (:129-137): 0 unused, -1 bad channel, 1/count good channel
+    for (int c = 0; c < C1; ++c) {
+      int cnt = 0;
+#pragma unroll
+      for (int j = 0; j < kCountPlanes; ++j) cnt |= (int)((plane[j] >> c) & 1u) << j;
+      const float v = cnt == 0 ? 0.0f : (((ch >> c) & 1u) ? P->inv_count[cnt] : -1.0f);
+      if (a.obs)
+        for (int k = 0; k < N; ++k) a.obs[((size_t)P->obs_off[k] + P->deadline[k] + c) * B + b] = v;   // :181-184
+      if (a.ack) reinterpret_cast<float*>(a.ack)[(size_t)c * B + b] = v;
+      if (a.state) a.state[((size_t)P->sum_dl + c) * B + b] = (float)((ch_new >> c) & 1u);             // :186
+    }
+    a.reward[b] = n_success;                                     // :188
+    if (a.done) a.done[b] = (uint8_t)a.done_flag;
+  }
+}
+
+template <int W>
+__global__ void __launch_bounds__(256) sel_reset_kernel(const StepArgs a) {
+  extern __shared__ __align__(16) uint8_t smem[];
+  const EnvParamsHdr* P = stage_params(a, smem);
+  const uint32_t* cdf = reinterpret_cast<const uint32_t*>(smem + P->off_cdf);
+  const int N = P->N, C1 = P->C + 1;
+  const size_t B = (size_t)a.B;
+  uint32_t* chan = reinterpret_cast<uint32_t*>(a.chan);
+  const uint32_t cmask = C1 >= 32 ? 0xFFFFFFFFu : ((1u << C1) - 1u);
+  for (int b = blockIdx.x * blockDim.x + threadIdx.x; b < a.B; b += gridDim.x * blockDim.x) {
+    for (int k = 0; k < N; ++k) {
+      const size_t idx = (size_t)k * B + b;
+      Rec<W> r;
+#pragma unroll
+      for (int j = 0; j < W; ++j) r.w[j] = 0;
+      uint32_t arrived = 0;
+      if ((a.active >> k) & 1ull) {
+        arrived = draw_arrival(a, P, cdf, k, b);
+        rec_set_byte<W>(r, P->deadline[k] - 1, arrived);
+      }
+      rec_store<W>(a.buf, idx, r);
+      a.disc[idx] = 0;
+      a.recv[idx] = arrived;
+      if (a.obs) {                        // channel_selection_env.py:90-94 (ack/nack slot is zeros)
+        float* o = a.obs + (size_t)P->obs_off[k] * B + b;
+        rec_emit<W>(r, P->deadline[k], o, B);
+        o += (size_t)P->deadline[k] * B;
+        for (int c = 0; c < C1; ++c) o[(size_t)c * B] = 0.0f;
+      }
+      if (a.state) rec_emit<W>(r, P->deadline[k], a.state + (size_t)P->sbuf_off[k] * B + b, B);
+    }
+    chan[b] = cmask;                      // :76
+    a.stats[b] = 0;
+    a.stats[B + b] = 0;
+    if (a.state)
+      for (int c = 0; c < C1; ++c) a.state[((size_t)P->sum_dl + c) * B + b] = 1.0f;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// small utilities
+// ------------------------------------------------------------------------------------------------
+// u8 [B][N][C] 0/1 -> bitmask [N][B]
+template <typename MaskT>
+__global__ void pack_actions_kernel(const uint8_t* __restrict__ src, MaskT* __restrict__ dst, int B, int N, int C) {
+  const long long total = (long long)B * N;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int k = (int)(i / B), b = (int)(i % B);
+    const uint8_t* s = src + ((size_t)b * N + k) * C;
+    uint32_t m = 0;
+    for (int c = 0; c < C; ++c) m |= (uint32_t)(s[c] != 0) << c;
+    dst[i] = (MaskT)m;
+  }
+}
+
+// per-env URLLC score, Jain index, channel score (combinatorial_env.py:245-264), in float64 like numpy
+__global__ void scores_kernel(const uint32_t* __restrict__ disc, const uint32_t* __restrict__ recv,
+                              const uint32_t* __restrict__ stats, int kind, int B, int N, double* urllc,
+                              double* jains, double* chscore) {
+  for (int b = blockIdx.x * blockDim.x + threadIdx.x; b < B; b += gridDim.x * blockDim.x) {
+    double sd = 0, sr = 0, s1 = 0, s2 = 0;
+    for (int k = 0; k < N; ++k) {
+      const double d = disc[(size_t)k * B + b], r = recv[(size_t)k * B + b];
+      sd += d, sr += r;
+      const double u = r > 0 ? 1.0 - d / r : 1.0;
+      s1 += u, s2 += u * u;
+    }
+    if (urllc) urllc[b] = 1.0 - sd / sr;
+    if (jains) jains[b] = s1 * s1 / N / s2;
+    if (chscore) {
+      double v = 1.0;
+      if (kind == D2D_ENV_CHANNEL_SELECTION && stats[(size_t)B + b] != 0)
+        v = (double)stats[b] / (double)stats[(size_t)B + b];
+      chscore[b] = v;
+    }
+  }
+}
+
+}  // namespace d2d
+
+// ================================================================================================
+// C ABI
+// ================================================================================================
+using namespace d2d;
+
+struct d2d_env {
+  int kind, B, N, C, T, homog, rng_mode;
+  uint64_t seed, env_offset;
+  int D, W, CB;  // max deadline, words per record, bytes per channel mask element
+  int t;
+  bool is_reset;
+  std::vector<int> deadlines, obs_off, obs_dim;
+  std::vector<uint64_t> active;
+  int obs_rows, state_rows, sum_dl;
+  uint32_t* buf = nullptr;
+  void* chan = nullptr;
+  uint32_t* disc = nullptr;
+  uint32_t* recv = nullptr;
+  uint32_t* stats = nullptr;
+  uint8_t* params = nullptr;
+  int params_bytes = 0;
+  const uint8_t* rp_arr = nullptr;
+  const void* rp_sw = nullptr;
+  int rp_len = 0;
+  size_t chan_elems() const { return kind == D2D_ENV_CHANNEL_SELECTION ? (size_t)B : (size_t)N * B; }
+};
+
+static int env_free(d2d_env* e) {
+  if (!e) return D2D_OK;
+  cudaFree(e->buf), cudaFree(e->chan), cudaFree(e->disc), cudaFree(e->recv), cudaFree(e->stats), cudaFree(e->params);
+  delete e;
+  return D2D_OK;
+}
+
+extern "C" int d2d_env_create(const d2d_env_config* cfg, d2d_env** out) {
+  D2D_REQUIRE(cfg && out, "d2d_env_create: null argument");
+  *out = nullptr;
+  D2D_REQUIRE(cfg->kind >= 0 && cfg->kind <= 2, "d2d_env_create: unknown env kind %d", cfg->kind);
+  D2D_REQUIRE(cfg->n_envs > 0, "d2d_env_create: n_envs must be positive");
+  D2D_REQUIRE(cfg->n_agents > 0 && cfg->n_agents <= D2D_MAX_AGENTS, "d2d_env_create: n_agents %d not in 1..%d",
+              cfg->n_agents, D2D_MAX_AGENTS);
+  const int maxC = cfg->kind == D2D_ENV_CHANNEL_SELECTION ? D2D_MAX_CHANNELS - 1 : D2D_MAX_CHANNELS;
+  D2D_REQUIRE(cfg->n_channels > 0 && cfg->n_channels <= maxC, "d2d_env_create: n_channels %d not in 1..%d",
+              cfg->n_channels, maxC);
+  D2D_REQUIRE(cfg->kind != D2D_ENV_SINGLE_CHANNEL || cfg->n_channels == 1,
+              "d2d_env_create: the single-channel env has n_channels = 1");
+  D2D_REQUIRE(cfg->episode_length > 0, "d2d_env_create: episode_length must be positive");
+  D2D_REQUIRE(cfg->rng_mode == D2D_RNG_PHILOX || cfg->rng_mode == D2D_RNG_REPLAY, "d2d_env_create: bad rng_mode");
+  D2D_REQUIRE(cfg->deadlines && cfg->arrival_kind && cfg->arrival_active && cfg->poisson_cdf && cfg->bernoulli_thr &&
+                  cfg->switch_thr,
+              "d2d_env_create: null table pointer");
+  D2D_REQUIRE((uint64_t)cfg->n_envs + cfg->env_offset <= 0xFFFFFFFFull, "d2d_env_create: env index exceeds 32 bits");
+
+  d2d_env* e = new (std::nothrow) d2d_env();
+  D2D_REQUIRE(e, "d2d_env_create: out of host memory");
+  e->kind = cfg->kind, e->B = cfg->n_envs, e->N = cfg->n_agents, e->C = cfg->n_channels, e->T = cfg->episode_length;
+  e->homog = cfg->homogeneous_size != 0, e->rng_mode = cfg->rng_mode, e->seed = cfg->seed;
+  e->env_offset = cfg->env_offset, e->t = 0, e->is_reset = false;
+  const int N = e->N, C = e->C;
+  e->D = 0, e->sum_dl = 0;
+  for (int k = 0; k < N; ++k) {
+    const int dl = cfg->deadlines[k];
+    if (dl < 1 || dl > D2D_MAX_DEADLINE) {
+      set_error("d2d_env_create: deadline[%d] = %d not in 1..%d", k, dl, D2D_MAX_DEADLINE);
+      env_free(e);
+      return D2D_ERR_INVALID;
+    }
+    e->deadlines.push_back(dl);
+    e->D = std::max(e->D, dl);
+    e->sum_dl += dl;
+  }
+  e->W = e->D <= 8 ? 2 : (e->D <= 16 ? 4 : 8);
+  e->CB = C <= 8 ? 1 : (C <= 16 ? 2 : 4);
+  if (e->kind == D2D_ENV_SINGLE_CHANNEL) e->CB = 1;
+  if (e->kind == D2D_ENV_CHANNEL_SELECTION) e->CB = 4;
+  e->active.assign(cfg->arrival_active, cfg->arrival_active + e->T + 1);
+
+  // ---- parameter blob ----
+  std::vector<int> nbr_off(N + 1, 0);
+  std::vector<uint8_t> nbr_idx;
+  if (e->kind == D2D_ENV_SINGLE_CHANNEL) {
+    for (int k = 0; k < N; ++k) {
+      if (cfg->nbr_offset && cfg->nbr_index) {
+        for (int j = cfg->nbr_offset[k]; j < cfg->nbr_offset[k + 1]; ++j) {
+          const int i = cfg->nbr_index[j];
+          if (i < 0 || i >= N) {
+            set_error("d2d_env_create: neighbour index %d out of range", i);
+            env_free(e);
+            return D2D_ERR_INVALID;
+          }
+          nbr_idx.push_back((uint8_t)i);
+        }
+      } else {
+        nbr_idx.push_back((uint8_t)k);
+      }
+      nbr_off[k + 1] = (int)nbr_idx.size();
+    }
+  }
+  const int n_sw = e->kind == D2D_ENV_COMBINATORIAL ? N * C : (e->kind == D2D_ENV_SINGLE_CHANNEL ? N : C + 1);
+  auto align16 = [](int x) { return (x + 15) & ~15; };
+  EnvParamsHdr h;
+  memset(&h, 0, sizeof(h));
+  h.N = N, h.C = C, h.D = e->D, h.T = e->T, h.homog = e->homog, h.kind = e->kind, h.sum_dl = e->sum_dl;
+  h.off_cdf = align16((int)sizeof(EnvParamsHdr));
+  h.off_sw = h.off_cdf + align16(N * D2D_POISSON_KMAX * 4);
+  h.off_nbr_off = h.off_sw + align16(n_sw * 4);
+  h.off_nbr_idx = h.off_nbr_off + align16((N + 1) * 4);
+  h.total_bytes = h.off_nbr_idx + align16((int)nbr_idx.size() + 1);
+  int row = 0, srow = 0;
+  for (int k = 0; k < N; ++k) {
+    int dim;
+    if (e->kind == D2D_ENV_COMBINATORIAL) {
+      dim = (e->homog ? e->D : e->deadlines[k]) + 2 * C;                 // combinatorial_env.py:47-53
+    } else if (e->kind == D2D_ENV_SINGLE_CHANNEL) {
+      dim = 1;                                                           // env.py:43-44
+      for (int j = nbr_off[k]; j < nbr_off[k + 1]; ++j) dim += e->deadlines[nbr_idx[j]] + 1;
+    } else {
+      dim = e->deadlines[k] + C + 1;                                     // channel_selection_env.py:41-42
+    }
+    e->obs_off.push_back(row), e->obs_dim.push_back(dim);
+    h.deadline[k] = (uint8_t)e->deadlines[k];
+    h.arrival_kind[k] = (uint8_t)cfg->arrival_kind[k];
+    h.obs_off[k] = (uint16_t)row, h.obs_dim[k] = (uint16_t)dim, h.sbuf_off[k] = (uint16_t)srow;
+    h.bern_thr[k] = cfg->bernoulli_thr[k];
+    row += dim, srow += e->deadlines[k];
+  }
+  for (int n = 1; n <= D2D_MAX_AGENTS; ++n) h.inv_count[n] = (float)(1.0 / (double)n);
+  e->obs_rows = row;
+  e->state_rows = e->kind == D2D_ENV_COMBINATORIAL ? e->sum_dl + C * (N + 1)       // combinatorial_env.py:57-58
+                  : e->kind == D2D_ENV_SINGLE_CHANNEL ? e->sum_dl + N + 1          // env.py:47-48
+                                                      : e->sum_dl + C + 1;         // channel_selection_env.py:45-46
+  h.obs_rows = e->obs_rows, h.state_rows = e->state_rows;
+  std::vector<uint8_t> blob(h.total_bytes, 0);
+  memcpy(blob.data(), &h, sizeof(h));
+  memcpy(blob.data() + h.off_cdf, cfg->poisson_cdf, (size_t)N * D2D_POISSON_KMAX * 4);
+  memcpy(blob.data() + h.off_sw, cfg->switch_thr, (size_t)n_sw * 4);
+  memcpy(blob.data() + h.off_nbr_off, nbr_off.data(), (size_t)(N + 1) * 4);
+  if (!nbr_idx.empty()) memcpy(blob.data() + h.off_nbr_idx, nbr_idx.data(), nbr_idx.size());
+  e->params_bytes = h.total_bytes;
+
+  const size_t nb = (size_t)N * e->B;
+  cudaError_t err = cudaSuccess;
+  auto alloc = [&](void** p, size_t bytes) {
+    if (err == cudaSuccess) err = cudaMalloc(p, bytes);
+    if (err == cudaSuccess) err = cudaMemset(*p, 0, bytes);
+  };
+  alloc((void**)&e->buf, nb * e->W * 4);
+  alloc(&e->chan, e->chan_elems() * e->CB);
+  alloc((void**)&e->disc, nb * 4);
+  alloc((void**)&e->recv, nb * 4);
+  alloc((void**)&e->stats, (size_t)2 * e->B * 4);
+  alloc((void**)&e->params, blob.size());
+  if (err == cudaSuccess) err = cudaMemcpy(e->params, blob.data(), blob.size(), cudaMemcpyHostToDevice);
+  if (err != cudaSuccess) {
+    set_error("d2d_env_create: CUDA allocation failed: %s", cudaGetErrorString(err));
+    env_free(e);
+    return D2D_ERR_CUDA;
+  }
+  *out = e;
+  return D2D_OK;
+}
+
+extern "C" int d2d_env_destroy(d2d_env* env) { return env_free(env); }
+extern "C" int d2d_env_obs_rows(const d2d_env* e) { return e ? e->obs_rows : D2D_ERR_INVALID; }
+extern "C" int d2d_env_obs_offset(const d2d_env* e, int k) {
+  return (e && k >= 0 && k < e->N) ? e->obs_off[k] : D2D_ERR_INVALID;
+}
+extern "C" int d2d_env_obs_dim(const d2d_env* e, int k) {
+  return (e && k >= 0 && k < e->N) ? e->obs_dim[k] : D2D_ERR_INVALID;
+}
+extern "C" int d2d_env_state_rows(const d2d_env* e) { return e ? e->state_rows : D2D_ERR_INVALID; }
+extern "C" int d2d_env_timestep(const d2d_env* e) { return e ? e->t : D2D_ERR_INVALID; }
+extern "C" int d2d_env_record_bytes(const d2d_env* e) { return e ? e->W * 4 : D2D_ERR_INVALID; }
+extern "C" int d2d_env_mask_bytes(const d2d_env* e) { return e ? e->CB : D2D_ERR_INVALID; }
+
+extern "C" int d2d_env_set_replay(d2d_env* e, const uint8_t* arrivals, const void* switches, int t_len) {
+  D2D_REQUIRE(e, "d2d_env_set_replay: null env");
+  D2D_REQUIRE(e->rng_mode == D2D_RNG_REPLAY, "d2d_env_set_replay: env was not created with D2D_RNG_REPLAY");
+  D2D_REQUIRE(arrivals && switches && t_len >= 1, "d2d_env_set_replay: null stream or empty length");
+  e->rp_arr = arrivals, e->rp_sw = switches, e->rp_len = t_len;
+  return D2D_OK;
+}
+
+static int fill_args(d2d_env* e, StepArgs& a, uint32_t t, const char* who) {
+  memset(&a, 0, sizeof(a));
+  a.buf = e->buf, a.chan = e->chan, a.disc = e->disc, a.recv = e->recv, a.stats = e->stats;
+  a.params = e->params, a.params_bytes = e->params_bytes;
+  a.B = e->B, a.t = t, a.k0 = (uint32_t)(e->seed & 0xFFFFFFFFull), a.k1 = (uint32_t)(e->seed >> 32);
+  a.env_offset = (uint32_t)e->env_offset, a.active = e->active[t], a.rng_mode = e->rng_mode;
+  a.done_flag = (int)t >= e->T;
+  if (e->rng_mode == D2D_RNG_REPLAY) {
+    D2D_REQUIRE(e->rp_arr && (int)t < e->rp_len, "%s: replay streams missing or shorter than timestep %u", who, t);
+    const size_t nb = (size_t)e->N * e->B;
+    a.rp_arr = e->rp_arr + (size_t)t * nb;
+    a.rp_sw = reinterpret_cast<const uint8_t*>(e->rp_sw) + (size_t)t * e->chan_elems() * e->CB;
+  }
+  return D2D_OK;
+}
+
+template <typename K>
+static int launch_env(K kernel, const StepArgs& a, int params_bytes, void* stream) {
+  const int block = 256;
+  kernel<<<grid_for(a.B, block), block, params_bytes, as_stream(stream)>>>(a);
+  D2D_LAUNCHED();
+  return D2D_OK;
+}
+
+extern "C" int d2d_env_reset(d2d_env* e, float* obs, float* state, void* stream) {
+  D2D_REQUIRE(e, "d2d_env_reset: null env");
+  StepArgs a;
+  int rc = fill_args(e, a, 0u, "d2d_env_reset");
+  if (rc) return rc;
+  a.obs = obs, a.state = state;
+  if (e->kind == D2D_ENV_COMBINATORIAL) {
+#define D2D_RESET_CASE(WW, MT) rc = launch_env(comb_reset_kernel<WW, MT>, a, e->params_bytes, stream)
+    if (e->W == 2 && e->CB == 1) D2D_RESET_CASE(2, uint8_t);
+    else if (e->W == 2 && e->CB == 2) D2D_RESET_CASE(2, uint16_t);
+    else if (e->W == 2) D2D_RESET_CASE(2, uint32_t);
+    else if (e->W == 4 && e->CB == 1) D2D_RESET_CASE(4, uint8_t);
+    else if (e->W == 4 && e->CB == 2) D2D_RESET_CASE(4, uint16_t);
+    else if (e->W == 4) D2D_RESET_CASE(4, uint32_t);
+    else if (e->CB == 1) D2D_RESET_CASE(8, uint8_t);
+    else if (e->CB == 2) D2D_RESET_CASE(8, uint16_t);
+    else D2D_RESET_CASE(8, uint32_t);
+#undef D2D_RESET_CASE
+  } else if (e->kind == D2D_ENV_SINGLE_CHANNEL) {
+    rc = e->W == 2 ? launch_env(sc_reset_kernel<2>, a, e->params_bytes, stream)
+         : e->W == 4 ? launch_env(sc_reset_kernel<4>, a, e->params_bytes, stream)
+                     : launch_env(sc_reset_kernel<8>, a, e->params_bytes, stream);
+  } else {
+    rc = e->W == 2 ? launch_env(sel_reset_kernel<2>, a, e->params_bytes, stream)
+         : e->W == 4 ? launch_env(sel_reset_kernel<4>, a, e->params_bytes, stream)
+                     : launch_env(sel_reset_kernel<8>, a, e->params_bytes, stream);
+  }
+  if (rc) return rc;
+  e->t = 0, e->is_reset = true;
+  return D2D_OK;
+}
+
+static int env_step_impl(d2d_env* e, StepArgs& a, void* stream) {
+  int rc;
+  if (e->kind == D2D_ENV_COMBINATORIAL) {
+#define D2D_STEP_CASE(WW, MT)                                                               \
+  rc = (e->N == 6) ? launch_env(comb_step_kernel<WW, MT, 6>, a, e->params_bytes, stream)    \
+                   : launch_env(comb_step_kernel<WW, MT, 0>, a, e->params_bytes, stream)
+    if (e->W == 2 && e->CB == 1) D2D_STEP_CASE(2, uint8_t);
+    else if (e->W == 2 && e->CB == 2) D2D_STEP_CASE(2, uint16_t);
+    else if (e->W == 2) D2D_STEP_CASE(2, uint32_t);
+    else if (e->W == 4 && e->CB == 1) D2D_STEP_CASE(4, uint8_t);
+    else if (e->W == 4 && e->CB == 2) D2D_STEP_CASE(4, uint16_t);
+    else if (e->W == 4) D2D_STEP_CASE(4, uint32_t);
+    else if (e->CB == 1) D2D_STEP_CASE(8, uint8_t);
+    else if (e->CB == 2) D2D_STEP_CASE(8, uint16_t);
+    else D2D_STEP_CASE(8, uint32_t);
+#undef D2D_STEP_CASE
+  } else if (e->kind == D2D_ENV_SINGLE_CHANNEL) {
+    rc = e->W == 2 ? launch_env(sc_step_kernel<2>, a, e->params_bytes, stream)
+         : e->W == 4 ? launch_env(sc_step_kernel<4>, a, e->params_bytes, stream)
+                     : launch_env(sc_step_kernel<8>, a, e->params_bytes, stream);
+  } else {
+    rc = e->W == 2 ? launch_env(sel_step_kernel<2>, a, e->params_bytes, stream)
+         : e->W == 4 ? launch_env(sel_step_kernel<4>, a, e->params_bytes, stream)
+                     : launch_env(sel_step_kernel<8>, a, e->params_bytes, stream);
+  }
+  if (rc) return rc;
+  e->t += 1;
+  return D2D_OK;
+}
+
+extern "C" int d2d_env_step(d2d_env* e, const void* actions, float* obs, float* state, int32_t* reward,
+                            uint8_t* done, void* ack, void* stream) {
+  D2D_REQUIRE(e && actions && reward, "d2d_env_step: null env, actions or reward");
+  if (!e->is_reset) {
+    set_error("d2d_env_step: reset() has not been called");
+    return D2D_ERR_STATE;
+  }
+  if (e->t >= e->T) {
+    set_error("d2d_env_step: episode is over (timestep %d >= episode_length %d); call reset()", e->t, e->T);
+    return D2D_ERR_STATE;
+  }
+  StepArgs a;
+  int rc = fill_args(e, a, (uint32_t)(e->t + 1), "d2d_env_step");
+  if (rc) return rc;
+  a.actions = actions, a.obs = obs, a.state = state, a.reward = reward, a.done = done, a.ack = ack, a.act_mode = 0;
+  return env_step_impl(e, a, stream);
+}
+
+extern "C" int d2d_env_step_random_access(d2d_env* e, double tp, void* actions_out, float* obs, float* state,
+                                          int32_t* reward, uint8_t* done, void* ack, void* stream) {
+  D2D_REQUIRE(e && reward, "d2d_env_step_random_access: null env or reward");
+  D2D_REQUIRE(e->kind != D2D_ENV_CHANNEL_SELECTION,
+              "d2d_env_step_random_access: the reference defines no random-access policy for the selection env");
+  D2D_REQUIRE(tp >= 0.0 && tp <= 1.0, "d2d_env_step_random_access: transmission_prob must be in [0, 1]");
+  if (!e->is_reset) {
+    set_error("d2d_env_step_random_access: reset() has not been called");
+    return D2D_ERR_STATE;
+  }
+  if (e->t >= e->T) {
+    set_error("d2d_env_step_random_access: episode is over (timestep %d >= %d); call reset()", e->t, e->T);
+    return D2D_ERR_STATE;
+  }
+  StepArgs a;
+  int rc = fill_args(e, a, (uint32_t)(e->t + 1), "d2d_env_step_random_access");
+  if (rc) return rc;
+  a.actions_out = actions_out, a.obs = obs, a.state = state, a.reward = reward, a.done = done, a.ack = ack;
+  a.act_mode = 1;
+  a.tp_thr = (uint32_t)std::min(65536.0, std::max(0.0, std::floor(tp * 65536.0 + 0.5)));
+  return env_step_impl(e, a, stream);
+}
+
+extern "C" int d2d_pack_actions(const uint8_t* src, void* dst, int B, int N, int C, void* stream) {
+  D2D_REQUIRE(src && dst && B > 0 && N > 0 && C > 0 && C <= D2D_MAX_CHANNELS, "d2d_pack_actions: bad argument");
+  const int block = 256, grid = grid_for((long long)B * N, block);
+  if (C <= 8) pack_actions_kernel<uint8_t><<<grid, block, 0, as_stream(stream)>>>(src, (uint8_t*)dst, B, N, C);
+  else if (C <= 16) pack_actions_kernel<uint16_t><<<grid, block, 0, as_stream(stream)>>>(src, (uint16_t*)dst, B, N, C);
+  else pack_actions_kernel<uint32_t><<<grid, block, 0, as_stream(stream)>>>(src, (uint32_t*)dst, B, N, C);
+  D2D_LAUNCHED();
+  return D2D_OK;
+}
+
+extern "C" int d2d_env_export_state(const d2d_env* e, uint8_t* buffers, void* channel, uint32_t* discarded,
+                                    uint32_t* received, uint32_t* stats, void* stream) {
+  D2D_REQUIRE(e, "d2d_env_export_state: null env");
+  const size_t nb = (size_t)e->N * e->B;
+  cudaStream_t s = as_stream(stream);
+  if (buffers) D2D_CUDA(cudaMemcpyAsync(buffers, e->buf, nb * e->W * 4, cudaMemcpyDeviceToDevice, s));
+  if (channel) D2D_CUDA(cudaMemcpyAsync(channel, e->chan, e->chan_elems() * e->CB, cudaMemcpyDeviceToDevice, s));
+  if (discarded) D2D_CUDA(cudaMemcpyAsync(discarded, e->disc, nb * 4, cudaMemcpyDeviceToDevice, s));
+  if (received) D2D_CUDA(cudaMemcpyAsync(received, e->recv, nb * 4, cudaMemcpyDeviceToDevice, s));
+  if (stats) D2D_CUDA(cudaMemcpyAsync(stats, e->stats, (size_t)2 * e->B * 4, cudaMemcpyDeviceToDevice, s));
+  return D2D_OK;
+}
+
+extern "C" int d2d_env_import_state(d2d_env* e, const uint8_t* buffers, const void* channel,
+                                    const uint32_t* discarded, const uint32_t* received, const uint32_t* stats,
+                                    int timestep, void* stream) {
+  D2D_REQUIRE(e, "d2d_env_import_state: null env");
+  D2D_REQUIRE(timestep >= 0 && timestep <= e->T, "d2d_env_import_state: timestep out of range");
+  const size_t nb = (size_t)e->N * e->B;
+  cudaStream_t s = as_stream(stream);
+  if (buffers) D2D_CUDA(cudaMemcpyAsync(e->buf, buffers, nb * e->W * 4, cudaMemcpyDeviceToDevice, s));
+  if (channel) D2D_CUDA(cudaMemcpyAsync(e->chan, channel, e->chan_elems() * e->CB, cudaMemcpyDeviceToDevice, s));
+  if (discarded) D2D_CUDA(cudaMemcpyAsync(e->disc, discarded, nb * 4, cudaMemcpyDeviceToDevice, s));
+  if (received) D2D_CUDA(cudaMemcpyAsync(e->recv, received, nb * 4, cudaMemcpyDeviceToDevice, s));
+  if (stats) D2D_CUDA(cudaMemcpyAsync(e->stats, stats, (size_t)2 * e->B * 4, cudaMemcpyDeviceToDevice, s));
+  e->t = timestep, e->is_reset = true;
+  return D2D_OK;
+}
+
+extern "C" int d2d_env_scores(const d2d_env* e, double* urllc, double* jains, double* channel_score, void* stream) {
+  D2D_REQUIRE(e, "d2d_env_scores: null env");
+  const int block = 256;
+  scores_kernel<<<grid_for(e->B, block), block, 0, as_stream(stream)>>>(e->disc, e->recv, e->stats, e->kind, e->B,
+                                                                         e->N, urllc, jains, channel_score);
+  D2D_LAUNCHED();
+  return D2D_OK;
+}

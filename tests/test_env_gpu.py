@@ -1,0 +1,214 @@
+"""CUDA envs (through the C ABI) against the oracle and the reference's golden outputs -- bit exact."""
+import numpy as np
+import pytest
+
+from _helpers import cat_obs, env_case_names, load_env_case, make_cuda_env, make_oracle, to_np
+
+pytestmark = pytest.mark.gpu
+
+
+def _check_state(env, orc, kind, tag):
+    assert np.array_equal(to_np(env.current_buffers), orc.buffers), tag
+    assert np.array_equal(to_np(env.discarded_packets), orc.discarded), tag
+    assert np.array_equal(to_np(env.received_packets), orc.received), tag
+    assert np.array_equal(to_np(env.channel_state), orc.channel_state), tag
+
+
+def _rollout_against_oracle(env, orc, kind, actions, check_every=1):
+    T = actions.shape[0]
+    obs, state = env.reset()
+    o_obs, o_state = orc.reset()
+    assert np.array_equal(cat_obs(obs), cat_obs(o_obs))
+    assert np.array_equal(to_np(state), o_state)
+    _check_state(env, orc, kind, "reset")
+    for t in range(T):
+        obs, state, rew, done, _ = env.step(actions[t])
+        o_obs, o_state, o_rew, o_done, _ = orc.step(actions[t])
+        assert np.array_equal(cat_obs(obs), cat_obs(o_obs)), ("obs", t)
+        assert np.array_equal(to_np(state), o_state), ("state", t)
+        assert np.array_equal(to_np(rew).astype(np.float64), o_rew.astype(np.float64)), ("reward", t)
+        assert done == o_done
+        assert np.array_equal(to_np(env.done_tensor), np.full(env.n_envs, int(o_done), dtype=np.uint8))
+        if t % check_every == 0 or t == T - 1:
+            _check_state(env, orc, kind, t)
+    assert np.allclose(to_np(env.compute_urllc()), orc.compute_urllc(), rtol=0, atol=1e-15, equal_nan=True)
+    assert np.allclose(to_np(env.compute_jains()), orc.compute_jains(), rtol=1e-14, equal_nan=True)
+
+
+@pytest.mark.parametrize("name", env_case_names())
+def test_cuda_env_matches_reference_golden(name, cuda_device):
+    import torch
+    g = load_env_case(name)
+    kind, kw = g["kind"], g["config"]
+    T, B = g["actions"].shape[:2]
+    env = make_cuda_env(kind, kw, B, rng="replay", device=cuda_device)
+    env.set_replay(g["arrivals"], g["switches"])
+    obs, state = env.reset()
+    assert np.array_equal(cat_obs(obs), g["obs0"])
+    assert np.array_equal(to_np(state), g["state0"])
+    assert np.array_equal(to_np(env.current_buffers), g["buffers0"])
+    for t in range(T):
+        obs, state, rew, done, _ = env.step(torch.as_tensor(g["actions"][t]))
+        assert np.array_equal(cat_obs(obs), g["obs"][t]), (name, t)
+        assert np.array_equal(to_np(state), g["state"][t]), (name, t)
+        assert np.array_equal(to_np(rew).astype(np.float32), g["rewards"][t]), (name, t)
+        assert done == bool(g["done"][t])
+        assert np.array_equal(to_np(env.current_buffers), g["buffers"][t])
+        assert np.array_equal(to_np(env.discarded_packets), g["discarded"][t])
+        assert np.array_equal(to_np(env.received_packets), g["received"][t])
+        assert np.array_equal(to_np(env.channel_state), g["channel"][t])
+    assert np.allclose(to_np(env.compute_urllc()), g["urllc"], rtol=0, atol=1e-15)
+    assert np.allclose(to_np(env.compute_jains()), g["jains"], rtol=1e-14)
+    if kind == "d2d":
+        assert np.array_equal(to_np(env.channel_errors), g["channel_errors"])
+        assert np.array_equal(to_np(env.n_collisions), g["n_collisions"])
+    if kind == "channel_selection":
+        assert np.allclose(to_np(env.compute_channel_score()), g["channel_score"], rtol=1e-15)
+
+
+def test_survey_known_answer_step_cuda(cuda_device):
+    g = load_env_case("kat_survey4")
+    env = make_cuda_env("combinatorial", g["config"], 1, rng="replay", device=cuda_device)
+    env.set_replay(g["arrivals"], g["switches"])
+    env.reset()
+    masks = (g["forced_channel"].astype(np.int64) * (1 << np.arange(3))).sum(1)[:, None]   # [N, B=1]
+    env.import_state(channel_masks=masks)
+    obs, state, rew, done, _ = env.step(g["actions"][0])
+    assert to_np(env.last_ack)[:, 0].tolist() == [-1, 1, -1]
+    assert to_np(rew)[0].tolist() == [1, 1, 1, 1]
+    assert to_np(env.current_buffers)[0].tolist() == [[0, 2, 0], [0, 0, 1], [0, 0, 0], [0, 1, 0]]
+    assert np.array_equal(cat_obs(obs)[0], g["obs"]) and np.array_equal(to_np(state)[0], g["state"])
+    assert to_np(env.received_packets)[0].tolist() == [2, 2, 0, 1]
+    assert np.array_equal(to_np(env.channel_state)[0], g["channel"])
+
+
+@pytest.mark.parametrize("name,B,T", [("comb_c3_load0.33", 1000, 200), ("comb_c1_16ch", 333, 60),
+                                      ("comb_c4_n12_aperiodic", 257, 50), ("comb_deadline20_c20", 65, 45),
+                                      ("d2d_c2", 4096, 200), ("d2d_neighbourhoods", 100, 50),
+                                      ("sel_xp_gamma", 500, 50), ("sel_heterogeneous", 129, 40)])
+def test_cuda_env_matches_oracle_replay_large(name, B, T, cuda_device):
+    from oracle.envs_np import ReplaySource
+    from oracle.gen_golden import draw_actions, draw_streams
+    g = load_env_case(name)
+    kind, kw = g["kind"], dict(g["config"])
+    kw["episode_length"] = T
+    rng = np.random.default_rng(abs(hash(name)) % 1000)
+    arr, sw = draw_streams(kind, kw, B, T, rng)
+    act = draw_actions(kind, kw, B, T, 0.3, rng)
+    env = make_cuda_env(kind, kw, B, rng="replay", device=cuda_device)
+    env.set_replay(arr, sw)
+    orc = make_oracle(kind, kw, B, ReplaySource(arr, sw))
+    _rollout_against_oracle(env, orc, kind, act, check_every=7)
+
+
+@pytest.mark.parametrize("name,offset", [("comb_c3_load0.33", 0), ("comb_c1_16ch", 12345), ("comb_c4_n12_aperiodic", 7),
+                                         ("comb_periodic_offsets", 0), ("comb_deadline20_c20", 3), ("d2d_c2", 99),
+                                         ("sel_xp_gamma", 5), ("sel_heterogeneous", 0)])
+def test_cuda_philox_mode_matches_oracle(name, offset, cuda_device):
+    """Throughput-mode streams: device Philox == numpy Philox restatement, env state bit exact."""
+    from oracle.envs_np import PhiloxSource
+    from oracle.gen_golden import draw_actions
+    g = load_env_case(name)
+    kind, kw = g["kind"], g["config"]
+    B, T = 300, kw["episode_length"]
+    act = draw_actions(kind, kw, B, T, 0.3, np.random.default_rng(3))
+    env = make_cuda_env(kind, kw, B, rng="philox", seed=0x1234567890ABCDEF, env_offset=offset, device=cuda_device)
+    orc = make_oracle(kind, kw, B, PhiloxSource(B, 0x1234567890ABCDEF, env_offset=offset,
+                                                env_level_switch=(kind == "channel_selection")))
+    _rollout_against_oracle(env, orc, kind, act, check_every=5)
+
+
+def test_fused_random_access_policy(cuda_device):
+    """step_random_access == oracle step fed with the Philox policy-stream action bits."""
+    from oracle import philox_np as px
+    from oracle.envs_np import PhiloxSource
+    g = load_env_case("comb_c3_load0.33")
+    kw = g["config"]
+    B, T, seed, tp = 500, kw["episode_length"], 77, 0.3
+    env = make_cuda_env("combinatorial", kw, B, rng="philox", seed=seed, device=cuda_device)
+    orc = make_oracle("combinatorial", kw, B, PhiloxSource(B, seed))
+    env.reset(), orc.reset()
+    envs = np.arange(B)
+    for t in range(1, T + 1):
+        obs, state, rew, done, _, acts = env.step_random_access(tp, return_actions=True)
+        a = np.stack([px.lanes16(seed, envs, t, k, px.PURPOSE_POLICY, 8) < px.thr16(tp) for k in range(6)], axis=1)
+        packed = (a.astype(np.int64) * (1 << np.arange(8))).sum(-1)            # [B, N]
+        assert np.array_equal(to_np(acts).astype(np.uint8).T, packed.astype(np.uint8))
+        o_obs, o_state, o_rew, o_done, _ = orc.step(a)
+        assert np.array_equal(cat_obs(obs), cat_obs(o_obs)) and np.array_equal(to_np(state), o_state)
+        assert np.array_equal(to_np(rew), o_rew)
+    assert np.array_equal(to_np(env.received_packets), orc.received)
+    assert np.array_equal(to_np(env.discarded_packets), orc.discarded)
+
+
+def test_reference_compatible_single_env_mode(cuda_device):
+    """n_envs=None: host numpy outputs with the reference's shapes and dtypes."""
+    g = load_env_case("comb_c3_load1_ragged_obs")
+    kw = g["config"]
+    env = make_cuda_env("combinatorial", kw, None, rng="replay", device=cuda_device)
+    env.set_replay(g["arrivals"][:, :1], g["switches"][:, :1])
+    obs, state = env.reset()
+    assert isinstance(obs, list) and len(obs) == 6 and obs[0].dtype == np.float64 and obs[0].shape == (7 + 16,)
+    assert isinstance(state, list) and len(state) == 3
+    assert np.array_equal(np.concatenate(obs).astype(np.float32), g["obs0"][0])
+    for t in range(5):
+        obs, state, rew, done, info = env.step(g["actions"][t, 0].astype(np.float64))
+        assert np.array_equal(np.concatenate(obs).astype(np.float32), g["obs"][t, 0])
+        assert np.array_equal(np.concatenate(state).astype(np.float32), g["state"][t, 0])
+        assert rew.shape == (6,) and np.array_equal(rew.astype(np.float32), g["rewards"][t, 0])
+        assert done is False and info == {}
+    assert env.current_buffers.shape == (6, 14) and env.discarded_packets.shape == (6,)
+    assert isinstance(env.compute_urllc(), float)
+    assert env.observation_space[1].shape == (14 + 16,) and env.action_space[0].n == 8
+    assert env.state_space.shape == (63 + 8 * 7,)
+
+
+def test_error_behaviour(cuda_device):
+    from d2d_ppo_b200._lib import D2DError
+    g = load_env_case("comb_periodic_offsets")
+    kw = dict(g["config"])
+    kw["episode_length"] = 3
+    env = make_cuda_env("combinatorial", kw, 4, device=cuda_device)
+    a = np.zeros((4, 4, 3), dtype=np.uint8)
+    with pytest.raises(D2DError):
+        env.step(a)                       # step before reset
+    env.reset()
+    for _ in range(3):
+        _, _, _, done, _ = env.step(a)
+    assert done is True
+    with pytest.raises(D2DError):
+        env.step(a)                       # the reference has no auto-reset either; stepping past T is an error
+    env.reset()
+    env.step(a)
+    replay = make_cuda_env("combinatorial", kw, 4, rng="replay", device=cuda_device)
+    with pytest.raises(D2DError):
+        replay.reset()                    # replay mode without streams
+    with pytest.raises(ValueError):
+        make_cuda_env("combinatorial", dict(kw, traffic_model="bursty"), 4, device=cuda_device)
+
+
+def test_full_size_conservation_and_determinism(cuda_device):
+    """BASELINE config c3/c5 shape at 1M envs: packet conservation, a checksum of checksums, determinism."""
+    import torch
+    from d2d_ppo_b200.presets import combinatorial_kwargs
+    B, T = 1 << 20, 40
+    kw = combinatorial_kwargs("setup_8_channels", load=2 / 3, episode_length=T)
+    sums = []
+    for rep in range(2):
+        env = make_cuda_env("combinatorial", kw, B, seed=2024, device=cuda_device)
+        env.reset()
+        delivered = torch.zeros(B, dtype=torch.int64, device=cuda_device)
+        for t in range(T):
+            _, _, rew, done, _ = env.step_random_access(0.2, with_state=False)
+            delivered += rew[:, 0]
+        assert done
+        recv = env.received_packets.to(torch.int64).sum(1)
+        disc = env.discarded_packets.to(torch.int64).sum(1)
+        held = env.current_buffers.to(torch.int64).sum((1, 2))
+        assert torch.equal(recv, delivered + disc + held)          # every packet is delivered, dropped or queued
+        assert int(delivered.sum()) > 0 and int(disc.sum()) > 0
+        sums.append((int(recv.sum()), int(disc.sum()), int(delivered.sum()),
+                     int((env.current_buffers.to(torch.int64) * 31).sum())))
+        u = env.compute_urllc()
+        assert float(u.min()) >= 0.0 and float(u.max()) <= 1.0
+    assert sums[0] == sums[1]
