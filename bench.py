@@ -41,7 +41,7 @@ FALLBACK_HBM = 6650.0
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=400)
+    ap.add_argument("--steps", type=int, default=4000)
     ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
     ap.add_argument("--envs", type=int, default=1 << 20, help="lockstep envs per GPU")
@@ -54,6 +54,10 @@ def parse():
 # clocks sampled DURING the timed region
 # ------------------------------------------------------------------------------------------------
 class ClockSampler:
+    """nvidia-smi polled every 100 ms.  It is started ~1 s BEFORE the timed region (during untimed spin-up steps
+    of the same kernel) because the tool needs several hundred ms to print its first row; only rows whose
+    wall-clock arrival falls inside [t_begin, t_end] (the timed region) are summarised when there are any,
+    otherwise the rows of the spin-up + timed window are used and `window` says so."""
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
@@ -73,16 +77,19 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([x.strip() for x in line.split(",")])
+            self.rows.append((time.perf_counter(), [x.strip() for x in line.split(",")]))
 
-    def stop(self):
+    def stop(self, t_begin=None, t_end=None):
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
         self.proc.terminate()
+        rows = [r for (t, r) in self.rows if t_begin is not None and t_begin <= t <= t_end + 0.05]
+        window = "timed region"
+        if not rows:
+            rows, window = [r for (_, r) in self.rows], "spin-up + timed region (timed region shorter than one sample)"
         sm, mx, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
+        for r in rows:
             try:
                 sm.append(float(r[0])), mx.append(float(r[1]))
             except (ValueError, IndexError):
@@ -92,7 +99,7 @@ class ClockSampler:
                     reasons.add(n)
         sm.sort()
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+                "reasons": sorted(reasons), "samples": len(sm), "window": window}
 
 
 # ------------------------------------------------------------------------------------------------
@@ -222,8 +229,14 @@ def run_native(args):
     sampler = ClockSampler(local)
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(K + 1)]
     launches0 = _lib.launch_count()
-    barrier()
     sampler.start()
+    t_spin = time.perf_counter()
+    while time.perf_counter() - t_spin < 1.2:      # untimed spin-up under the same load (see ClockSampler)
+        for _ in range(50):
+            step()
+        torch.cuda.synchronize()
+    barrier()
+    t_begin = time.perf_counter()
     ev[0].record()
     n_resets = 0
     for i in range(K):
@@ -232,7 +245,7 @@ def run_native(args):
         step()
         ev[i + 1].record()
     barrier()
-    clocks = sampler.stop()
+    clocks = sampler.stop(t_begin, time.perf_counter())
     launches = _lib.launch_count() - launches0
     total_ms = max_over_ranks(ev[0].elapsed_time(ev[K]))
     per = np.array([ev[i].elapsed_time(ev[i + 1]) for i in range(K)])

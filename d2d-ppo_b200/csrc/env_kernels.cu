@@ -23,288 +23,16 @@
 #include <new>
 #include <vector>
 
-#include "common.cuh"
-#include "philox.cuh"
+#include "env_common.cuh"
 
 namespace d2d {
 
-// ------------------------------------------------------------------------------------------------
-// parameter blob (device global -> shared memory at block start)
-// ------------------------------------------------------------------------------------------------
-struct EnvParamsHdr {
-  int32_t N, C, D, T, homog, kind, sum_dl, obs_rows, state_rows;
-  int32_t off_cdf, off_sw, off_nbr_off, off_nbr_idx, total_bytes;
-  uint8_t deadline[D2D_MAX_AGENTS];
-  uint8_t arrival_kind[D2D_MAX_AGENTS];
-  uint16_t obs_off[D2D_MAX_AGENTS];
-  uint16_t obs_dim[D2D_MAX_AGENTS];
-  uint16_t sbuf_off[D2D_MAX_AGENTS];  // first row of device k's buffer inside `state`
-  uint64_t bern_thr[D2D_MAX_AGENTS];
-  float inv_count[D2D_MAX_AGENTS + 1];  // (float)(1.0 / count) -- channel_selection_env.py:137
-};
-
-struct StepArgs {
-  uint32_t* buf;
-  void* chan;
-  uint32_t* disc;
-  uint32_t* recv;
-  uint32_t* stats;
-  const uint8_t* params;
-  int params_bytes;
-  const void* actions;
-  void* actions_out;
-  float* obs;
-  float* state;
-  int32_t* reward;
-  uint8_t* done;
-  void* ack;
-  const uint8_t* rp_arr;  // replay arrivals of this timestep, u8 [N][B]
-  const void* rp_sw;      // replay switch draws of this timestep
-  int B;
-  uint32_t t;  // timestep being produced (0 = reset)
-  uint32_t k0, k1;
-  uint32_t env_offset;
-  uint64_t active;  // bit k: device k draws an arrival at timestep t
-  int rng_mode;
-  int act_mode;  // 0 = actions from memory, 1 = fused random-access policy
-  uint32_t tp_thr;
-  int done_flag;
-};
-
-__device__ __forceinline__ const EnvParamsHdr* stage_params(const StepArgs& a, uint8_t* smem) {
-  const uint32_t* src = reinterpret_cast<const uint32_t*>(a.params);
-  uint32_t* dst = reinterpret_cast<uint32_t*>(smem);
-  for (int i = threadIdx.x; i < a.params_bytes / 4; i += blockDim.x) dst[i] = src[i];
-  __syncthreads();
-  return reinterpret_cast<const EnvParamsHdr*>(smem);
-}
-
-// ------------------------------------------------------------------------------------------------
-// packet-buffer records: W 32-bit words, byte d (little endian) = packets with d slots left
-// ------------------------------------------------------------------------------------------------
 template <int W>
-struct Rec {
-  uint32_t w[W];
-};
-
-template <int W>
-__device__ __forceinline__ Rec<W> rec_load(const uint32_t* base, size_t idx) {
-  Rec<W> r;
-  if constexpr (W == 2) {
-    const uint2 v = reinterpret_cast<const uint2*>(base)[idx];
-    r.w[0] = v.x, r.w[1] = v.y;
-  } else {
-#pragma unroll
-    for (int q = 0; q < W / 4; ++q) {
-      const uint4 v = reinterpret_cast<const uint4*>(base)[idx * (W / 4) + q];
-      r.w[4 * q] = v.x, r.w[4 * q + 1] = v.y, r.w[4 * q + 2] = v.z, r.w[4 * q + 3] = v.w;
-    }
-  }
-  return r;
-}
-
-template <int W>
-__device__ __forceinline__ void rec_store(uint32_t* base, size_t idx, const Rec<W>& r) {
-  if constexpr (W == 2) {
-    reinterpret_cast<uint2*>(base)[idx] = make_uint2(r.w[0], r.w[1]);
-  } else {
-#pragma unroll
-    for (int q = 0; q < W / 4; ++q)
-      reinterpret_cast<uint4*>(base)[idx * (W / 4) + q] =
-          make_uint4(r.w[4 * q], r.w[4 * q + 1], r.w[4 * q + 2], r.w[4 * q + 3]);
-  }
-}
-
-template <int W>
-__device__ __forceinline__ bool rec_any(const Rec<W>& r) {
-  uint32_t o = 0;
-#pragma unroll
-  for (int j = 0; j < W; ++j) o |= r.w[j];
-  return o != 0;
-}
-
-// remove one packet from the earliest non-empty slot (combinatorial_env.py:169-170)
-template <int W>
-__device__ __forceinline__ void rec_pop_earliest(Rec<W>& r, bool enable) {
-  bool done = !enable;
-#pragma unroll
-  for (int j = 0; j < W; ++j) {
-    const uint32_t w = r.w[j];
-    const bool hit = !done && w != 0;
-    const int pos = (__ffs((int)w) - 1) & 24;  // bit offset of the lowest non-zero byte
-    r.w[j] = hit ? w - (1u << pos) : w;
-    done |= hit;
-  }
-}
-
-// age by one slot (combinatorial_env.py:120-124); returns the expired count (old slot 0)
-template <int W>
-__device__ __forceinline__ uint32_t rec_age(Rec<W>& r) {
-  const uint32_t expired = r.w[0] & 0xFFu;
-#pragma unroll
-  for (int j = 0; j + 1 < W; ++j) r.w[j] = __funnelshift_r(r.w[j], r.w[j + 1], 8);
-  r.w[W - 1] >>= 8;
-  return expired;
-}
-
-template <int W>
-__device__ __forceinline__ void rec_set_byte(Rec<W>& r, int idx, uint32_t val) {
-  const int s = (idx & 3) * 8;
-#pragma unroll
-  for (int j = 0; j < W; ++j)
-    if (j == (idx >> 2)) r.w[j] = (r.w[j] & ~(0xFFu << s)) | (val << s);
-}
-
-template <int W>
-__device__ __forceinline__ uint32_t rec_sum(const Rec<W>& r) {
-  uint32_t s = 0;
-#pragma unroll
-  for (int j = 0; j < W; ++j) s += __vsadu4(r.w[j], 0u);
-  return s;
-}
-
-// write the first `n` slots of a record as f32 rows p[0], p[B], p[2B], ...
-template <int W>
-__device__ __forceinline__ void rec_emit(const Rec<W>& r, int n, float* p, size_t B) {
-#pragma unroll
-  for (int d = 0; d < 4 * W; ++d) {
-    if (d < n) {
-      *p = (float)((r.w[d >> 2] >> (8 * (d & 3))) & 0xFFu);
-      p += B;
-    }
-  }
-}
-
-// arrival of device k at timestep a.t (only called when the device is active)
-__device__ __forceinline__ uint32_t draw_arrival(const StepArgs& a, const EnvParamsHdr* P, const uint32_t* cdf, int k,
-                                                 int b) {
-  if (a.rng_mode == D2D_RNG_REPLAY) return a.rp_arr[(size_t)k * a.B + b];
-  const uint32_t u =
-      philox4x32_10(a.env_offset + (uint32_t)b, a.t, (uint32_t)k | (kPurposeArrival << 16), 0u, a.k0, a.k1).x;
-  if (P->arrival_kind[k] == D2D_ARRIVAL_BERNOULLI) return (uint64_t)u < P->bern_thr[k] ? 1u : 0u;
-  const uint32_t* c = cdf + k * D2D_POISSON_KMAX;
-  uint32_t n = 0;
-#pragma unroll 1
-  for (int m = 0; m < D2D_POISSON_KMAX; ++m) {
-    if (u < c[m]) break;  // thresholds are non-decreasing
-    ++n;
-  }
-  return n;
-}
+int launch_comb_step(const StepArgs& a, int N, int C, int mask_bytes, cudaStream_t s);  // env_comb_w{2,4,8}.cu
 
 // ================================================================================================
-// CombinatorialEnv
+// CombinatorialEnv reset (the step kernel lives in env_comb_step.cuh)
 // ================================================================================================
-template <int W, typename MaskT, int NFIX>
-__global__ void __launch_bounds__(256) comb_step_kernel(const StepArgs a) {
-  extern __shared__ __align__(16) uint8_t smem[];
-  const EnvParamsHdr* P = stage_params(a, smem);
-  const uint32_t* cdf = reinterpret_cast<const uint32_t*>(smem + P->off_cdf);
-  const uint32_t* swthr = reinterpret_cast<const uint32_t*>(smem + P->off_sw);
-  const int N = NFIX ? NFIX : P->N;
-  const int C = P->C;
-  const size_t B = (size_t)a.B;
-  constexpr int NMAX = NFIX ? NFIX : D2D_MAX_AGENTS;
-  MaskT* chan = reinterpret_cast<MaskT*>(a.chan);
-  const MaskT* act = reinterpret_cast<const MaskT*>(a.actions);
-  MaskT* act_out = reinterpret_cast<MaskT*>(a.actions_out);
-  const MaskT* rp_sw = reinterpret_cast<const MaskT*>(a.rp_sw);
-  const uint32_t cmask = C >= 32 ? 0xFFFFFFFFu : ((1u << C) - 1u);
-
-  for (int b = blockIdx.x * blockDim.x + threadIdx.x; b < a.B; b += gridDim.x * blockDim.x) {
-    const uint32_t env = a.env_offset + (uint32_t)b;
-    MaskT att[NMAX];
-    Rec<W> recs[NFIX ? NFIX : 1];
-    MaskT chn[NFIX ? NFIX : 1];
-
-    // ---- pass 1: who transmits where (combinatorial_env.py:135-148) ----
-    uint32_t once = 0, twice = 0, good_any = 0;
-#pragma unroll
-    for (int k = 0; k < N; ++k) {
-      const Rec<W> r = rec_load<W>(a.buf, (size_t)k * B + b);
-      const uint32_t ch = chan[(size_t)k * B + b];
-      uint32_t want;
-      if (a.act_mode == 0) {
-        want = act[(size_t)k * B + b];
-      } else {
-        const uint32_t thr = a.tp_thr;
-        want = philox_lane_mask(env, a.t, (uint32_t)k | (kPurposePolicy << 16), C, a.k0, a.k1,
-                                [thr](int) { return thr; });
-        if (act_out) act_out[(size_t)k * B + b] = (MaskT)want;
-      }
-      const uint32_t at = rec_any<W>(r) ? (want & cmask) : 0u;
-      twice |= once & at;
-      once |= at;
-      good_any |= at & ch;
-      att[k] = (MaskT)at;
-      if constexpr (NFIX != 0) recs[k] = r, chn[k] = (MaskT)ch;
-    }
-    // ack/nack per channel (combinatorial_env.py:155-157): +1 iff exactly one user and its channel is good
-    const uint32_t acked = once & ~twice & good_any;
-    const uint32_t nacked = once & ~acked;
-
-    // ---- pass 2: serve, age, switch, arrive, observe ----
-    int n_success = 0;
-#pragma unroll
-    for (int k = 0; k < N; ++k) {
-      const size_t idx = (size_t)k * B + b;
-      Rec<W> r;
-      uint32_t ch;
-      if constexpr (NFIX != 0) {
-        r = recs[k], ch = chn[k];
-      } else {
-        r = rec_load<W>(a.buf, idx), ch = chan[idx];
-      }
-      const bool success = ((uint32_t)att[k] & ch & acked) != 0;  // :160-161
-      n_success += success;
-      rec_pop_earliest<W>(r, success);                            // :164-170
-      const uint32_t expired = rec_age<W>(r);                     // :173
-      if (expired) a.disc[idx] += expired;                        // :174
-      uint32_t sw;                                                // :175, :116-118
-      if (a.rng_mode == D2D_RNG_REPLAY) {
-        sw = rp_sw[idx];
-      } else {
-        const uint32_t* thr = swthr + k * C;
-        sw = philox_lane_mask(env, a.t, (uint32_t)k | (kPurposeSwitch << 16), C, a.k0, a.k1,
-                              [thr](int c) { return thr[c]; });
-      }
-      const uint32_t ch_new = (ch ^ sw) & cmask;
-      chan[idx] = (MaskT)ch_new;
-      const int dl = P->deadline[k];
-      if ((a.active >> k) & 1ull) {                               // :178-196
-        const uint32_t arrived = draw_arrival(a, P, cdf, k, b);
-        rec_set_byte<W>(r, dl - 1, arrived);
-        if (arrived) a.recv[idx] += arrived;
-      }
-      rec_store<W>(a.buf, idx, r);
-      if (a.obs) {                                                // :199-206
-        float* o = a.obs + (size_t)P->obs_off[k] * B + b;
-        const int nb = P->homog ? P->D : dl;
-        rec_emit<W>(r, nb, o, B);
-        o += (size_t)nb * B;
-        for (int c = 0; c < C; ++c) o[(size_t)c * B] = (float)((ch >> c) & 1u);  // pre-switch copy (:145)
-        o += (size_t)C * B;
-        for (int c = 0; c < C; ++c) o[(size_t)c * B] = (float)((acked >> c) & 1u) - (float)((nacked >> c) & 1u);
-      }
-      if (a.state) {                                              // :207-209
-        rec_emit<W>(r, dl, a.state + (size_t)P->sbuf_off[k] * B + b, B);
-        float* s = a.state + ((size_t)P->sum_dl + (size_t)k * C) * B + b;
-        for (int c = 0; c < C; ++c) s[(size_t)c * B] = (float)((ch_new >> c) & 1u);
-      }
-    }
-    if (a.state) {
-      float* s = a.state + ((size_t)P->sum_dl + (size_t)N * C) * B + b;
-      for (int c = 0; c < C; ++c) s[(size_t)c * B] = (float)((acked >> c) & 1u) - (float)((nacked >> c) & 1u);
-    }
-    if (a.ack) {
-      int8_t* q = reinterpret_cast<int8_t*>(a.ack) + b;
-      for (int c = 0; c < C; ++c) q[(size_t)c * B] = (int8_t)((int)((acked >> c) & 1u) - (int)((nacked >> c) & 1u));
-    }
-    a.reward[b] = n_success;                                      // :211
-    if (a.done) a.done[b] = (uint8_t)a.done_flag;                 // :233-236
-  }
-}
-
 template <int W, typename MaskT>
 __global__ void __launch_bounds__(256) comb_reset_kernel(const StepArgs a) {
   extern __shared__ __align__(16) uint8_t smem[];
@@ -849,6 +577,7 @@ static int fill_args(d2d_env* e, StepArgs& a, uint32_t t, const char* who) {
   a.buf = e->buf, a.chan = e->chan, a.disc = e->disc, a.recv = e->recv, a.stats = e->stats;
   a.params = e->params, a.params_bytes = e->params_bytes;
   a.B = e->B, a.t = t, a.k0 = (uint32_t)(e->seed & 0xFFFFFFFFull), a.k1 = (uint32_t)(e->seed >> 32);
+  for (int r = 0; r < 10; ++r) a.rk0[r] = a.k0 + (uint32_t)r * 0x9E3779B9u, a.rk1[r] = a.k1 + (uint32_t)r * 0xBB67AE85u;
   a.env_offset = (uint32_t)e->env_offset, a.active = e->active[t], a.rng_mode = e->rng_mode;
   a.done_flag = (int)t >= e->T;
   if (e->rng_mode == D2D_RNG_REPLAY) {
@@ -903,19 +632,9 @@ extern "C" int d2d_env_reset(d2d_env* e, float* obs, float* state, void* stream)
 static int env_step_impl(d2d_env* e, StepArgs& a, void* stream) {
   int rc;
   if (e->kind == D2D_ENV_COMBINATORIAL) {
-#define D2D_STEP_CASE(WW, MT)                                                               \
-  rc = (e->N == 6) ? launch_env(comb_step_kernel<WW, MT, 6>, a, e->params_bytes, stream)    \
-                   : launch_env(comb_step_kernel<WW, MT, 0>, a, e->params_bytes, stream)
-    if (e->W == 2 && e->CB == 1) D2D_STEP_CASE(2, uint8_t);
-    else if (e->W == 2 && e->CB == 2) D2D_STEP_CASE(2, uint16_t);
-    else if (e->W == 2) D2D_STEP_CASE(2, uint32_t);
-    else if (e->W == 4 && e->CB == 1) D2D_STEP_CASE(4, uint8_t);
-    else if (e->W == 4 && e->CB == 2) D2D_STEP_CASE(4, uint16_t);
-    else if (e->W == 4) D2D_STEP_CASE(4, uint32_t);
-    else if (e->CB == 1) D2D_STEP_CASE(8, uint8_t);
-    else if (e->CB == 2) D2D_STEP_CASE(8, uint16_t);
-    else D2D_STEP_CASE(8, uint32_t);
-#undef D2D_STEP_CASE
+    rc = e->W == 2 ? launch_comb_step<2>(a, e->N, e->C, e->CB, as_stream(stream))
+         : e->W == 4 ? launch_comb_step<4>(a, e->N, e->C, e->CB, as_stream(stream))
+                     : launch_comb_step<8>(a, e->N, e->C, e->CB, as_stream(stream));
   } else if (e->kind == D2D_ENV_SINGLE_CHANNEL) {
     rc = e->W == 2 ? launch_env(sc_step_kernel<2>, a, e->params_bytes, stream)
          : e->W == 4 ? launch_env(sc_step_kernel<4>, a, e->params_bytes, stream)
