@@ -1,0 +1,234 @@
+"""PPO / IPPO fixtures from the UNMODIFIED reference learners (run via ``python -m oracle.gen_golden ppo``).
+
+TEST INFRASTRUCTURE ONLY.  Writes tests/golden/ppo_*.npz:
+
+* ppo_nets_*      reference ``RNN`` / ``Policy`` / ``Value`` modules: state_dicts, inputs, outputs, and the
+                  ``select_action`` / ``evaluate`` log-probs and entropies for recorded actions.
+* ppo_returns     ``compute_gae`` and ``discount_rewards`` on random trajectories with episode boundaries.
+* ppo_ippo_*      one reference ``iPPO.train(num_iter=1)`` on a replayed CombinatorialEnv: the rollout
+                  (observations, actions, log-probs, values, advantages, returns), every epoch's losses and the
+                  parameters before / after.
+* ppo_d2dppo_*    the same for ``D2DPPO.train`` (sequential M chain, central critic).
+
+torch's RNG is seeded here (the reference never seeds it) so that fixtures are reproducible; actions are then
+teacher-forced in the tests.
+"""
+from __future__ import annotations
+
+import json
+import os
+
+import numpy as np
+import torch
+
+from .gen_golden import GOLDEN, draw_streams, to_ref_kwargs
+from .ref_harness import ReplayRandom, _NumpyProxy, import_reference, tagged_array
+
+
+def _sd(module):
+    return {k: v.detach().numpy().copy() for k, v in module.state_dict().items()}
+
+
+def _flat(prefix, d):
+    return {f"{prefix}/{k}": v for k, v in d.items()}
+
+
+def gen_nets():
+    ippo = import_reference("algorithms.ippo")
+    for tag, n_in, n_out, H, L, comb in [("small", 11, 4, 16, 4, True), ("c3", 30, 8, 64, 6, True),
+                                          ("categorical", 12, 5, 16, 3, False)]:
+        torch.manual_seed(123)
+        R = 40
+        out = {"meta": json.dumps(dict(n_in=n_in, n_out=n_out, hidden=H, L=L, combinatorial=comb))}
+        x2 = torch.randint(-1, 4, (R, n_in)).float()
+        x3 = torch.randint(-1, 4, (R, L, n_in)).float()
+        out["x_mlp"], out["x_gru"] = x2.numpy(), x3.numpy()
+        for arch in ("mlp", "gru"):
+            agent = ippo.PPO(n_in, n_out, hidden_size=H, useRNN=(arch == "gru"), combinatorial=comb, history_len=L)
+            # perturb biases so that they matter (the reference initialises Linear biases to zero)
+            with torch.no_grad():
+                for prm in list(agent.policy_network.parameters()) + list(agent.value_network.parameters()):
+                    if prm.dim() == 1:
+                        prm.add_(0.1 * torch.randn_like(prm))
+            x = x3 if arch == "gru" else x2
+            probs = agent.policy_network(x)
+            value = agent.value_network(x)
+            if comb:
+                actions = torch.bernoulli(probs.detach())
+            else:
+                actions = torch.multinomial(probs.detach(), 1).squeeze(1)
+            logp, ent = agent.evaluate(x, actions.numpy())
+            out.update(_flat(f"{arch}/policy", _sd(agent.policy_network)))
+            out.update(_flat(f"{arch}/value", _sd(agent.value_network)))
+            out[f"{arch}/probs"] = probs.detach().numpy()
+            out[f"{arch}/value_out"] = value.detach().numpy()
+            out[f"{arch}/actions"] = actions.numpy()
+            out[f"{arch}/logp"] = logp.detach().numpy()
+            out[f"{arch}/entropy"] = ent.detach().numpy()
+            # select_action on single rows (the rollout call): greedy action, log-prob and entropy of it
+            sel = [agent.select_action(x[i], train=False) for i in range(8)]
+            out[f"{arch}/greedy_actions"] = np.stack([np.asarray(s[0]).reshape(-1) for s in sel])
+            out[f"{arch}/greedy_logp"] = np.array([float(s[1]) for s in sel], dtype=np.float32)
+            out[f"{arch}/greedy_entropy"] = np.array([float(s[2]) for s in sel], dtype=np.float32)
+        path = os.path.join(GOLDEN, f"ppo_nets_{tag}.npz")
+        np.savez_compressed(path, **out)
+        print("wrote", path)
+
+
+def gen_returns():
+    ippo = import_reference("algorithms.ippo")
+    rng = np.random.default_rng(5)
+    out = {}
+    for tag, T, E, N in [("a", 7, 5, 3), ("b", 20, 4, 1), ("c", 200, 3, 6)]:
+        R = T * E
+        rewards = rng.integers(0, 4, (R, N)).astype(np.float64)
+        values = rng.normal(0, 1, (R, N))
+        dones = [(i % T) == T - 1 for i in range(R)]
+        for gamma in (0.6, 0.99):
+            adv = ippo.compute_gae(rewards, dones, values, gamma, 0.97)
+            ret = ippo.discount_rewards(rewards, gamma, dones, True)
+            out[f"{tag}/g{gamma}/adv"] = adv.numpy()
+            out[f"{tag}/g{gamma}/ret"] = ret.numpy()
+        # the D2DPPO call shape: 1-D agent-mean rewards and critic values (d2d_ppo.py:426)
+        adv1 = ippo.compute_gae(rewards.mean(1), dones, values[:, 0], 0.6, 0.97)
+        out[f"{tag}/adv1d"] = adv1.numpy()
+        out[f"{tag}/rewards"], out[f"{tag}/values"], out[f"{tag}/T"] = rewards, values, np.array(T)
+    # degenerate: zero variance column -> no normalisation (d2d_ppo.py:108, :122)
+    rewards = np.ones((12, 2))
+    values = np.zeros((12, 2))
+    dones = [(i % 4) == 3 for i in range(12)]
+    out["deg/adv"] = ippo.compute_gae(rewards, dones, values, 0.0, 0.97).numpy()
+    out["deg/ret"] = ippo.discount_rewards(rewards, 0.0, dones, True).numpy()
+    path = os.path.join(GOLDEN, "ppo_returns.npz")
+    np.savez_compressed(path, **out)
+    print("wrote", path)
+
+
+class _EpisodeReplayEnv:
+    """The reference CombinatorialEnv where episode e (the e-th reset) replays stream column e."""
+
+    def __init__(self, kw, arrivals, switches):
+        mod = import_reference("envs.combinatorial_env")
+        self.mod, self.saved = mod, mod.np
+        self.rnd = ReplayRandom()
+        kw = dict(to_ref_kwargs("combinatorial", kw))
+        kw["lbdas"] = tagged_array(kw["lbdas"], "arr")
+        if kw.get("arrival_probs") is not None:
+            kw["arrival_probs"] = tagged_array(kw["arrival_probs"], "arr")
+        kw["periodic_devices"] = [int(i) for i in kw.get("periodic_devices", [])]
+        self.env = mod.CombinatorialEnv(**kw)
+        self.arr, self.sw, self.episode = arrivals, switches, -1
+
+    def __getattr__(self, name):
+        return getattr(self.env, name)
+
+    def reset(self):
+        self.episode += 1
+        self.rnd.arrivals, self.rnd.switch = self.arr[0, self.episode], None
+        self.mod.np = _NumpyProxy(self.rnd)
+        try:
+            return self.env.reset()
+        finally:
+            self.mod.np = self.saved
+
+    def step(self, actions):
+        t = self.env.timestep + 1
+        self.rnd.arrivals, self.rnd.switch = self.arr[t, self.episode], self.sw[t, self.episode]
+        self.mod.np = _NumpyProxy(self.rnd)
+        try:
+            return self.env.step(actions)
+        finally:
+            self.mod.np = self.saved
+
+
+def _train_case(algo, tag, kw, E, H, L, arch, n_epoch, gamma, seed):
+    mod = import_reference("algorithms.ippo" if algo == "ippo" else "algorithms.d2d_ppo")
+    T, N = kw["episode_length"], kw["n_agents"]
+    rng = np.random.default_rng(seed)
+    arr, sw = draw_streams("combinatorial", kw, E, T, rng)
+    env = _EpisodeReplayEnv(kw, arr, sw)
+    torch.manual_seed(seed)
+    np.random.seed(seed)  # D2DPPO shuffles the agent cycle with the global numpy RNG (d2d_ppo.py:421-422)
+    common = dict(hidden_size=H, gamma=gamma, policy_lr=3e-4, value_lr=1e-3, device="cpu", useRNN=(arch == "gru"),
+                  combinatorial=True, history_len=L, early_stopping=False)
+    agent = mod.iPPO(env, **common) if algo == "ippo" else mod.D2DPPO(env, beta_entropy=0.01, **common)
+    out = {"meta": json.dumps(dict(algo=algo, arch=arch, hidden=H, L=L, E=E, T=T, N=N, n_epoch=n_epoch, gamma=gamma,
+                                   policy_lr=3e-4, value_lr=1e-3)),
+           "config": json.dumps(kw), "arrivals": arr, "switches": sw}
+    for i, a in enumerate(agent.agents):
+        out.update(_flat(f"init/policy{i}", _sd(a.policy_network)))
+        if algo == "ippo":
+            out.update(_flat(f"init/value{i}", _sd(a.value_network)))
+    if algo == "d2dppo":
+        out.update(_flat("init/critic", _sd(agent.value_network)))
+
+    # record the rollout the training iteration will see, by wrapping create_rollouts (harness-level, no source edit)
+    rec = {}
+    orig = agent.create_rollouts
+
+    def create_rollouts(num_episodes=4):
+        res = orig(num_episodes)
+        rec["res"] = res
+        return res
+    agent.create_rollouts = create_rollouts
+    agent.test = lambda n: (0.0, 0.0, 0, 0.0)      # keep test() out of the RNG / env streams
+    cycles = []
+    if algo == "d2dppo":
+        real_shuffle = np.random.shuffle
+
+        def shuffle(x):
+            real_shuffle(x)
+            cycles.append(np.array(x).copy())
+        mod.np.random.shuffle = shuffle
+    try:
+        if algo == "ippo":
+            _, _, ploss, vloss = agent.train(num_iter=1, n_epoch=n_epoch, num_episodes=E, test_freq=10 ** 9)
+        else:
+            _, _, ploss, vloss = agent.train(num_iter=1, num_episodes=E, n_epoch=n_epoch, test_freq=10 ** 9)
+    finally:
+        if algo == "d2dppo":
+            mod.np.random.shuffle = real_shuffle
+    res = rec["res"]
+    if algo == "ippo":
+        obs, actions, logp_old, returns, values, adv, scores, dones = res
+        out.update(values=np.asarray(values, dtype=np.float32), advantages=adv.numpy(), returns=returns.numpy())
+        out["policy_loss"] = np.array(ploss, dtype=np.float32)      # last agent's loss per epoch (ippo.py:425)
+        out["value_loss"] = np.array(vloss, dtype=np.float32)
+    else:
+        obs, states, actions, logp_old, rewards, returns, scores, dones = res
+        out.update(states=states.numpy(), rewards_mean=np.asarray(rewards, dtype=np.float64), returns=returns.numpy(),
+                   cycles=np.stack(cycles))
+        out["policy_loss"] = np.array(ploss, dtype=np.float32)      # [n_epoch, N] in cycle order
+        out["value_loss"] = np.array([float(v) for v in vloss], dtype=np.float32)
+    out.update(obs=np.stack([o.numpy() for o in obs], axis=1), actions=np.asarray(actions, dtype=np.uint8),
+               logp_old=logp_old.numpy(), scores=np.array(scores), dones=np.array(dones))
+    for i, a in enumerate(agent.agents):
+        out.update(_flat(f"final/policy{i}", _sd(a.policy_network)))
+        if algo == "ippo":
+            out.update(_flat(f"final/value{i}", _sd(a.value_network)))
+    if algo == "d2dppo":
+        out.update(_flat("final/critic", _sd(agent.value_network)))
+    path = os.path.join(GOLDEN, f"ppo_{algo}_{tag}.npz")
+    np.savez_compressed(path, **out)
+    print("wrote", path, os.path.getsize(path), "bytes")
+
+
+def gen_train():
+    small = dict(n_agents=3, n_channels=4, deadlines=[3, 5, 3], lbdas=[0.5] * 3, period=[2] * 3,
+                 arrival_probs=[0.6, 0.9, 1.0], offsets=[0, 1, 0], episode_length=12, traffic_model="heterogeneous",
+                 homogeneous_size=True, periodic_devices=[0], channel_switch=[[0.2, 0.4, 0.6, 0.8]] * 3)
+    from .gen_golden import SETUP8
+    c3 = dict(n_agents=6, n_channels=8, deadlines=SETUP8["deadlines"], lbdas=[0.5] * 6, period=[2] * 6,
+              arrival_probs=SETUP8["arrival_probs"], offsets=SETUP8["offsets"], episode_length=20,
+              traffic_model="heterogeneous", homogeneous_size=True, periodic_devices=SETUP8["periodic_devices"],
+              channel_switch=SETUP8["channel_switch"])
+    for algo in ("ippo", "d2dppo"):
+        _train_case(algo, "small_gru", small, E=5, H=16, L=4, arch="gru", n_epoch=3, gamma=0.6, seed=11)
+        _train_case(algo, "small_mlp", small, E=5, H=16, L=4, arch="mlp", n_epoch=3, gamma=0.9, seed=12)
+        _train_case(algo, "c3_gru", c3, E=3, H=64, L=6, arch="gru", n_epoch=2, gamma=0.6, seed=13)
+
+
+def main():
+    gen_nets()
+    gen_returns()
+    gen_train()

