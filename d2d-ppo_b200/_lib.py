@@ -35,6 +35,19 @@ class EnvConfig(C.Structure):
     ]
 
 
+class NetConfig(C.Structure):
+    _fields_ = [
+        ("arch", C.c_int32), ("out_kind", C.c_int32), ("n_agents", C.c_int32), ("n_envs", C.c_int32),
+        ("hidden", C.c_int32), ("n_out", C.c_int32), ("history_len", C.c_int32), ("in_rows", C.c_int32),
+        ("in_dim", C.POINTER(C.c_int32)), ("in_off", C.POINTER(C.c_int32)), ("scratch_bytes", C.c_int64),
+    ]
+
+
+NET_MLP, NET_GRU = 0, 1
+OUT_SOFTMAX, OUT_SIGMOID, OUT_IDENTITY = 0, 1, 2
+DIST_BERNOULLI, DIST_CATEGORICAL = 0, 1
+ACT_SAMPLE, ACT_GREEDY, ACT_GIVEN = 0, 1, 2
+
 _lib = None
 
 _P = C.c_void_p
@@ -60,6 +73,23 @@ _SIGNATURES = {
     "d2d_env_export_state": (C.c_int, [_P, _P, _P, _P, _P, _P, _P]),
     "d2d_env_import_state": (C.c_int, [_P, _P, _P, _P, _P, _P, C.c_int, _P]),
     "d2d_env_scores": (C.c_int, [_P, _P, _P, _P, _P]),
+    "d2d_net_create": (C.c_int, [C.POINTER(NetConfig), C.POINTER(_P)]),
+    "d2d_net_destroy": (C.c_int, [_P]),
+    "d2d_net_param_stride": (C.c_int64, [_P]),
+    "d2d_net_num_tensors": (C.c_int, [_P]),
+    "d2d_net_tensor": (C.c_int, [_P, C.c_int, C.c_int, C.POINTER(C.c_int64), C.POINTER(C.c_int32),
+                                 C.POINTER(C.c_int32)]),
+    "d2d_net_forward": (C.c_int, [_P, _P, _P, C.c_int, C.c_int, C.c_int, C.c_int, _P, _P]),
+    "d2d_policy_head": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _P, _P, _P, _P, _P,
+                                  C.c_uint64, C.c_uint64, C.c_int, _P]),
+    "d2d_ppo_policy_grad": (C.c_int, [_P, _P, _P, C.c_int, C.c_int, C.c_int, C.c_int, _P, _P, _P, C.c_int, _P,
+                                      C.c_float, C.c_float, C.c_float, _P, _P, _P, _P]),
+    "d2d_value_grad": (C.c_int, [_P, _P, _P, C.c_int, C.c_int, C.c_int, C.c_int, _P, C.c_int, C.c_float, _P, _P, _P,
+                                 _P]),
+    "d2d_adam_step": (C.c_int, [_P, _P, _P, _P, C.c_int, C.c_int64, C.c_float, C.c_int, C.c_float, _P, _P]),
+    "d2d_returns_scan": (C.c_int, [_P, _P, _P, _P, _P, C.c_int, C.c_int, C.c_int, C.c_double, C.c_double, C.c_int,
+                                   _P]),
+    "d2d_normalize": (C.c_int, [_P, _P, _P, _P, _P, C.c_int, C.c_int, C.c_int, C.c_int, _P]),
 }
 
 

@@ -1,0 +1,616 @@
+// Host orchestration + C ABI of the learner (PPO / IPPO networks, losses, returns, optimiser).
+//
+// Replaces (file:line under /root/reference):
+//   RNN / Policy / Value forward            algorithms/d2d_ppo.py:24-98, algorithms/ippo.py:14-90  -> d2d_net_forward
+//   PPO.select_action / PPO.evaluate        d2d_ppo.py:159-196, ippo.py:154-191                    -> d2d_policy_head
+//   PPO.train_step (policy part)            d2d_ppo.py:198-216, ippo.py:194-206                    -> d2d_ppo_policy_grad
+//   critic MSE step                         d2d_ppo.py:440-446, ippo.py:208-215                    -> d2d_value_grad
+//   compute_gae / discount_rewards          d2d_ppo.py:100-124                                     -> d2d_returns_scan
+//   clip_grad_norm_ + Adam                  d2d_ppo.py:211-212,445-446                             -> d2d_adam_step
+//
+// A net set evaluates N independent per-agent networks with grid.y = agent.  Time blocks are processed in
+// chunks sized to the activation-scratch budget; the GRU window is unrolled step by step over the chunk with
+// the input projection of every observation computed ONCE and shared by the up-to-L windows that contain it.
+#include <algorithm>
+#include <cstring>
+#include <new>
+#include <vector>
+
+#include "learner_pointwise.cuh"
+
+using namespace d2d;
+
+struct d2d_net {
+  int arch, out_kind, N, B, H, O, L, in_rows;
+  std::vector<int> in_dim, in_off;
+  int max_in;
+  long long stride;  // floats per agent block
+  // per-agent tensor offsets inside the block
+  std::vector<int> o_wih, o_whh, o_bih, o_bhh, o_w1, o_b1, o_w2, o_b2;
+  long long scratch_bytes;
+  float* scratch = nullptr;
+  long long scratch_cap = 0;  // floats
+  float* partial = nullptr;   // wgrad partial sums
+  long long part_stride = 0;
+  int n_strips = 0;
+};
+
+// ------------------------------------------------------------------------------------------------
+// helpers
+// ------------------------------------------------------------------------------------------------
+static View make_view(float* p, long long t_stride, int t_off, int N, int feat_per_agent, int B) {
+  View v;
+  memset(&v, 0, sizeof(v));
+  v.p = p, v.t_stride = t_stride, v.t_off = t_off;
+  for (int g = 0; g < N; ++g) v.f_off[g] = g * feat_per_agent;
+  (void)B;
+  return v;
+}
+
+static int launch_dense(const d2d_net* n, DenseArgs& a, int max_in, cudaStream_t s) {
+  a.B = n->B;
+  const int OC = a.out_dim >= 64 ? 64 : 16;
+  const int out_pad = (a.out_dim + OC - 1) / OC * OC;
+  const size_t smem = ((size_t)max_in * out_pad + out_pad) * sizeof(float);
+  const int tiles = (a.t1 - a.t0) * ((n->B + kRowsPerBlock - 1) / kRowsPerBlock);
+  if (tiles <= 0) return D2D_OK;
+  // persistent over row tiles: the weight matrix is staged in shared memory once per block
+  const int gx = std::max(1, std::min(tiles, (148 * 4 + n->N - 1) / n->N));
+  dim3 grid(gx, n->N);
+  if (OC == 64) {
+    static bool attr64 = false;
+    if (!attr64) {
+      D2D_CUDA(cudaFuncSetAttribute(dense_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+      attr64 = true;
+    }
+    dense_kernel<64><<<grid, kRowsPerBlock, smem, s>>>(a);
+  } else {
+    static bool attr16 = false;
+    if (!attr16) {
+      D2D_CUDA(cudaFuncSetAttribute(dense_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+      attr16 = true;
+    }
+    dense_kernel<16><<<grid, kRowsPerBlock, smem, s>>>(a);
+  }
+  D2D_LAUNCHED();
+  return D2D_OK;
+}
+
+// weight tensor descriptor: offsets per agent, input dims per agent
+struct Wt {
+  const std::vector<int>* w_off;
+  const std::vector<int>* b_off;   // may be null
+  const std::vector<int>* in_dim;  // per agent rows' length of the stored matrix (K)
+  int in_const;                    // used when in_dim == nullptr
+  int out_dim;
+};
+
+static void fill_dense_w(const d2d_net* n, DenseArgs& a, const float* params, const Wt& w, int trans) {
+  a.w = params, a.w_agent_stride = n->stride, a.trans = trans;
+  for (int g = 0; g < n->N; ++g) {
+    const int K = w.in_dim ? (*w.in_dim)[g] : w.in_const;
+    a.w_off[g] = (*w.w_off)[g];
+    a.b_off[g] = (w.b_off && !trans) ? (*w.b_off)[g] : -1;
+    a.w_ld[g] = K;
+    a.in_dim[g] = trans ? w.out_dim : K;
+  }
+  a.out_dim = trans ? (w.in_dim ? 0 : w.in_const) : w.out_dim;
+}
+
+template <int TO, int TK>
+static void launch_wgrad_t(const WgradArgs& a, dim3 grid, cudaStream_t s) {
+  const size_t smem = (size_t)(16 * TO + 16 * TK) * (kWgRows + 1) * sizeof(float);
+  wgrad_kernel<TO, TK><<<grid, 256, smem, s>>>(a);
+}
+
+// dW (+ db) of `w` from dy [out_dim] and x [K]; accumulated into grads
+static int launch_wgrad(d2d_net* n, const View& dy, const View& x, const Wt& w, bool zero_in, float* grads, int t0,
+                        int t1, cudaStream_t s) {
+  WgradArgs a;
+  memset(&a, 0, sizeof(a));
+  a.dy = dy, a.x = x, a.partial = n->partial, a.part_stride = n->part_stride;
+  a.out_dim = w.out_dim, a.B = n->B, a.t0 = t0, a.t1 = t1, a.with_bias = w.b_off != nullptr;
+  int maxK = 0;
+  for (int g = 0; g < n->N; ++g) {
+    a.in_dim[g] = zero_in ? 0 : (w.in_dim ? (*w.in_dim)[g] : w.in_const);
+    maxK = std::max(maxK, a.in_dim[g]);
+  }
+  dim3 grid(n->n_strips, n->N);
+  const int O = w.out_dim;
+  if (O > 192 || maxK > 128) {
+    set_error("learner: weight-gradient tile %d x %d exceeds the supported 192 x 128", O, maxK);
+    return D2D_ERR_INVALID;
+  }
+  const int to = O > 64 ? 12 : (O > 16 ? 4 : 1);
+  const int tk = maxK > 64 ? 8 : (maxK > 32 ? 4 : 2);
+#define WG(TO_, TK_) if (to == TO_ && tk == TK_) launch_wgrad_t<TO_, TK_>(a, grid, s)
+  WG(12, 2); WG(12, 4); WG(12, 8); WG(4, 2); WG(4, 4); WG(4, 8); WG(1, 2); WG(1, 4); WG(1, 8);
+#undef WG
+  D2D_LAUNCHED();
+  WreduceArgs r;
+  memset(&r, 0, sizeof(r));
+  r.partial = n->partial, r.part_stride = n->part_stride, r.n_strips = n->n_strips, r.grads = grads;
+  r.g_agent_stride = n->stride, r.out_dim = O, r.with_bias = a.with_bias;
+  for (int g = 0; g < n->N; ++g) {
+    r.w_off[g] = (*w.w_off)[g];
+    r.b_off[g] = w.b_off ? (*w.b_off)[g] : 0;
+    r.in_dim[g] = a.in_dim[g];
+  }
+  const int total = O * maxK + O;
+  wreduce_kernel<<<dim3((total + 255) / 256, n->N), 256, 0, s>>>(r);
+  D2D_LAUNCHED();
+  return D2D_OK;
+}
+
+static int launch_gate(const GateArgs& a, int N, bool bwd, cudaStream_t s) {
+  const long long n = (long long)(a.t1 - a.t0) * a.H * a.B;
+  if (n <= 0) return D2D_OK;
+  dim3 grid(grid_for(n, 256), N);
+  if (bwd) gru_gate_bwd_kernel<<<grid, 256, 0, s>>>(a);
+  else gru_gate_fwd_kernel<<<grid, 256, 0, s>>>(a);
+  D2D_LAUNCHED();
+  return D2D_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// scratch carving for one chunk of Tc time blocks
+// ------------------------------------------------------------------------------------------------
+struct Chunk {
+  int Tc, halo;
+  float *gi, *gh, *acts, *hs, *y1, *logits, *dl, *dy1, *dh0, *dh1, *dgi;
+};
+
+static long long floats_per_t(const d2d_net* n, bool train) {
+  const long long NB = (long long)n->N * n->B;
+  const long long H = n->H, O = n->O, L = n->arch == D2D_NET_GRU ? n->L : 0;
+  long long f = H + O;                                // y1, logits
+  if (n->arch == D2D_NET_GRU) f += 3 * H + 3 * H;     // gi, gh
+  if (n->arch == D2D_NET_GRU) f += train ? L * H + 4 * L * H : 2 * H;   // hs (+ acts)
+  if (train) f += O + H;                              // dl, dy1
+  if (train && n->arch == D2D_NET_GRU) f += 2 * H + 3 * H;   // dh ping-pong, dgi
+  return f * NB;
+}
+
+static int plan_chunk(d2d_net* n, bool train, int n_t, Chunk& c) {
+  const long long NB = (long long)n->N * n->B;
+  const int halo = n->arch == D2D_NET_GRU ? n->L - 1 : 0;
+  const long long per_t = floats_per_t(n, train);
+  const long long halo_f = (long long)halo * 3 * n->H * NB * (train ? 2 : 1);
+  long long budget = n->scratch_bytes / 4;
+  int Tc = (int)std::max<long long>(1, std::min<long long>(n_t, (budget - halo_f) / per_t));
+  const long long need = per_t * Tc + halo_f;
+  if (need > n->scratch_cap) {
+    if (n->scratch) cudaFree(n->scratch);
+    n->scratch = nullptr, n->scratch_cap = 0;
+    D2D_CUDA(cudaMalloc((void**)&n->scratch, (size_t)need * 4));
+    n->scratch_cap = need;
+  }
+  c.Tc = Tc, c.halo = halo;
+  float* p = n->scratch;
+  auto take = [&](long long f) { float* q = p; p += f; return q; };
+  const long long H = n->H, O = n->O, L = n->L;
+  c.gi = c.gh = c.acts = c.hs = c.dl = c.dy1 = c.dh0 = c.dh1 = c.dgi = nullptr;
+  if (n->arch == D2D_NET_GRU) {
+    c.gi = take((long long)(Tc + halo) * 3 * H * NB);
+    c.gh = take((long long)Tc * 3 * H * NB);
+    if (train) {
+      c.hs = take((long long)L * Tc * H * NB);
+      c.acts = take((long long)L * Tc * 4 * H * NB);
+    } else {
+      c.hs = take((long long)2 * Tc * H * NB);
+    }
+  }
+  c.y1 = take((long long)Tc * H * NB);
+  c.logits = take((long long)Tc * O * NB);
+  if (train) {
+    c.dl = take((long long)Tc * O * NB);
+    c.dy1 = take((long long)Tc * H * NB);
+    if (n->arch == D2D_NET_GRU) {
+      c.dh0 = take((long long)Tc * H * NB);
+      c.dh1 = take((long long)Tc * H * NB);
+      c.dgi = take((long long)(Tc + halo) * 3 * H * NB);
+    }
+  }
+  return D2D_OK;
+}
+
+// hidden state buffer of window step s for the chunk (training keeps all L of them)
+static float* hs_ptr(const d2d_net* n, const Chunk& c, bool train, int s) {
+  const long long per = (long long)c.Tc * n->H * n->N * n->B;
+  return c.hs + per * (train ? s : (s & 1));
+}
+
+// forward of chunk [c0, c1) (c1 - c0 <= Tc): fills c.logits (local time index t - c0)
+static int forward_chunk(d2d_net* n, const float* params, const float* x, int x_lead, int c0, int c1, int padded,
+                         bool train, const Chunk& c, cudaStream_t s) {
+  const int N = n->N, B = n->B, H = n->H, O = n->O;
+  const long long NB = (long long)N * B;
+  View xin;
+  memset(&xin, 0, sizeof(xin));
+  xin.p = const_cast<float*>(x), xin.t_stride = (long long)n->in_rows * B, xin.t_off = x_lead;
+  for (int g = 0; g < N; ++g) xin.f_off[g] = n->in_off[g];
+  const View y1 = make_view(c.y1, H * NB, -c0, N, H, B);
+  const View lg = make_view(c.logits, O * NB, -c0, N, O, B);
+  Wt w1{&n->o_w1, &n->o_b1, nullptr, H, H};
+  Wt w2{&n->o_w2, &n->o_b2, nullptr, H, O};
+  int rc;
+  View last;
+  if (n->arch == D2D_NET_MLP) {
+    w1.in_dim = &n->in_dim;
+    last = xin;
+  } else {
+    const int L = n->L, halo = c.halo;
+    // input projections of every observation the chunk's windows touch: times [c0 - halo, c1)
+    const View gi = make_view(c.gi, 3 * H * NB, -(c0 - halo), N, 3 * H, B);
+    {
+      DenseArgs a;
+      memset(&a, 0, sizeof(a));
+      Wt wih{&n->o_wih, &n->o_bih, &n->in_dim, 0, 3 * H};
+      fill_dense_w(n, a, params, wih, 0);
+      a.x = xin, a.y = gi, a.epilogue = kEpiNone, a.t0 = c0 - halo, a.t1 = c1;
+      if ((rc = launch_dense(n, a, n->max_in, s))) return rc;
+    }
+    const View gh = make_view(c.gh, 3 * H * NB, -c0, N, 3 * H, B);
+    for (int st = 0; st < L; ++st) {
+      const View hprev = make_view(hs_ptr(n, c, train, st - 1 < 0 ? 0 : st - 1), H * NB, -c0, N, H, B);
+      const View hout = make_view(hs_ptr(n, c, train, st), H * NB, -c0, N, H, B);
+      {
+        DenseArgs a;
+        memset(&a, 0, sizeof(a));
+        Wt whh{&n->o_whh, &n->o_bhh, nullptr, st == 0 ? 0 : H, 3 * H};   // step 0: h = 0, gh = b_hh
+        fill_dense_w(n, a, params, whh, 0);
+        for (int g = 0; g < N; ++g) a.w_ld[g] = H;
+        a.x = hprev, a.y = gh, a.epilogue = kEpiNone, a.t0 = c0, a.t1 = c1;
+        if ((rc = launch_dense(n, a, H, s))) return rc;
+      }
+      GateArgs ga;
+      memset(&ga, 0, sizeof(ga));
+      ga.gi = gi, ga.gi.t_off = gi.t_off - (L - 1 - st);
+      ga.gh = gh, ga.h_prev = hprev, ga.h_out = hout;
+      if (train) ga.acts = make_view(c.acts + (long long)st * c.Tc * 4 * H * NB, 4 * H * NB, -c0, N, 4 * H, B);
+      ga.H = H, ga.B = B, ga.t0 = c0, ga.t1 = c1, ga.back = L - 1 - st, ga.padded = padded, ga.first = st == 0;
+      ga.store = train, ga.t_episode0 = 0;
+      if ((rc = launch_gate(ga, N, false, s))) return rc;
+    }
+    last = make_view(hs_ptr(n, c, train, L - 1), H * NB, -c0, N, H, B);
+  }
+  {
+    DenseArgs a;
+    memset(&a, 0, sizeof(a));
+    fill_dense_w(n, a, params, w1, 0);
+    a.x = last, a.y = y1, a.epilogue = kEpiRelu, a.t0 = c0, a.t1 = c1;
+    if ((rc = launch_dense(n, a, n->arch == D2D_NET_MLP ? n->max_in : H, s))) return rc;
+  }
+  {
+    DenseArgs a;
+    memset(&a, 0, sizeof(a));
+    fill_dense_w(n, a, params, w2, 0);
+    a.x = y1, a.y = lg, a.epilogue = kEpiNone, a.t0 = c0, a.t1 = c1;
+    if ((rc = launch_dense(n, a, H, s))) return rc;
+  }
+  return D2D_OK;
+}
+
+// backward of chunk [c0, c1) given c.dl = d(loss)/d(pre-activation outputs); accumulates into grads
+static int backward_chunk(d2d_net* n, const float* params, const float* x, int x_lead, int c0, int c1,
+                          const Chunk& c, float* grads, cudaStream_t s) {
+  const int N = n->N, B = n->B, H = n->H, O = n->O;
+  const long long NB = (long long)N * B;
+  View xin;
+  memset(&xin, 0, sizeof(xin));
+  xin.p = const_cast<float*>(x), xin.t_stride = (long long)n->in_rows * B, xin.t_off = x_lead;
+  for (int g = 0; g < N; ++g) xin.f_off[g] = n->in_off[g];
+  const View y1 = make_view(c.y1, H * NB, -c0, N, H, B);
+  const View dl = make_view(c.dl, O * NB, -c0, N, O, B);
+  const View dy1 = make_view(c.dy1, H * NB, -c0, N, H, B);
+  Wt w1{&n->o_w1, &n->o_b1, nullptr, H, H};
+  Wt w2{&n->o_w2, &n->o_b2, nullptr, H, O};
+  int rc;
+  // head: dW2 = dl^T y1 ; dy1 = (dl W2) * relu'(y1)
+  if ((rc = launch_wgrad(n, dl, y1, w2, false, grads, c0, c1, s))) return rc;
+  {
+    DenseArgs a;
+    memset(&a, 0, sizeof(a));
+    fill_dense_w(n, a, params, w2, 1);
+    a.out_dim = H;
+    a.x = dl, a.y = dy1, a.aux = y1, a.epilogue = kEpiReluBwd, a.t0 = c0, a.t1 = c1;
+    if ((rc = launch_dense(n, a, O, s))) return rc;
+  }
+  if (n->arch == D2D_NET_MLP) {
+    w1.in_dim = &n->in_dim;
+    return launch_wgrad(n, dy1, xin, w1, false, grads, c0, c1, s);
+  }
+  const int L = n->L, halo = c.halo;
+  const View hlast = make_view(hs_ptr(n, c, true, L - 1), H * NB, -c0, N, H, B);
+  if ((rc = launch_wgrad(n, dy1, hlast, w1, false, grads, c0, c1, s))) return rc;
+  float* dh_cur = c.dh0;
+  float* dh_nxt = c.dh1;
+  {
+    DenseArgs a;   // d(h_last) = dy1 W1
+    memset(&a, 0, sizeof(a));
+    fill_dense_w(n, a, params, w1, 1);
+    a.out_dim = H;
+    a.x = dy1, a.y = make_view(dh_cur, H * NB, -c0, N, H, B), a.epilogue = kEpiNone, a.t0 = c0, a.t1 = c1;
+    if ((rc = launch_dense(n, a, H, s))) return rc;
+  }
+  D2D_CUDA(cudaMemsetAsync(c.dgi, 0, (size_t)(c.Tc + halo) * 3 * H * NB * 4, s));
+  const View dgi = make_view(c.dgi, 3 * H * NB, -(c0 - halo), N, 3 * H, B);
+  const View dgh = make_view(c.gh, 3 * H * NB, -c0, N, 3 * H, B);
+  Wt whh{&n->o_whh, &n->o_bhh, nullptr, H, 3 * H};
+  for (int st = L - 1; st >= 0; --st) {
+    const View hprev = make_view(hs_ptr(n, c, true, st - 1 < 0 ? 0 : st - 1), H * NB, -c0, N, H, B);
+    GateArgs ga;
+    memset(&ga, 0, sizeof(ga));
+    ga.gh = dgh, ga.h_prev = hprev;
+    ga.h_out = make_view(dh_nxt, H * NB, -c0, N, H, B);
+    ga.dh = make_view(dh_cur, H * NB, -c0, N, H, B);
+    ga.acts = make_view(c.acts + (long long)st * c.Tc * 4 * H * NB, 4 * H * NB, -c0, N, 4 * H, B);
+    ga.dgi = dgi, ga.dgi.t_off = dgi.t_off - (L - 1 - st);
+    ga.H = H, ga.B = B, ga.t0 = c0, ga.t1 = c1, ga.back = L - 1 - st, ga.padded = 1, ga.first = st == 0;
+    if ((rc = launch_gate(ga, N, true, s))) return rc;
+    // dW_hh += d(gh)^T h_{s-1}, db_hh += sum d(gh)   (h_{-1} = 0: bias only)
+    if ((rc = launch_wgrad(n, dgh, hprev, whh, st == 0, grads, c0, c1, s))) return rc;
+    if (st > 0) {
+      DenseArgs a;   // d(h_{s-1}) += d(gh) W_hh
+      memset(&a, 0, sizeof(a));
+      fill_dense_w(n, a, params, whh, 1);
+      a.out_dim = H;
+      a.x = dgh, a.y = make_view(dh_nxt, H * NB, -c0, N, H, B), a.epilogue = kEpiAccum, a.t0 = c0, a.t1 = c1;
+      if ((rc = launch_dense(n, a, 3 * H, s))) return rc;
+    }
+    std::swap(dh_cur, dh_nxt);
+  }
+  // dW_ih = d(gi)^T x over every observation the chunk touched (zero observations before t = 0 feed b_ih only)
+  Wt wih{&n->o_wih, &n->o_bih, &n->in_dim, 0, 3 * H};
+  return launch_wgrad(n, dgi, xin, wih, false, grads, c0 - halo, c1, s);
+}
+
+// ================================================================================================
+// C ABI
+// ================================================================================================
+extern "C" int d2d_net_create(const d2d_net_config* cfg, d2d_net** out) {
+  D2D_REQUIRE(cfg && out, "d2d_net_create: null argument");
+  *out = nullptr;
+  D2D_REQUIRE(cfg->arch == D2D_NET_MLP || cfg->arch == D2D_NET_GRU, "d2d_net_create: unknown arch");
+  D2D_REQUIRE(cfg->out_kind >= 0 && cfg->out_kind <= 2, "d2d_net_create: unknown out_kind");
+  D2D_REQUIRE(cfg->n_agents >= 1 && cfg->n_agents <= D2D_MAX_AGENTS, "d2d_net_create: n_agents out of range");
+  D2D_REQUIRE(cfg->n_envs >= 1, "d2d_net_create: n_envs must be positive");
+  D2D_REQUIRE(cfg->hidden >= 1 && cfg->hidden <= 64, "d2d_net_create: hidden size %d not in 1..64 (this build)",
+              cfg->hidden);
+  D2D_REQUIRE(cfg->n_out >= 1 && cfg->n_out <= kMaxOut, "d2d_net_create: n_out not in 1..%d", kMaxOut);
+  D2D_REQUIRE(cfg->arch == D2D_NET_MLP || (cfg->history_len >= 1 && cfg->history_len <= 64),
+              "d2d_net_create: history_len out of range");
+  D2D_REQUIRE(cfg->in_dim && cfg->in_off, "d2d_net_create: null in_dim / in_off");
+  d2d_net* n = new (std::nothrow) d2d_net();
+  D2D_REQUIRE(n, "d2d_net_create: out of host memory");
+  n->arch = cfg->arch, n->out_kind = cfg->out_kind, n->N = cfg->n_agents, n->B = cfg->n_envs, n->H = cfg->hidden;
+  n->O = cfg->n_out, n->L = cfg->arch == D2D_NET_GRU ? cfg->history_len : 1, n->in_rows = cfg->in_rows;
+  n->scratch_bytes = cfg->scratch_bytes > 0 ? cfg->scratch_bytes : (2ll << 30);
+  n->max_in = 0, n->stride = 0;
+  const int H = n->H, O = n->O;
+  for (int g = 0; g < n->N; ++g) {
+    const int I = cfg->in_dim[g];
+    if (I < 1 || I > 128 || cfg->in_off[g] < 0 || cfg->in_off[g] + I > cfg->in_rows) {
+      set_error("d2d_net_create: agent %d input rows [%d, %d) invalid (in_rows %d, max 128 inputs)", g,
+                cfg->in_off[g], cfg->in_off[g] + I, cfg->in_rows);
+      delete n;
+      return D2D_ERR_INVALID;
+    }
+    n->in_dim.push_back(I), n->in_off.push_back(cfg->in_off[g]);
+    n->max_in = std::max(n->max_in, I);
+    int o = 0;
+    if (n->arch == D2D_NET_GRU) {
+      n->o_wih.push_back(o), o += 3 * H * I;
+      n->o_whh.push_back(o), o += 3 * H * H;
+      n->o_bih.push_back(o), o += 3 * H;
+      n->o_bhh.push_back(o), o += 3 * H;
+      n->o_w1.push_back(o), o += H * H;
+    } else {
+      n->o_w1.push_back(o), o += H * I;
+    }
+    n->o_b1.push_back(o), o += H;
+    n->o_w2.push_back(o), o += O * H;
+    n->o_b2.push_back(o), o += O;
+    n->stride = std::max<long long>(n->stride, o);
+  }
+  n->n_strips = 64;
+  n->part_stride = (long long)std::max(3 * H, std::max(H, O)) * std::max(n->max_in, 3 * H) + 3 * H + 64;
+  cudaError_t e = cudaMalloc((void**)&n->partial, (size_t)n->N * n->n_strips * n->part_stride * 4);
+  if (e != cudaSuccess) {
+    set_error("d2d_net_create: cudaMalloc failed: %s", cudaGetErrorString(e));
+    delete n;
+    return D2D_ERR_CUDA;
+  }
+  *out = n;
+  return D2D_OK;
+}
+
+extern "C" int d2d_net_destroy(d2d_net* n) {
+  if (!n) return D2D_OK;
+  cudaFree(n->scratch), cudaFree(n->partial);
+  delete n;
+  return D2D_OK;
+}
+extern "C" int64_t d2d_net_param_stride(const d2d_net* n) { return n ? n->stride : D2D_ERR_INVALID; }
+extern "C" int d2d_net_num_tensors(const d2d_net* n) { return n ? (n->arch == D2D_NET_GRU ? 8 : 4) : D2D_ERR_INVALID; }
+extern "C" int d2d_net_tensor(const d2d_net* n, int g, int index, int64_t* offset, int32_t* rows, int32_t* cols) {
+  D2D_REQUIRE(n && offset && rows && cols && g >= 0 && g < n->N, "d2d_net_tensor: bad argument");
+  const int H = n->H, O = n->O, I = n->in_dim[g];
+  if (n->arch == D2D_NET_GRU) {
+    // state_dict order: weight_ih, weight_hh, bias_ih, bias_hh, layers.0.weight, layers.0.bias, layers.2.weight, .bias
+    const int off[8] = {n->o_wih[g], n->o_whh[g], n->o_bih[g], n->o_bhh[g], n->o_w1[g], n->o_b1[g], n->o_w2[g], n->o_b2[g]};
+    const int r[8] = {3 * H, 3 * H, 3 * H, 3 * H, H, H, O, O};
+    const int c[8] = {I, H, 1, 1, H, 1, H, 1};
+    D2D_REQUIRE(index >= 0 && index < 8, "d2d_net_tensor: index out of range");
+    *offset = off[index], *rows = r[index], *cols = c[index];
+  } else {
+    const int off[4] = {n->o_w1[g], n->o_b1[g], n->o_w2[g], n->o_b2[g]};
+    const int r[4] = {H, H, O, O};
+    const int c[4] = {I, 1, H, 1};
+    D2D_REQUIRE(index >= 0 && index < 4, "d2d_net_tensor: index out of range");
+    *offset = off[index], *rows = r[index], *cols = c[index];
+  }
+  return D2D_OK;
+}
+
+static int check_range(const d2d_net* n, int x_lead, int t0, int t1, const char* who) {
+  D2D_REQUIRE(t0 >= 0 && t1 > t0, "%s: empty or negative time range [%d, %d)", who, t0, t1);
+  D2D_REQUIRE(n->arch == D2D_NET_MLP || x_lead >= n->L - 1,
+              "%s: GRU inputs need x_lead >= history_len - 1 zero blocks before time 0", who);
+  D2D_REQUIRE(x_lead >= 0, "%s: negative x_lead", who);
+  return D2D_OK;
+}
+
+extern "C" int d2d_net_forward(d2d_net* n, const float* params, const float* x, int x_lead, int t0, int t1,
+                               int padded, float* out, void* stream) {
+  D2D_REQUIRE(n && params && x && out, "d2d_net_forward: null argument");
+  int rc = check_range(n, x_lead, t0, t1, "d2d_net_forward");
+  if (rc) return rc;
+  cudaStream_t s = as_stream(stream);
+  Chunk c;
+  if ((rc = plan_chunk(n, false, t1 - t0, c))) return rc;
+  const long long per_t = (long long)n->N * n->O * n->B;
+  for (int c0 = t0; c0 < t1; c0 += c.Tc) {
+    const int c1 = std::min(t1, c0 + c.Tc);
+    if ((rc = forward_chunk(n, params, x, x_lead, c0, c1, padded, false, c, s))) return rc;
+    D2D_CUDA(cudaMemcpyAsync(out + (long long)(c0 - t0) * per_t, c.logits, (size_t)(c1 - c0) * per_t * 4,
+                             cudaMemcpyDeviceToDevice, s));
+  }
+  return D2D_OK;
+}
+
+static void fill_head(HeadArgs& h, int N, int B, int O, int out_kind, int dist_kind) {
+  memset(&h, 0, sizeof(h));
+  h.A = O, h.B = B, h.n_agents = N, h.out_kind = out_kind, h.dist_kind = dist_kind;
+  h.mask_bytes = O <= 8 ? 1 : (O <= 16 ? 2 : 4);
+  h.act_t_stride = (long long)N * B;
+}
+
+extern "C" int d2d_policy_head(int N, int B, int O, int n_t, int out_kind, int dist_kind, int act_mode,
+                               const float* logits, void* actions, float* logp, float* entropy, float* probs,
+                               uint64_t seed, uint64_t env_offset, int t_abs0, void* stream) {
+  D2D_REQUIRE(logits && actions, "d2d_policy_head: null logits or actions");
+  D2D_REQUIRE(N >= 1 && N <= D2D_MAX_AGENTS && B >= 1 && O >= 1 && O <= kMaxOut && n_t >= 1,
+              "d2d_policy_head: bad shape");
+  D2D_REQUIRE(act_mode >= 0 && act_mode <= 2 && (dist_kind == 0 || dist_kind == 1) && out_kind >= 0 && out_kind <= 2,
+              "d2d_policy_head: bad mode");
+  HeadArgs h;
+  fill_head(h, N, B, O, out_kind, dist_kind);
+  h.logits = make_view(const_cast<float*>(logits), (long long)N * O * B, 0, N, O, B);
+  if (probs) h.probs = make_view(probs, (long long)N * O * B, 0, N, O, B);
+  h.t0 = 0, h.t1 = n_t, h.act_mode = act_mode, h.actions = actions, h.logp = logp, h.entropy = entropy;
+  h.k0 = (uint32_t)(seed & 0xFFFFFFFFull), h.k1 = (uint32_t)(seed >> 32), h.env_offset = (uint32_t)env_offset;
+  h.t_abs_off = t_abs0;
+  const long long rows = (long long)n_t * B;
+  policy_head_kernel<<<dim3(grid_for(rows, 128), N), 128, 0, as_stream(stream)>>>(h);
+  D2D_LAUNCHED();
+  return D2D_OK;
+}
+
+extern "C" int d2d_ppo_policy_grad(d2d_net* n, const float* params, const float* x, int x_lead, int t0, int t1,
+                                   int dist_kind, const void* actions, const float* logp_old, const float* weight,
+                                   int weight_per_agent, const int32_t* cycle, float inv_rows, float cliprange,
+                                   float beta, float* grads, double* loss_sums, float* ratio_out, void* stream) {
+  D2D_REQUIRE(n && params && x && actions && logp_old && weight && grads && loss_sums,
+              "d2d_ppo_policy_grad: null argument");
+  D2D_REQUIRE(n->out_kind != D2D_OUT_IDENTITY, "d2d_ppo_policy_grad: net has no probability output");
+  int rc = check_range(n, x_lead, t0, t1, "d2d_ppo_policy_grad");
+  if (rc) return rc;
+  cudaStream_t s = as_stream(stream);
+  Chunk c;
+  if ((rc = plan_chunk(n, true, t1 - t0, c))) return rc;
+  const long long NB = (long long)n->N * n->B;
+  for (int c0 = t0; c0 < t1; c0 += c.Tc) {
+    const int c1 = std::min(t1, c0 + c.Tc);
+    if ((rc = forward_chunk(n, params, x, x_lead, c0, c1, 1, true, c, s))) return rc;
+    HeadArgs h;
+    fill_head(h, n->N, n->B, n->O, n->out_kind, dist_kind);
+    h.logits = make_view(c.logits, n->O * NB, -c0, n->N, n->O, n->B);
+    h.dlogits = make_view(c.dl, n->O * NB, -c0, n->N, n->O, n->B);
+    h.t0 = c0, h.t1 = c1, h.actions = const_cast<void*>(actions), h.logp_old = logp_old, h.weight = weight;
+    h.weight_per_agent = weight_per_agent, h.cycle = cycle, h.ratio_out = ratio_out, h.inv_rows = inv_rows;
+    h.cliprange = cliprange, h.beta = beta, h.loss_sums = loss_sums;
+    const long long rows = (long long)(c1 - c0) * n->B;
+    ppo_dlogits_kernel<<<grid_for(rows, 128), 128, 0, s>>>(h);
+    D2D_LAUNCHED();
+    if ((rc = backward_chunk(n, params, x, x_lead, c0, c1, c, grads, s))) return rc;
+  }
+  return D2D_OK;
+}
+
+extern "C" int d2d_value_grad(d2d_net* n, const float* params, const float* x, int x_lead, int t0, int t1,
+                              int padded, const float* target, int per_agent, float inv_rows, float* grads,
+                              double* loss_sum, float* value_out, void* stream) {
+  D2D_REQUIRE(n && params && x && target && grads && loss_sum, "d2d_value_grad: null argument");
+  D2D_REQUIRE(n->O == 1 && n->out_kind == D2D_OUT_IDENTITY, "d2d_value_grad: net is not a critic (n_out 1, identity)");
+  int rc = check_range(n, x_lead, t0, t1, "d2d_value_grad");
+  if (rc) return rc;
+  D2D_REQUIRE(padded == 1 || n->arch == D2D_NET_MLP, "d2d_value_grad: GRU critics train on padded windows");
+  cudaStream_t s = as_stream(stream);
+  Chunk c;
+  if ((rc = plan_chunk(n, true, t1 - t0, c))) return rc;
+  const long long NB = (long long)n->N * n->B;
+  for (int c0 = t0; c0 < t1; c0 += c.Tc) {
+    const int c1 = std::min(t1, c0 + c.Tc);
+    if ((rc = forward_chunk(n, params, x, x_lead, c0, c1, 1, true, c, s))) return rc;
+    MseArgs m;
+    memset(&m, 0, sizeof(m));
+    m.value = make_view(c.logits, NB, -c0, n->N, 1, n->B);
+    m.dvalue = make_view(c.dl, NB, -c0, n->N, 1, n->B);
+    m.target = target, m.per_agent = per_agent, m.tgt_t_stride = per_agent ? NB : n->B, m.tgt_t_off = 0;
+    m.B = n->B, m.t0 = c0, m.t1 = c1, m.inv_rows = inv_rows, m.loss_sum = loss_sum;
+    m.value_out = value_out, m.out_t_stride = NB;
+    const long long rows = (long long)(c1 - c0) * n->B;
+    mse_dvalue_kernel<<<dim3(grid_for(rows, 128), n->N), 128, 0, s>>>(m);
+    D2D_LAUNCHED();
+    if ((rc = backward_chunk(n, params, x, x_lead, c0, c1, c, grads, s))) return rc;
+  }
+  return D2D_OK;
+}
+
+extern "C" int d2d_adam_step(float* params, float* m, float* v, const float* grads, int N, int64_t per_agent,
+                             float lr, int step, float max_norm, double* sqnorm, void* stream) {
+  D2D_REQUIRE(params && m && v && grads && N >= 1 && per_agent >= 1 && step >= 1, "d2d_adam_step: bad argument");
+  D2D_REQUIRE(max_norm <= 0.f || sqnorm, "d2d_adam_step: clipping needs the sqnorm scratch buffer");
+  cudaStream_t s = as_stream(stream);
+  const int gx = grid_for(per_agent, 256);
+  if (max_norm > 0.f) {
+    D2D_CUDA(cudaMemsetAsync(sqnorm, 0, sizeof(double) * N, s));
+    grad_sqnorm_kernel<<<dim3(gx, N), 256, 0, s>>>(grads, per_agent, sqnorm);
+    D2D_LAUNCHED();
+  }
+  AdamArgs a;
+  a.p = params, a.m = m, a.v = v, a.g = grads, a.sqnorm = max_norm > 0.f ? sqnorm : nullptr;
+  a.per_agent = per_agent, a.lr = lr, a.beta1 = 0.9f, a.beta2 = 0.999f, a.eps = 1e-8f, a.max_norm = max_norm;
+  a.bc1 = (float)(1.0 - pow(0.9, (double)step));
+  a.bc2 = (float)(1.0 - pow(0.999, (double)step));
+  adam_kernel<<<dim3(gx, N), 256, 0, s>>>(a);
+  D2D_LAUNCHED();
+  return D2D_OK;
+}
+
+extern "C" int d2d_returns_scan(const int32_t* reward, const float* value, double* adv_raw, double* ret_raw,
+                                double* stats, int T, int B, int n_cols, double gamma, double lam, int last_shard,
+                                void* stream) {
+  D2D_REQUIRE(reward && stats && T >= 1 && B >= 1 && n_cols >= 1 && n_cols <= D2D_MAX_AGENTS,
+              "d2d_returns_scan: bad argument");
+  D2D_REQUIRE(!adv_raw || value, "d2d_returns_scan: lambda-returns need values");
+  ScanArgs a;
+  memset(&a, 0, sizeof(a));
+  a.reward_i = reward, a.value = value, a.adv_raw = adv_raw, a.ret_raw = ret_raw, a.stats = stats;
+  a.T = T, a.B = B, a.n_cols = n_cols, a.gamma = gamma, a.lam = lam, a.last_env_is_global_last = last_shard;
+  returns_scan_kernel<<<dim3(grid_for(B, 128), n_cols), 128, 0, as_stream(stream)>>>(a);
+  D2D_LAUNCHED();
+  return D2D_OK;
+}
+
+extern "C" int d2d_normalize(const double* raw, float* out, const double* mean, const double* std,
+                             const int32_t* do_norm, int fp32_math, int T, int B, int n_cols, void* stream) {
+  D2D_REQUIRE(raw && out && mean && std && do_norm, "d2d_normalize: null argument");
+  NormArgs a;
+  a.raw = raw, a.out = out, a.mean = mean, a.std = std, a.do_norm = do_norm, a.fp32_math = fp32_math;
+  a.per_t = (long long)n_cols * B, a.B = B, a.n = (long long)T * n_cols * B;
+  normalize_kernel<<<grid_for(a.n, 256), 256, 0, as_stream(stream)>>>(a);
+  D2D_LAUNCHED();
+  return D2D_OK;
+}

@@ -1,0 +1,219 @@
+// Device kernels of the PPO / IPPO learner: per-agent networks evaluated for all N agents in one launch.
+//
+// Data layout ("env-minor", as everywhere in this library): an activation matrix is stored as
+//   A[time block t][feature row f][env b]   with b fastest,
+// so a warp of 32 consecutive envs reads / writes 32 consecutive floats for any (t, f).  Agent g's features
+// start at row f_off[g] of a time block.  Every thread owns ONE row (t, b) of ONE agent: all per-row work
+// (dot products against weights broadcast from shared memory, gate maths, distribution maths) needs no
+// cross-thread traffic; only the weight gradients reduce over rows (wgrad_kernel).
+//
+// The B*N-row "MLP" of the north_star is N grouped GEMMs with K in {30, 64, 119} and fp32 parity at 1e-5, so this
+// first implementation runs them as FP32 FMA on the CUDA cores (see DESIGN.md section 6 for the tcgen05 plan).
+#pragma once
+#include "common.cuh"
+#include "philox.cuh"
+
+namespace d2d {
+
+constexpr int kRowsPerBlock = 128;
+
+struct View {
+  float* p;
+  long long t_stride;  // floats between consecutive time blocks
+  int t_off;           // added to the time index (window shifts / halos)
+  int f_off[D2D_MAX_AGENTS];
+};
+
+__device__ __forceinline__ float* view_ptr(const View& v, int g, int t, int B, int b) {
+  return v.p + (long long)(t + v.t_off) * v.t_stride + (long long)v.f_off[g] * B + b;
+}
+
+// ------------------------------------------------------------------------------------------------
+// dense: y[out][row] = epilogue( sum_in x[in][row] * M[in][out] + bias[out] )
+//   trans = 0: M[in][out] = W[out][in]  (forward,   W stored [out_dim][in_dim], row length w_ld)
+//   trans = 1: M[in][out] = W[in][out]  (backward-data through W stored [in_dim][out_dim], row length w_ld)
+// ------------------------------------------------------------------------------------------------
+enum { kEpiNone = 0, kEpiRelu = 1, kEpiAccum = 2, kEpiReluBwd = 3 };
+
+struct DenseArgs {
+  View x, y, aux;
+  const float* w;
+  long long w_agent_stride;
+  int w_off[D2D_MAX_AGENTS];
+  int b_off[D2D_MAX_AGENTS];  // < 0: no bias
+  int in_dim[D2D_MAX_AGENTS];
+  int w_ld[D2D_MAX_AGENTS];
+  int out_dim;
+  int trans;
+  int epilogue;
+  int B, t0, t1;
+};
+
+template <int OC>  // outputs accumulated per pass (registers per thread)
+__global__ void __launch_bounds__(kRowsPerBlock) dense_kernel(const DenseArgs a) {
+  extern __shared__ __align__(16) float sm[];
+  const int g = blockIdx.y;
+  const int in_dim = a.in_dim[g], out_dim = a.out_dim;
+  const int out_pad = (out_dim + OC - 1) / OC * OC;
+  float* Ms = sm;                      // [in_dim][out_pad]
+  float* bs = sm + in_dim * out_pad;   // [out_pad]
+  const float* W = a.w + g * a.w_agent_stride + a.w_off[g];
+  const int ld = a.w_ld[g];
+  for (int i = threadIdx.x; i < in_dim * out_pad; i += blockDim.x) {
+    const int in = i / out_pad, o = i % out_pad;
+    float v = 0.f;
+    if (o < out_dim) v = a.trans ? W[(long long)in * ld + o] : W[(long long)o * ld + in];
+    Ms[i] = v;
+  }
+  for (int o = threadIdx.x; o < out_pad; o += blockDim.x)
+    bs[o] = (o < out_dim && a.b_off[g] >= 0) ? a.w[g * a.w_agent_stride + a.b_off[g] + o] : 0.f;
+  __syncthreads();
+
+  const int tiles_per_t = (a.B + kRowsPerBlock - 1) / kRowsPerBlock;
+  const int n_tiles = (a.t1 - a.t0) * tiles_per_t;
+  for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    const int t = a.t0 + tile / tiles_per_t;
+    const int b = (tile % tiles_per_t) * kRowsPerBlock + threadIdx.x;
+    if (b >= a.B) continue;
+    const float* xp = view_ptr(a.x, g, t, a.B, b);
+    float* yp = view_ptr(a.y, g, t, a.B, b);
+    const float* ap = a.epilogue == kEpiReluBwd ? view_ptr(a.aux, g, t, a.B, b) : nullptr;
+    for (int o0 = 0; o0 < out_dim; o0 += OC) {
+      float acc[OC];
+#pragma unroll
+      for (int j = 0; j < OC; ++j) acc[j] = bs[o0 + j];
+      const float* mrow = Ms + o0;
+#pragma unroll 4
+      for (int in = 0; in < in_dim; ++in) {
+        const float xv = xp[(long long)in * a.B];
+        const float4* m4 = reinterpret_cast<const float4*>(mrow + in * out_pad);
+#pragma unroll
+        for (int j = 0; j < OC / 4; ++j) {
+          const float4 m = m4[j];
+          acc[4 * j + 0] = fmaf(xv, m.x, acc[4 * j + 0]);
+          acc[4 * j + 1] = fmaf(xv, m.y, acc[4 * j + 1]);
+          acc[4 * j + 2] = fmaf(xv, m.z, acc[4 * j + 2]);
+          acc[4 * j + 3] = fmaf(xv, m.w, acc[4 * j + 3]);
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < OC; ++j) {
+        const int o = o0 + j;
+        if (o < out_dim) {
+          float v = acc[j];
+          float* q = yp + (long long)o * a.B;
+          if (a.epilogue == kEpiRelu) v = fmaxf(v, 0.f);
+          else if (a.epilogue == kEpiAccum) v += *q;
+          else if (a.epilogue == kEpiReluBwd) v = ap[(long long)o * a.B] > 0.f ? v : 0.f;
+          *q = v;
+        }
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// weight gradient: dW[o][k] (+ db[o]) = sum over rows of dy[o][row] * x[k][row]   (partial sums per row strip)
+// ------------------------------------------------------------------------------------------------
+struct WgradArgs {
+  View dy, x;
+  float* partial;              // [N][n_strips][part_stride]
+  long long part_stride;       // >= out_dim * max_in + out_dim
+  int in_dim[D2D_MAX_AGENTS];
+  int out_dim;
+  int B, t0, t1;
+  int with_bias;
+};
+
+constexpr int kWgRows = 32;  // rows staged per iteration
+
+template <int TO, int TK>    // each of the 16 x 16 threads owns outputs o = ty + 16 i (i < TO), k = tx + 16 j (j < TK)
+__global__ void __launch_bounds__(256) wgrad_kernel(const WgradArgs a) {
+  extern __shared__ __align__(16) float sm[];
+  const int g = blockIdx.y, strip = blockIdx.x, n_strips = gridDim.x;
+  const int K = a.in_dim[g], O = a.out_dim;
+  constexpr int LD = kWgRows + 1;
+  float* dys = sm;                 // [16 * TO][LD]
+  float* xs = sm + 16 * TO * LD;   // [16 * TK][LD]
+  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+  float acc[TO][TK];
+  float accb[TO];
+#pragma unroll
+  for (int i = 0; i < TO; ++i) {
+    accb[i] = 0.f;
+#pragma unroll
+    for (int j = 0; j < TK; ++j) acc[i][j] = 0.f;
+  }
+  const int chunks_per_t = (a.B + kWgRows - 1) / kWgRows;
+  const long long n_chunks = (long long)(a.t1 - a.t0) * chunks_per_t;
+  for (long long c = strip; c < n_chunks; c += n_strips) {
+    const int t = a.t0 + (int)(c / chunks_per_t);
+    const int b0 = (int)(c % chunks_per_t) * kWgRows;
+    __syncthreads();
+    for (int i = threadIdx.x; i < 16 * TO * kWgRows; i += 256) {
+      const int o = i / kWgRows, r = i % kWgRows;
+      dys[o * LD + r] = (o < O && b0 + r < a.B) ? view_ptr(a.dy, g, t, a.B, b0 + r)[(long long)o * a.B] : 0.f;
+    }
+    for (int i = threadIdx.x; i < 16 * TK * kWgRows; i += 256) {
+      const int k = i / kWgRows, r = i % kWgRows;
+      xs[k * LD + r] = (k < K && b0 + r < a.B) ? view_ptr(a.x, g, t, a.B, b0 + r)[(long long)k * a.B] : 0.f;
+    }
+    __syncthreads();
+#pragma unroll 4
+    for (int r = 0; r < kWgRows; ++r) {
+      float dv[TO], xv[TK];
+#pragma unroll
+      for (int i = 0; i < TO; ++i) dv[i] = dys[(ty + 16 * i) * LD + r];
+#pragma unroll
+      for (int j = 0; j < TK; ++j) xv[j] = xs[(tx + 16 * j) * LD + r];
+#pragma unroll
+      for (int i = 0; i < TO; ++i) {
+        accb[i] += dv[i];
+#pragma unroll
+        for (int j = 0; j < TK; ++j) acc[i][j] = fmaf(dv[i], xv[j], acc[i][j]);
+      }
+    }
+  }
+  float* out = a.partial + ((long long)g * n_strips + strip) * a.part_stride;
+#pragma unroll
+  for (int i = 0; i < TO; ++i) {
+    const int o = ty + 16 * i;
+    if (o < O) {
+#pragma unroll
+      for (int j = 0; j < TK; ++j) {
+        const int k = tx + 16 * j;
+        if (k < K) out[(long long)o * K + k] = acc[i][j];
+      }
+      if (a.with_bias && tx == 0) out[(long long)O * K + o] = accb[i];
+    }
+  }
+}
+
+// grads[g][w_off + i] += sum_strips partial[g][s][i]  (fixed order: deterministic)
+struct WreduceArgs {
+  const float* partial;
+  long long part_stride;
+  int n_strips;
+  float* grads;
+  long long g_agent_stride;
+  int w_off[D2D_MAX_AGENTS];
+  int b_off[D2D_MAX_AGENTS];
+  int in_dim[D2D_MAX_AGENTS];
+  int out_dim;
+  int with_bias;
+};
+
+__global__ void wreduce_kernel(const WreduceArgs a) {
+  const int g = blockIdx.y;
+  const int nw = a.out_dim * a.in_dim[g];
+  const int n = nw + (a.with_bias ? a.out_dim : 0);
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    float s = 0.f;
+    const float* p = a.partial + (long long)g * a.n_strips * a.part_stride + i;
+    for (int k = 0; k < a.n_strips; ++k) s += p[(long long)k * a.part_stride];
+    float* dst = a.grads + g * a.g_agent_stride + (i < nw ? a.w_off[g] + i : a.b_off[g] + (i - nw));
+    *dst += s;
+  }
+}
+
+}  // namespace d2d

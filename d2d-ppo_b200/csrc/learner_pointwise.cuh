@@ -1,0 +1,495 @@
+// Row-wise (pointwise) kernels of the learner: GRU gates, distribution heads, PPO loss derivatives,
+// lambda-return / discounted-return scans, normalisation, Adam.  One thread per (agent, time, env) row.
+#pragma once
+#include "learner_kernels.cuh"
+
+namespace d2d {
+
+__device__ __forceinline__ float sigmoidf_(float x) { return 1.0f / (1.0f + expf(-x)); }
+
+// ------------------------------------------------------------------------------------------------
+// GRU cell, torch gate order (r, z, n):  r = s(gi_r + gh_r), z = s(gi_z + gh_z), n = tanh(gi_n + r * gh_n),
+// h' = (1 - z) n + z h        (nn.GRU; reference d2d_ppo.py:30,52)
+// ------------------------------------------------------------------------------------------------
+struct GateArgs {
+  View gi;      // [.. 3H ..] input projections of the observation at time t - back (view.t_off = -back + halo)
+  View gh;      // [.. 3H ..] hidden projections of this step (forward) / d(gh) (backward out)
+  View h_prev;  // [.. H ..]  (forward in; backward in)
+  View h_out;   // [.. H ..]  forward: h'; backward: d(h_prev) out
+  View acts;    // [.. 4H ..] stored r, z, n, gh_n (forward out if store; backward in)
+  View dh;      // backward in: d(h')
+  View dgi;     // backward: accumulated into (same time shift as gi)
+  int H, B, t0, t1;
+  int back;       // this step looks `back` observations into the past
+  int padded;     // 1: observations before the episode start are zero INPUTS that still run (training windows)
+                  // 0: those steps do not exist (rollout windows): h' = h
+  int first;      // 1: h_prev is the zero initial state (not read)
+  int store;      // forward: write acts
+  int t_episode0; // absolute time index of the episode's first observation in units of this call's t (usually 0)
+};
+
+__global__ void gru_gate_fwd_kernel(const GateArgs a) {
+  const int g = blockIdx.y, H = a.H;
+  const long long per_t = (long long)H * a.B;
+  const long long n = (long long)(a.t1 - a.t0) * per_t;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const int t = a.t0 + (int)(i / per_t);
+    const int u = (int)((i % per_t) / a.B), b = (int)(i % a.B);
+    const long long uB = (long long)u * a.B, HB = per_t;
+    const float hp = a.first ? 0.f : view_ptr(a.h_prev, g, t, a.B, b)[uB];
+    float* ho = view_ptr(a.h_out, g, t, a.B, b) + uB;
+    const bool exists = a.padded || (t - a.back >= a.t_episode0);
+    if (!exists) {
+      *ho = hp;
+      continue;
+    }
+    const float* gi = view_ptr(a.gi, g, t, a.B, b) + uB;
+    const float* gh = view_ptr(a.gh, g, t, a.B, b) + uB;
+    const float ghn = gh[2 * HB];
+    const float r = sigmoidf_(gi[0] + gh[0]);
+    const float z = sigmoidf_(gi[HB] + gh[HB]);
+    const float nn = tanhf(gi[2 * HB] + r * ghn);
+    *ho = (1.0f - z) * nn + z * hp;
+    if (a.store) {
+      float* ac = view_ptr(a.acts, g, t, a.B, b) + uB;
+      ac[0] = r, ac[HB] = z, ac[2 * HB] = nn, ac[3 * HB] = ghn;
+    }
+  }
+}
+
+// backward of one (always existing: training windows are padded) GRU step
+__global__ void gru_gate_bwd_kernel(const GateArgs a) {
+  const int g = blockIdx.y, H = a.H;
+  const long long per_t = (long long)H * a.B;
+  const long long n = (long long)(a.t1 - a.t0) * per_t;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const int t = a.t0 + (int)(i / per_t);
+    const int u = (int)((i % per_t) / a.B), b = (int)(i % a.B);
+    const long long uB = (long long)u * a.B, HB = per_t;
+    const float* ac = view_ptr(a.acts, g, t, a.B, b) + uB;
+    const float r = ac[0], z = ac[HB], nn = ac[2 * HB], ghn = ac[3 * HB];
+    const float hp = a.first ? 0.f : view_ptr(a.h_prev, g, t, a.B, b)[uB];
+    const float dh = view_ptr(a.dh, g, t, a.B, b)[uB];
+    const float dn = dh * (1.0f - z) * (1.0f - nn * nn);   // through tanh
+    const float dz = dh * (hp - nn) * z * (1.0f - z);      // through sigmoid
+    const float dr = dn * ghn * r * (1.0f - r);
+    float* dgh = view_ptr(a.gh, g, t, a.B, b) + uB;
+    dgh[0] = dr, dgh[HB] = dz, dgh[2 * HB] = dn * r;
+    float* dgi = view_ptr(a.dgi, g, t, a.B, b) + uB;       // several windows share an observation: accumulate
+    dgi[0] += dr, dgi[HB] += dz, dgi[2 * HB] += dn;
+    view_ptr(a.h_out, g, t, a.B, b)[uB] = dh * z;          // direct path; dense_kernel adds d(gh) W_hh on top
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// policy head: probabilities -> actions / log-prob / entropy, and the PPO surrogate derivative
+// torch.distributions numerics (Bernoulli / Categorical built from `probs`), reference d2d_ppo.py:159-196
+// ------------------------------------------------------------------------------------------------
+enum { kOutSoftmax = 0, kOutSigmoid = 1, kOutIdentity = 2 };
+enum { kDistBernoulli = 0, kDistCategorical = 1 };
+enum { kActSample = 0, kActGreedy = 1, kActGiven = 2 };
+constexpr int kMaxOut = 32;
+constexpr float kProbEps = 1.1920928955078125e-07f;  // torch.finfo(float32).eps
+
+struct HeadArgs {
+  View logits;           // [.. A ..] pre-activation outputs of the last Linear
+  View probs;            // optional out [.. A ..] (p == nullptr: not written)
+  int A, B, t0, t1, n_agents;
+  int out_kind, dist_kind, act_mode;
+  // actions: Bernoulli -> channel bitmask (mask_bytes per element), Categorical -> u8 index;  layout [t][N][B]
+  void* actions;
+  int mask_bytes;
+  long long act_t_stride;   // elements between time blocks (N * B)
+  int act_t_off;
+  float* logp;              // [t][N][B] (same strides as actions)
+  float* entropy;           // may be null
+  uint32_t k0, k1, env_offset;
+  int t_abs_off;            // Philox timestep = t + t_abs_off
+  // ---- loss / backward (ppo_dlogits_kernel) ----
+  const float* logp_old;    // [t][N][B]
+  const float* weight;      // per-row weight (advantage or HAPPO M): [t][N][B] if weight_per_agent else [t][B]
+  int weight_per_agent;
+  const int* cycle;         // HAPPO order (device, [N]) or null
+  float* ratio_out;         // optional [t][N][B]
+  View dlogits;             // out
+  float inv_rows;           // 1 / R_total
+  float cliprange, beta;
+  double* loss_sums;        // [N][2]: sum over rows of min(surr1, surr2), sum of entropy
+};
+
+__device__ __forceinline__ void head_probs(const HeadArgs& a, const float* lg, long long sB, float* p) {
+  if (a.out_kind == kOutSigmoid) {
+    for (int j = 0; j < a.A; ++j) p[j] = sigmoidf_(lg[j * sB]);
+  } else if (a.out_kind == kOutSoftmax) {
+    float m = -INFINITY;
+    for (int j = 0; j < a.A; ++j) m = fmaxf(m, lg[j * sB]);
+    float s = 0.f;
+    for (int j = 0; j < a.A; ++j) {
+      p[j] = expf(lg[j * sB] - m);
+      s += p[j];
+    }
+    for (int j = 0; j < a.A; ++j) p[j] = p[j] / s;
+  } else {
+    for (int j = 0; j < a.A; ++j) p[j] = lg[j * sB];
+  }
+}
+
+__device__ __forceinline__ float clamp_prob(float p) { return fminf(fmaxf(p, kProbEps), 1.0f - kProbEps); }
+// ATen binary_cross_entropy_with_logits: (1 - y) x - log_sigmoid(x), log_sigmoid(x) = min(x, 0) - log1p(exp(-|x|))
+__device__ __forceinline__ float bce_logits(float x, float y) {
+  return (1.0f - y) * x - (fminf(x, 0.f) - log1pf(expf(-fabsf(x))));
+}
+
+__device__ __forceinline__ uint32_t load_action(const HeadArgs& a, long long idx) {
+  if (a.dist_kind == kDistCategorical || a.mask_bytes == 1) return reinterpret_cast<const uint8_t*>(a.actions)[idx];
+  if (a.mask_bytes == 2) return reinterpret_cast<const uint16_t*>(a.actions)[idx];
+  return reinterpret_cast<const uint32_t*>(a.actions)[idx];
+}
+__device__ __forceinline__ void store_action(const HeadArgs& a, long long idx, uint32_t v) {
+  if (a.dist_kind == kDistCategorical || a.mask_bytes == 1) reinterpret_cast<uint8_t*>(a.actions)[idx] = (uint8_t)v;
+  else if (a.mask_bytes == 2) reinterpret_cast<uint16_t*>(a.actions)[idx] = (uint16_t)v;
+  else reinterpret_cast<uint32_t*>(a.actions)[idx] = v;
+}
+
+// log-prob and entropy of action `act` under probs p (registers)
+__device__ __forceinline__ void dist_logp_entropy(const HeadArgs& a, const float* p, uint32_t act, float& logp,
+                                                  float& ent) {
+  if (a.dist_kind == kDistBernoulli) {
+    float sl = 0.f, se = 0.f;
+    for (int j = 0; j < a.A; ++j) {
+      const float pc = clamp_prob(p[j]);
+      const float l = logf(pc) - log1pf(-pc);
+      sl += -bce_logits(l, (float)((act >> j) & 1u));
+      se += bce_logits(l, p[j]);
+    }
+    logp = sl / (float)a.A;   // .mean(-1) over channels, d2d_ppo.py:168-169
+    ent = se / (float)a.A;
+  } else {
+    float s = 0.f;
+    for (int j = 0; j < a.A; ++j) s += p[j];
+    float e = 0.f;
+    logp = 0.f;
+    for (int j = 0; j < a.A; ++j) {
+      const float pn = p[j] / s;
+      const float l = logf(clamp_prob(pn));
+      if ((uint32_t)j == act) logp = l;
+      e += l * pn;
+    }
+    ent = -e;
+  }
+}
+
+// act_mode sample / greedy / given -> actions, logp, entropy (rollout: select_action; training: evaluate)
+__global__ void policy_head_kernel(const HeadArgs a) {
+  const int g = blockIdx.y;
+  const long long n = (long long)(a.t1 - a.t0) * a.B;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const int t = a.t0 + (int)(i / a.B), b = (int)(i % a.B);
+    const float* lg = view_ptr(a.logits, g, t, a.B, b);
+    float p[kMaxOut];
+    head_probs(a, lg, a.B, p);
+    if (a.probs.p) {
+      float* q = view_ptr(a.probs, g, t, a.B, b);
+      for (int j = 0; j < a.A; ++j) q[(long long)j * a.B] = p[j];
+    }
+    const long long idx = (long long)(t + a.act_t_off) * a.act_t_stride + (long long)g * a.B + b;
+    uint32_t act = 0;
+    if (a.act_mode == kActGiven) {
+      act = load_action(a, idx);
+    } else {
+      if (a.dist_kind == kDistBernoulli) {
+        if (a.act_mode == kActGreedy) {
+          for (int j = 0; j < a.A; ++j) act |= (uint32_t)(p[j] > 0.5f) << j;      // d2d_ppo.py:166
+        } else {
+          for (int blk = 0; blk * 4 < a.A; ++blk) {
+            const uint4 r = philox4x32_10(a.env_offset + (uint32_t)b, (uint32_t)(t + a.t_abs_off),
+                                          (uint32_t)g | (kPurposePolicy << 16), (uint32_t)blk, a.k0, a.k1);
+            const uint32_t u[4] = {r.x, r.y, r.z, r.w};
+            for (int l = 0; l < 4 && blk * 4 + l < a.A; ++l) {
+              const int j = blk * 4 + l;
+              const double thr = (double)p[j] * 4294967296.0;          // P(u32 < thr) = p at 2^-32 resolution
+              act |= (uint32_t)((double)u[l] < thr) << j;
+            }
+          }
+        }
+      } else {
+        if (a.act_mode == kActGreedy) {
+          float best = p[0];
+          for (int j = 1; j < a.A; ++j)
+            if (p[j] > best) best = p[j], act = (uint32_t)j;            // argmax, first maximum (d2d_ppo.py:176)
+        } else {
+          const uint4 r = philox4x32_10(a.env_offset + (uint32_t)b, (uint32_t)(t + a.t_abs_off),
+                                        (uint32_t)g | (kPurposePolicy << 16), 0u, a.k0, a.k1);
+          double s = 0.0;
+          for (int j = 0; j < a.A; ++j) s += (double)p[j];
+          const double uu = ((double)r.x + 0.5) * (1.0 / 4294967296.0) * s;
+          double c = 0.0;
+          act = (uint32_t)(a.A - 1);
+          for (int j = 0; j < a.A; ++j) {
+            c += (double)p[j];
+            if (uu < c) {
+              act = (uint32_t)j;
+              break;
+            }
+          }
+        }
+      }
+      store_action(a, idx, act);
+    }
+    float logp, ent;
+    dist_logp_entropy(a, p, act, logp, ent);
+    if (a.logp) a.logp[idx] = logp;
+    if (a.entropy) a.entropy[idx] = ent;
+  }
+}
+
+// d(loss)/d(logits) of  loss = -mean_rows(min(ratio w, clip(ratio) w)) - beta mean_rows(entropy)
+// (reference d2d_ppo.py:201-207, ippo.py:196-202).  One thread per (time, env) handles ALL agents so that the
+// HAPPO weight M_j = adv * prod_{i before j in cycle} ratio_i (d2d_ppo.py:427-436) is a running product.
+__global__ void ppo_dlogits_kernel(const HeadArgs a) {
+  const long long n = (long long)(a.t1 - a.t0) * a.B;
+  const long long n_round = (n + blockDim.x - 1) / blockDim.x * blockDim.x;   // whole warps stay in the loop
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n_round;
+       i += (long long)gridDim.x * blockDim.x) {
+    const bool live = i < n;
+    const long long ii = live ? i : 0;
+    const int t = a.t0 + (int)(ii / a.B), b = (int)(ii % a.B);
+    float chain = 1.0f;
+    for (int ord = 0; ord < a.n_agents; ++ord) {
+      const int g = a.cycle ? a.cycle[ord] : ord;
+      const float* lg = view_ptr(a.logits, g, t, a.B, b);
+      float p[kMaxOut];
+      head_probs(a, lg, a.B, p);
+      const long long idx = (long long)(t + a.act_t_off) * a.act_t_stride + (long long)g * a.B + b;
+      const uint32_t act = load_action(a, idx);
+      float logp, ent;
+      dist_logp_entropy(a, p, act, logp, ent);
+      const float ratio = expf(logp - a.logp_old[idx]);
+      float w = a.weight_per_agent ? a.weight[idx]
+                                   : a.weight[(long long)(t + a.act_t_off) * a.B + b];
+      if (a.cycle) {
+        w *= chain;          // M for this agent (detached)
+        chain *= ratio;      // M <- ratio * M with the PRE-update ratio
+      }
+      if (a.ratio_out && live) a.ratio_out[idx] = ratio;
+      const float lo = 1.0f - a.cliprange, hi = 1.0f + a.cliprange;
+      const float surr1 = ratio * w, surr2 = fminf(fmaxf(ratio, lo), hi) * w;
+      // torch.min splits the gradient on ties (ratio inside the clip range: surr1 == surr2, both paths carry w)
+      const float dratio = (ratio >= lo && ratio <= hi) ? w : (surr1 < surr2 ? w : 0.f);
+      const float dlogp = -a.inv_rows * dratio * ratio;
+      const float dent = -a.inv_rows * a.beta;
+      double s0 = live ? (double)fminf(surr1, surr2) : 0.0, s1 = live ? (double)ent : 0.0;
+      for (int o = 16; o > 0; o >>= 1) {
+        s0 += __shfl_down_sync(0xFFFFFFFFu, s0, o);
+        s1 += __shfl_down_sync(0xFFFFFFFFu, s1, o);
+      }
+      if ((threadIdx.x & 31) == 0) {
+        atomicAdd(&a.loss_sums[2 * g], s0);
+        atomicAdd(&a.loss_sums[2 * g + 1], s1);
+      }
+      if (!live) continue;
+      // ---- d/dp, then through the output activation ----
+      float dp[kMaxOut];
+      if (a.dist_kind == kDistBernoulli) {
+        for (int j = 0; j < a.A; ++j) {
+          const float pc = clamp_prob(p[j]);
+          const float l = logf(pc) - log1pf(-pc);
+          const float dl_dp = (p[j] >= kProbEps && p[j] <= 1.0f - kProbEps) ? 1.0f / (pc * (1.0f - pc)) : 0.f;
+          const float y = (float)((act >> j) & 1u);
+          // logp_j = -bce(l, y): d/dl = y - sigmoid(l) = y - pc;  ent_j = bce(l, p): d/dp = -l + (pc - p) dl/dp
+          dp[j] = (dlogp * (y - pc) * dl_dp + dent * (-l + (pc - p[j]) * dl_dp)) / (float)a.A;
+        }
+      } else {
+        float s = 0.f;
+        for (int j = 0; j < a.A; ++j) s += p[j];
+        float dpn[kMaxOut];
+        float dot = 0.f;
+        for (int j = 0; j < a.A; ++j) {
+          const float pn = p[j] / s;
+          const float pc = clamp_prob(pn);
+          const float in = (pn >= kProbEps && pn <= 1.0f - kProbEps) ? 1.0f : 0.f;
+          const float l = logf(pc);
+          // logp = l[act]; ent = -sum l pn
+          dpn[j] = ((uint32_t)j == act ? dlogp * in / pc : 0.f) + dent * (-(l + in * pn / pc));
+          dot += dpn[j] * pn;
+        }
+        for (int j = 0; j < a.A; ++j) dp[j] = (dpn[j] - dot) / s;   // through pn = p / sum(p)
+      }
+      float* dl = view_ptr(a.dlogits, g, t, a.B, b);
+      if (a.out_kind == kOutSigmoid) {
+        for (int j = 0; j < a.A; ++j) dl[(long long)j * a.B] = dp[j] * p[j] * (1.0f - p[j]);
+      } else if (a.out_kind == kOutSoftmax) {
+        float dot = 0.f;
+        for (int j = 0; j < a.A; ++j) dot += dp[j] * p[j];
+        for (int j = 0; j < a.A; ++j) dl[(long long)j * a.B] = p[j] * (dp[j] - dot);
+      } else {
+        for (int j = 0; j < a.A; ++j) dl[(long long)j * a.B] = dp[j];
+      }
+    }
+  }
+}
+
+// critic: d(mse)/d(value) = 2 (v - target) / R ; loss sum accumulated in fp64
+struct MseArgs {
+  View value;        // [.. 1 ..]
+  View dvalue;       // out
+  const float* target;   // [t][N][B] if per_agent else [t][B]
+  int per_agent;
+  long long tgt_t_stride;
+  int tgt_t_off;
+  int B, t0, t1;
+  float inv_rows;
+  double* loss_sum;  // [N]
+  float* value_out;  // optional [t][N][B] copy
+  long long out_t_stride;
+};
+
+__global__ void mse_dvalue_kernel(const MseArgs a) {
+  const int g = blockIdx.y;
+  const long long n = (long long)(a.t1 - a.t0) * a.B;
+  double local = 0.0;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const int t = a.t0 + (int)(i / a.B), b = (int)(i % a.B);
+    const float v = *view_ptr(a.value, g, t, a.B, b);
+    const long long ti = (long long)(t + a.tgt_t_off) * a.tgt_t_stride;
+    const float y = a.per_agent ? a.target[ti + (long long)g * a.B + b] : a.target[ti + b];
+    const float d = v - y;
+    *view_ptr(a.dvalue, g, t, a.B, b) = 2.0f * d * a.inv_rows;
+    local += (double)d * (double)d;
+    if (a.value_out) a.value_out[(long long)(t + a.tgt_t_off) * a.out_t_stride + (long long)g * a.B + b] = v;
+  }
+  for (int o = 16; o > 0; o >>= 1) local += __shfl_down_sync(0xFFFFFFFFu, local, o);
+  if ((threadIdx.x & 31) == 0) atomicAdd(&a.loss_sum[g], local);
+}
+
+// ------------------------------------------------------------------------------------------------
+// lambda-returns (compute_gae, d2d_ppo.py:100-110) and discounted returns (discount_rewards, :112-124)
+// One thread per (agent column, env): reverse scan over the T steps of that env's episode, in float64 as
+// the reference (numpy) does.  Rows of the reference are episode-major, so only the LAST env's final step
+// keeps the `r - v` quirk of :102; every other episode end gives out = r exactly (done zeroes the bootstrap).
+// ------------------------------------------------------------------------------------------------
+struct ScanArgs {
+  const int32_t* reward_i;   // [T][B] shared integer reward (number of successes / ack) or null
+  const float* reward_f;     // [T][N][B] per-agent float reward or null
+  const float* value;        // [T][N][B]  (N = n_cols)
+  double* adv_raw;           // [T][N][B] out (unnormalised lambda-return), may be null
+  double* ret_raw;           // [T][N][B] out (unnormalised discounted return), may be null
+  double* stats;             // [N][4]: sum adv, sumsq adv, sum ret(f32-cast), sumsq ret(f32-cast)
+  int T, B, n_cols;
+  double gamma, lam;
+  int last_env_is_global_last;  // this shard holds the globally last env (multi-GPU)
+};
+
+__global__ void returns_scan_kernel(const ScanArgs a) {
+  const int g = blockIdx.y;
+  double s_adv = 0, q_adv = 0, s_ret = 0, q_ret = 0;
+  for (int b = blockIdx.x * blockDim.x + threadIdx.x; b < a.B; b += gridDim.x * blockDim.x) {
+    double gae = 0.0, run = 0.0, v_next = 0.0;
+    for (int t = a.T - 1; t >= 0; --t) {
+      const long long idx = ((long long)t * a.n_cols + g) * a.B + b;
+      const double r = a.reward_i ? (double)a.reward_i[(long long)t * a.B + b] : (double)a.reward_f[idx];
+      if (a.adv_raw) {
+        const double v = (double)a.value[idx];
+        double out;
+        if (t == a.T - 1) {
+          // done: delta = r - v, gae = delta, out = gae + v = r;  the globally last row keeps r - v (:102)
+          const bool quirk = a.last_env_is_global_last && b == a.B - 1;
+          gae = quirk ? 0.0 : r - v;
+          out = quirk ? r - v : gae + v;
+        } else {
+          const double delta = r + a.gamma * v_next - v;
+          gae = delta + a.gamma * a.lam * gae;
+          out = gae + v;
+        }
+        v_next = v;
+        a.adv_raw[idx] = out;
+        s_adv += out, q_adv += out * out;
+      }
+      if (a.ret_raw) {
+        run = (t == a.T - 1) ? r : r + run * a.gamma;
+        a.ret_raw[idx] = run;
+        const double rf = (double)(float)run;   // the reference casts to fp32 before normalising (:119)
+        s_ret += rf, q_ret += rf * rf;
+      }
+    }
+  }
+  double vals[4] = {s_adv, q_adv, s_ret, q_ret};
+  for (int k = 0; k < 4; ++k) {
+    double v = vals[k];
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xFFFFFFFFu, v, o);
+    if ((threadIdx.x & 31) == 0 && v != 0.0) atomicAdd(&a.stats[4 * g + k], v);
+  }
+}
+
+// out = (raw - mean) / std  per column (or a plain cast when do_norm[g] == 0), written as fp32
+struct NormArgs {
+  const double* raw;   // [T][N][B]
+  float* out;          // [T][N][B]
+  const double* mean;  // [N]
+  const double* std;   // [N]
+  const int* do_norm;  // [N]
+  int fp32_math;       // 1: torch semantics of discount_rewards (cast first, normalise in fp32)
+  long long per_t;     // N * B
+  int B;
+  long long n;         // T * N * B
+};
+
+__global__ void normalize_kernel(const NormArgs a) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < a.n; i += (long long)gridDim.x * blockDim.x) {
+    const int g = (int)((i % a.per_t) / a.B);
+    if (a.fp32_math) {
+      const float x = (float)a.raw[i];
+      a.out[i] = a.do_norm[g] ? (x - (float)a.mean[g]) / (float)a.std[g] : x;
+    } else {
+      const double x = a.raw[i];
+      a.out[i] = (float)(a.do_norm[g] ? (x - a.mean[g]) / a.std[g] : x);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// optimiser: per-agent gradient norm (clip_grad_norm_, d2d_ppo.py:211,445) and torch.optim.Adam defaults
+// ------------------------------------------------------------------------------------------------
+__global__ void grad_sqnorm_kernel(const float* __restrict__ g, long long per_agent, double* __restrict__ out) {
+  const int a = blockIdx.y;
+  double s = 0.0;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < per_agent;
+       i += (long long)gridDim.x * blockDim.x) {
+    const double v = g[a * per_agent + i];
+    s += v * v;
+  }
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_down_sync(0xFFFFFFFFu, s, o);
+  if ((threadIdx.x & 31) == 0) atomicAdd(&out[a], s);
+}
+
+struct AdamArgs {
+  float* p;
+  float* m;
+  float* v;
+  const float* g;
+  const double* sqnorm;   // [N] or null (no clipping)
+  long long per_agent;
+  float lr, beta1, beta2, eps, max_norm;
+  float bc1, bc2;         // 1 - beta^t
+};
+
+__global__ void adam_kernel(const AdamArgs a) {
+  const int ag = blockIdx.y;
+  float coef = 1.0f;
+  if (a.sqnorm) {
+    const float total = (float)sqrt(a.sqnorm[ag]);
+    coef = fminf(a.max_norm / (total + 1e-6f), 1.0f);
+  }
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < a.per_agent;
+       i += (long long)gridDim.x * blockDim.x) {
+    const long long j = ag * a.per_agent + i;
+    const float g = a.g[j] * coef;
+    const float m = a.beta1 * a.m[j] + (1.0f - a.beta1) * g;
+    const float v = a.beta2 * a.v[j] + (1.0f - a.beta2) * g * g;
+    a.m[j] = m, a.v[j] = v;
+    const float denom = sqrtf(v) / sqrtf(a.bc2) + a.eps;
+    a.p[j] = a.p[j] - (a.lr / a.bc1) * (m / denom);
+  }
+}
+
+}  // namespace d2d

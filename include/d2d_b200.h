@@ -150,6 +150,112 @@ int d2d_env_import_state(d2d_env* env, const uint8_t* buffers, const void* chann
  * (combinatorial_env.py:245-264): f64 [B] each, any may be NULL. */
 int d2d_env_scores(const d2d_env* env, double* urllc, double* jains, double* channel_score, void* stream);
 
+
+/* ------------------------------------------------------------------------------------------
+ * Learner: the per-agent actor / critic networks of algorithms/d2d_ppo.py and algorithms/ippo.py, evaluated
+ * for all N agents in one launch.  All matrices are env-minor f32: M[time block][feature row][env].
+ *
+ * A "net set" is N independent networks of one architecture (the reference builds one PPO object per agent,
+ * d2d_ppo.py:252-262, ippo.py:254-264); the D2DPPO central critic (d2d_ppo.py:265) is a net set with N = 1.
+ * Parameters live in ONE caller-owned f32 buffer [N][param_stride]; inside an agent's block the tensors are
+ * stored contiguously in the reference's state_dict order, row-major as torch stores them:
+ *   GRU ("RNN", d2d_ppo.py:24-59):  lstm.weight_ih_l0 [3H, I], lstm.weight_hh_l0 [3H, H], lstm.bias_ih_l0 [3H],
+ *                                   lstm.bias_hh_l0 [3H], layers.0.weight [H, H], layers.0.bias [H],
+ *                                   layers.2.weight [O, H], layers.2.bias [O]
+ *   MLP ("Policy"/"Value", :62-98): linear1.weight [H, I], linear1.bias [H], linear2.weight [O, H], linear2.bias [O]
+ * ------------------------------------------------------------------------------------------ */
+#define D2D_NET_MLP 0
+#define D2D_NET_GRU 1
+#define D2D_OUT_SOFTMAX 0   /* Policy.forward, RNN with combinatorial=False (d2d_ppo.py:56,81) */
+#define D2D_OUT_SIGMOID 1   /* RNN with combinatorial=True (d2d_ppo.py:58)                     */
+#define D2D_OUT_IDENTITY 2  /* Value, RNN(use_activation=False) (ippo.py:46,146)               */
+#define D2D_DIST_BERNOULLI 0    /* combinatorial=True: Bernoulli(probs), mean over channels    */
+#define D2D_DIST_CATEGORICAL 1
+#define D2D_ACT_SAMPLE 0   /* select_action(train=True)  */
+#define D2D_ACT_GREEDY 1   /* select_action(train=False) */
+#define D2D_ACT_GIVEN 2    /* evaluate(states, actions)  */
+
+typedef struct d2d_net_config {
+  int32_t arch;            /* D2D_NET_*                                                         */
+  int32_t out_kind;        /* D2D_OUT_*                                                         */
+  int32_t n_agents;        /* N networks                                                        */
+  int32_t n_envs;          /* B                                                                 */
+  int32_t hidden;          /* H                                                                 */
+  int32_t n_out;           /* O: action_space[k].n for policies, 1 for critics (<= 32)          */
+  int32_t history_len;     /* L: GRU window (d2d_ppo.py:302); ignored for MLP                   */
+  int32_t in_rows;         /* feature rows per time block of the input matrix                   */
+  const int32_t* in_dim;   /* [N] host: input size of agent k                                   */
+  const int32_t* in_off;   /* [N] host: first feature row of agent k inside a time block        */
+  int64_t scratch_bytes;   /* activation scratch budget per call (0: 2 GiB)                     */
+} d2d_net_config;
+
+typedef struct d2d_net d2d_net;
+int d2d_net_create(const d2d_net_config* cfg, d2d_net** out);
+int d2d_net_destroy(d2d_net* net);
+int64_t d2d_net_param_stride(const d2d_net* net);       /* floats per agent block                        */
+int d2d_net_num_tensors(const d2d_net* net);            /* 8 (GRU) or 4 (MLP)                            */
+/* state_dict tensor `index` of agent `agent`: offset inside the agent's block, rows, cols (cols = 1: vector) */
+int d2d_net_tensor(const d2d_net* net, int agent, int index, int64_t* offset, int32_t* rows, int32_t* cols);
+
+/* Forward of time blocks [t0, t1): net(x windows) -> PRE-activation outputs.
+ *   x       f32 [x_lead + T][in_rows][B]; block x_lead + t holds time t; for GRU nets x_lead >= L - 1 and the
+ *           blocks before time 0 are zero (the left zero padding of preprocess_input_for_rnn, d2d_ppo.py:385-398)
+ *   padded  1: training windows (zero inputs before the episode start still run a GRU step)
+ *           0: rollout windows (d2d_ppo.py:302: those steps do not exist)
+ *   out     f32 [t1 - t0][N][O][B]                                                                           */
+int d2d_net_forward(d2d_net* net, const float* params, const float* x, int x_lead, int t0, int t1, int padded,
+                    float* out, void* stream);
+
+/* Distribution head on pre-activation outputs (PPO.select_action / PPO.evaluate, d2d_ppo.py:159-196).
+ *   logits   f32 [n_t][N][O][B]
+ *   actions  Bernoulli: channel bitmask [n_t][N][B] (1/2/4 bytes for O <= 8/16/32); Categorical: u8 index.
+ *            Written for D2D_ACT_SAMPLE / GREEDY, read for D2D_ACT_GIVEN.
+ *   logp, entropy  f32 [n_t][N][B] (entropy may be NULL);  probs f32 [n_t][N][O][B] or NULL
+ *   sampling uses Philox4x32-10 keyed (seed; env_offset + b, t_abs0 + t, agent, purpose = policy)            */
+int d2d_policy_head(int n_agents, int n_envs, int n_out, int n_t, int out_kind, int dist_kind, int act_mode,
+                    const float* logits, void* actions, float* logp, float* entropy, float* probs, uint64_t seed,
+                    uint64_t env_offset, int t_abs0, void* stream);
+
+/* PPO clipped-surrogate gradient of all N policies over time blocks [t0, t1)  (PPO.train_step, d2d_ppo.py:198-216,
+ * ippo.py:194-206): forward on padded windows, loss, backward.
+ *   actions, logp_old   [T][N][B] (indexed by absolute time)
+ *   weight              f32 advantages [T][N][B] (weight_per_agent = 1, IPPO) or [T][B] (= 0, D2DPPO)
+ *   cycle               int32 device [N] or NULL: HAPPO order; agent cycle[j] is weighted by
+ *                       weight * prod_{i<j} ratio_{cycle[i]} (the sequential M chain of d2d_ppo.py:427-436)
+ *   inv_rows            1 / (rows of the whole batch, over all ranks): the loss is a mean over rows
+ *   grads               f32 [N][param_stride], ACCUMULATED into
+ *   loss_sums           f64 device [N][2], ACCUMULATED: sum_rows min(surr1, surr2), sum_rows entropy
+ *   ratio_out           f32 [T][N][B] or NULL                                                            */
+int d2d_ppo_policy_grad(d2d_net* net, const float* params, const float* x, int x_lead, int t0, int t1,
+                        int dist_kind, const void* actions, const float* logp_old, const float* weight,
+                        int weight_per_agent, const int32_t* cycle, float inv_rows, float cliprange, float beta,
+                        float* grads, double* loss_sums, float* ratio_out, void* stream);
+
+/* Critic MSE gradient over time blocks [t0, t1) (ippo.py:208-215, d2d_ppo.py:440-446).
+ *   target     f32 [T][N][B] (per_agent = 1) or [T][B] (= 0);  value_out f32 [T][N][B] or NULL
+ *   loss_sum   f64 device [N], ACCUMULATED: sum_rows (v - target)^2                                      */
+int d2d_value_grad(d2d_net* net, const float* params, const float* x, int x_lead, int t0, int t1, int padded,
+                   const float* target, int per_agent, float inv_rows, float* grads, double* loss_sum,
+                   float* value_out, void* stream);
+
+/* torch.optim.Adam (betas 0.9 / 0.999, eps 1e-8) on [N][per_agent] buffers, step counter `step` (1-based).
+ * max_norm > 0: clip_grad_norm_(max_norm) per agent first (d2d_ppo.py:211,445); sqnorm: f64 device [N] scratch. */
+int d2d_adam_step(float* params, float* m, float* v, const float* grads, int n_agents, int64_t per_agent,
+                  float lr, int step, float max_norm, double* sqnorm, void* stream);
+
+/* compute_gae (d2d_ppo.py:100-110) and discount_rewards (:112-124) as reverse scans in float64.
+ *   reward   i32 [T][B] (all agents of an env share the reward, combinatorial_env.py:211)
+ *   value    f32 [T][n_cols][B] (NULL: no lambda-returns)
+ *   adv_raw / ret_raw  f64 [T][n_cols][B] outputs (either may be NULL)
+ *   stats    f64 device [n_cols][4], ACCUMULATED: sum / sum of squares of adv_raw, of (float)ret_raw
+ *   last_shard  1 if this GPU holds the globally last env (its final row keeps the r - v quirk of :102)  */
+int d2d_returns_scan(const int32_t* reward, const float* value, double* adv_raw, double* ret_raw, double* stats,
+                     int T, int n_envs, int n_cols, double gamma, double lam, int last_shard, void* stream);
+/* out[i] = (raw[i] - mean[col]) / std[col] as f32 (do_norm[col] == 0: plain cast); fp32_math = 1 reproduces
+ * discount_rewards (cast to f32 first, normalise in f32).  mean/std f64 device [n_cols], do_norm i32 device. */
+int d2d_normalize(const double* raw, float* out, const double* mean, const double* std, const int32_t* do_norm,
+                  int fp32_math, int T, int n_envs, int n_cols, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
