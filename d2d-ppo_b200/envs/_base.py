@@ -195,8 +195,10 @@ class LockstepEnv:
     def _obs_views(self, obs):
         return [obs[o:o + d].t() for o, d in zip(self._obs_off, self._obs_dim)]
 
-    def _reset_device(self, with_obs=True, with_state=True):
-        obs, state = self._new_outputs(with_obs, with_state)
+    def _reset_device(self, with_obs=True, with_state=True, out_obs=None, out_state=None):
+        obs, state = self._new_outputs(with_obs and out_obs is None, with_state and out_state is None)
+        obs = out_obs if out_obs is not None else obs
+        state = out_state if out_state is not None else state
         with torch.cuda.device(self.device):
             L.check(self._lib.d2d_env_reset(self._h, L.ptr(obs), L.ptr(state), L.current_stream()))
         self.timestep = 0
@@ -204,12 +206,12 @@ class LockstepEnv:
         return obs, state
 
     def _step_device(self, actions_dev, with_obs=True, with_state=True, out_obs=None, out_state=None,
-                     random_access_tp=None, actions_out=None):
+                     random_access_tp=None, actions_out=None, out_reward=None):
         B, dev = self.n_envs, self.device
         obs, state = self._new_outputs(with_obs and out_obs is None, with_state and out_state is None)
         obs = out_obs if out_obs is not None else obs
         state = out_state if out_state is not None else state
-        reward = torch.empty(B, dtype=torch.int32, device=dev)
+        reward = out_reward if out_reward is not None else torch.empty(B, dtype=torch.int32, device=dev)
         done = torch.empty(B, dtype=torch.uint8, device=dev)
         ack = self._new_ack()
         with torch.cuda.device(dev):
@@ -227,6 +229,28 @@ class LockstepEnv:
 
     def _new_ack(self):
         return None
+
+    # ------------------------------------------------------------------ zero-copy entry points for the learners
+    def reset_into(self, out_obs, out_state=None):
+        """reset() writing the env-minor observation block [obs_rows, B] (and state block) in place."""
+        self._reset_device(True, out_state is not None, out_obs, out_state)
+
+    def step_into(self, actions_nb, out_obs, out_state=None, out_reward=None):
+        """step() on device-layout actions [N, B], writing observation / state / reward blocks in place.
+        Returns the lockstep done flag."""
+        return self._step_device(actions_nb, True, out_state is not None, out_obs, out_state,
+                                 out_reward=out_reward)[3]
+
+    @property
+    def obs_layout(self):
+        """(rows per time block, [first row of agent k], [obs_dim of agent k]) of the env-minor obs matrix."""
+        return self._obs_rows, list(self._obs_off), list(self._obs_dim)
+
+    @property
+    def action_kind(self):
+        """'bernoulli_mask' (combinatorial) | 'binary' (D2DEnv) | 'index' (channel selection)."""
+        return {L.ENV_COMBINATORIAL: "bernoulli_mask", L.ENV_SINGLE_CHANNEL: "binary",
+                L.ENV_CHANNEL_SELECTION: "index"}[self.KIND]
 
     # ------------------------------------------------------------------ raw state (reference attribute names)
     def _export(self):

@@ -78,6 +78,8 @@ class CombinatorialEnv(LockstepEnv):
     def step_random_access(self, transmission_prob, *, with_obs=True, with_state=True, out_obs=None,
                            out_state=None, return_actions=False):
         """One step with the fused CombinatorialRandomAccess policy (algorithms/baselines.py:181-183)."""
+        if self.compat:
+            with_obs = with_state = True
         acts = torch.empty((self.n_agents, self.n_envs), dtype=self._mask_dtype, device=self.device) \
             if return_actions else None
         obs, state, reward, done = self._step_device(None, with_obs, with_state, out_obs, out_state,

@@ -1,0 +1,168 @@
+"""End-to-end learner parity: the iPPO / D2DPPO classes on the CUDA env reproduce one full reference training
+iteration (rollout + epochs) from the fixtures, with the env on replayed streams and actions teacher-forced."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from _helpers import assert_params_close, load_ppo_case, make_cuda_env, params_from, rel_err
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-5
+
+
+def _setup(algo, tag, dev):
+    from d2d_ppo_b200.algorithms.d2d_ppo import D2DPPO
+    from d2d_ppo_b200.algorithms.ippo import iPPO
+    g = load_ppo_case(f"{algo}_{tag}")
+    m = g["meta"]
+    env = make_cuda_env("combinatorial", g["config"], m["E"], rng="replay", device=dev)
+    env.set_replay(g["arrivals"], g["switches"])
+    kw = dict(hidden_size=m["hidden"], gamma=m["gamma"], policy_lr=m["policy_lr"], value_lr=m["value_lr"],
+              useRNN=(m["arch"] == "gru"), combinatorial=True, history_len=m["L"], early_stopping=False)
+    agent = iPPO(env, **kw) if algo == "ippo" else D2DPPO(env, beta_entropy=0.01, **kw)
+    for i in range(m["N"]):
+        agent.policies.load_state_dict(i, params_from(g, f"init/policy{i}"))
+        if algo == "ippo":
+            agent.values.load_state_dict(i, params_from(g, f"init/value{i}"))
+    if algo == "d2dppo":
+        agent.critic.load_state_dict(0, params_from(g, "init/critic"))
+    C = g["config"]["n_channels"]
+    packed = (g["actions"].astype(np.int64) * (1 << np.arange(C))).sum(-1)                       # [R, N]
+    forced = torch.tensor(packed).reshape(m["E"], m["T"], m["N"]).permute(1, 2, 0).contiguous()
+    forced = forced.to(agent.act_buf.dtype).to(dev)
+    return g, m, env, agent, forced
+
+
+def _rows(t):     # [T, N, B] -> [B*T, N] episode-major ; [T, B] -> [B*T]
+    if t.dim() == 3:
+        T, N, B = t.shape
+        return t.permute(2, 0, 1).reshape(B * T, N).cpu().numpy()
+    return t.t().reshape(-1).cpu().numpy()
+
+
+@pytest.mark.parametrize("tag", ["small_gru", "small_mlp", "c3_gru"])
+def test_ippo_training_iteration(tag, cuda_device):
+    g, m, env, agent, forced = _setup("ippo", tag, cuda_device)
+    E, T, N = m["E"], m["T"], m["N"]
+    obs, actions, logp, ret, values, adv, scores, dones = agent.create_rollouts(E, forced_actions=forced)
+    I = g["obs"].shape[2]
+    mine_obs = obs[:T].reshape(T, N, I, E).permute(3, 0, 1, 2).reshape(E * T, N, I).cpu().numpy()
+    assert np.array_equal(mine_obs, g["obs"])                      # env + zero-copy rollout buffer: bit exact
+    assert rel_err(_rows(logp), g["logp_old"]) < TOL
+    assert rel_err(_rows(values), g["values"]) < TOL
+    assert rel_err(_rows(adv), g["advantages"]) < TOL
+    assert rel_err(_rows(ret), g["returns"]) < TOL
+    assert np.allclose(scores.cpu().numpy(), g["scores"], rtol=0, atol=1e-12)
+    assert dones == [bool(d) for d in g["dones"][:T]]
+    for epoch in range(m["n_epoch"]):
+        ploss, vloss = agent.update_epoch()
+        assert abs(ploss[-1] - g["policy_loss"][epoch]) <= 1e-4 * max(1.0, abs(g["policy_loss"][epoch]))
+        assert abs(vloss[-1] - g["value_loss"][epoch]) <= 1e-4 * max(1.0, abs(g["value_loss"][epoch]))
+    for i in range(N):
+        assert_params_close(agent.policies.state_dict(i), params_from(g, f"final/policy{i}"),
+                            params_from(g, f"init/policy{i}"), f"policy{i}")
+        assert_params_close(agent.values.state_dict(i), params_from(g, f"final/value{i}"),
+                            params_from(g, f"init/value{i}"), f"value{i}")
+
+
+@pytest.mark.parametrize("tag", ["small_gru", "small_mlp", "c3_gru"])
+def test_d2dppo_training_iteration(tag, cuda_device):
+    g, m, env, agent, forced = _setup("d2dppo", tag, cuda_device)
+    E, T, N = m["E"], m["T"], m["N"]
+    obs, states, actions, logp, rewards, ret, scores, dones = agent.create_rollouts(E, forced_actions=forced)
+    S = g["states"].shape[1]
+    mine_states = states.reshape(T, S, E).permute(2, 0, 1).reshape(E * T, S).cpu().numpy()
+    assert np.array_equal(mine_states, g["states"])
+    assert rel_err(_rows(logp), g["logp_old"]) < TOL
+    assert np.array_equal(_rows(rewards).astype(np.float64), g["rewards_mean"])
+    assert rel_err(_rows(ret), g["returns"]) < TOL
+    assert np.allclose(scores.cpu().numpy(), g["scores"], rtol=0, atol=1e-12)
+    for epoch in range(m["n_epoch"]):
+        ploss, vloss = agent.update_epoch(cycle=g["cycles"][epoch])
+        ref = g["policy_loss"][epoch]
+        assert np.allclose(ploss, ref, rtol=1e-4, atol=1e-5), (epoch, ploss, ref)
+        assert abs(vloss - g["value_loss"][epoch]) <= 1e-4 * max(1.0, abs(g["value_loss"][epoch]))
+    for i in range(N):
+        assert_params_close(agent.policies.state_dict(i), params_from(g, f"final/policy{i}"),
+                            params_from(g, f"init/policy{i}"), f"policy{i}")
+    assert_params_close(agent.critic.state_dict(0), params_from(g, "final/critic"), params_from(g, "init/critic"),
+                        "critic")
+
+
+def test_train_test_save_load_api(tmp_path, cuda_device):
+    """Reference call signatures: train(...) 4-tuple, test(n) 4-tuple, agent_{i}.pth with the reference's keys."""
+    from d2d_ppo_b200 import presets
+    from d2d_ppo_b200.algorithms.d2d_ppo import D2DPPO
+    from d2d_ppo_b200.algorithms.ippo import iPPO
+    from d2d_ppo_b200.envs import CombinatorialEnv
+    kw = presets.combinatorial_kwargs("setup_8_channels", load=0.5, episode_length=25)
+    env = CombinatorialEnv(n_envs=64, device=cuda_device, seed=3, **kw)
+    ppo = D2DPPO(env, hidden_size=64, gamma=0.6, policy_lr=3e-4, value_lr=1e-3, useRNN=True,
+                 save_path=str(tmp_path), combinatorial=True, history_len=6, early_stopping=True)
+    res = ppo.train(num_iter=2, n_epoch=2, num_episodes=64, test_freq=1)       # keyword order of xp_load.py:106
+    scores_episode, score_test_list, policy_loss_list, value_loss_list = res
+    assert len(scores_episode) == 128 and len(score_test_list) == 4
+    assert len(policy_loss_list) == 4 and len(policy_loss_list[0]) == 6 and len(value_loss_list) == 4
+    assert all(np.isfinite(v) for v in value_loss_list)
+    files = sorted(os.listdir(tmp_path))
+    assert files == [f"agent_{i}.pth" for i in range(6)]
+    sd = torch.load(tmp_path / "agent_0.pth")
+    assert list(sd) == ["lstm.weight_ih_l0", "lstm.weight_hh_l0", "lstm.bias_ih_l0", "lstm.bias_hh_l0",
+                        "layers.0.weight", "layers.0.bias", "layers.2.weight", "layers.2.bias"]
+    assert sd["lstm.weight_ih_l0"].shape == (192, 30) and sd["layers.2.weight"].shape == (8, 64)
+    before = ppo.policies.params.clone()
+    ppo.policies.params.zero_()
+    ppo.load(str(tmp_path))
+    assert ppo.policies.params.abs().sum() > 0 and before.shape == ppo.policies.params.shape
+    score, jains, errors, avg_reward = ppo.test(100)
+    assert 0.0 <= score <= 1.0 and 0.0 < jains <= 1.0 and errors == 0 and avg_reward >= 0
+    with pytest.raises(ValueError):
+        ppo.train(num_iter=1, num_episodes=10)                                   # lockstep batch is n_envs
+    ip = iPPO(env, hidden_size=32, gamma=0.4, policy_lr=3e-4, value_lr=1e-3, useRNN=False, combinatorial=True)
+    r = ip.train(1, 2, 64, 100)                                                  # positional order of ippo.py:406
+    assert len(r[2]) == 2 and isinstance(r[2][0], float)
+    sd = ip.policies.state_dict(0)
+    assert list(sd) == ["linear1.weight", "linear1.bias", "linear2.weight", "linear2.bias"]
+
+
+def test_learning_improves_score(cuda_device):
+    """Sanity: a few hundred IPPO updates on an easy config raise the URLLC score of greedy rollouts."""
+    from d2d_ppo_b200.algorithms.d2d_ppo import D2DPPO
+    from d2d_ppo_b200.envs import CombinatorialEnv
+    kw = dict(n_agents=3, n_channels=2, deadlines=np.array([4, 4, 4]), lbdas=np.array([0.3] * 3), period=None,
+              arrival_probs=None, offsets=None, episode_length=50, traffic_model="aperiodic", periodic_devices=[],
+              homogeneous_size=True, channel_switch=np.zeros((3, 2)))
+    env = CombinatorialEnv(n_envs=256, device=cuda_device, seed=1, **kw)
+    ppo = D2DPPO(env, hidden_size=32, gamma=0.6, policy_lr=3e-3, value_lr=3e-3, useRNN=False, combinatorial=True,
+                 early_stopping=False, seed=4)
+    s0 = ppo.test(256)[0]
+    ppo.train(num_iter=60, num_episodes=256, n_epoch=4, test_freq=10 ** 9)
+    s1 = ppo.test(256)[0]
+    assert s1 > s0 + 0.02, (s0, s1)
+
+
+def test_random_access_baseline(cuda_device):
+    from d2d_ppo_b200 import presets
+    from d2d_ppo_b200.algorithms.baselines import CombinatorialRandomAccess
+    from d2d_ppo_b200.envs import CombinatorialEnv
+    kw = presets.combinatorial_kwargs("setup", load=1 / 3, homogeneous_size=False)      # config c1 (16 channels)
+    env = CombinatorialEnv(n_envs=512, device=cuda_device, seed=9, **kw)
+    gf = CombinatorialRandomAccess(env)
+    cv = gf.get_best_transmission_probs(512)
+    assert len(cv) == 10 and np.isnan(cv[0]) or cv[0] <= max(cv)      # tp = 0 never transmits
+    gf.transmission_prob = gf.transmission_prob_list[int(np.nanargmax(cv))]
+    score, jains, chsc, rew = gf.run(1024)
+    assert 0.3 < score <= 1.0 and 0 < jains <= 1 and chsc == 1.0 and rew > 0
+    # statistical agreement with the CPU oracle driven by numpy draws (same distributions, different streams)
+    from _helpers import make_oracle
+    from oracle.envs_np import NumpySource
+    orc = make_oracle("combinatorial", kw, 512, NumpySource(512, 0))
+    rng = np.random.default_rng(1)
+    orc.reset()
+    done = False
+    while not done:
+        _, _, _, done, _ = orc.step(rng.binomial(1, gf.transmission_prob, (512, 6, 16)))
+    ref = 1 - orc.discarded.sum() / orc.received.sum()
+    assert abs(score - ref) < 0.02, (score, ref)
