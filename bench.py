@@ -47,6 +47,9 @@ def parse():
     ap.add_argument("--envs", type=int, default=1 << 20, help="lockstep envs per GPU")
     ap.add_argument("--cpu-envs", type=int, default=4096, help="envs per process of the CPU arm")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-learner", action="store_true", help="skip the learned-policy rollout / train SPS sections")
+    ap.add_argument("--rollout-envs", type=int, default=65536, help="envs per GPU of the learned-policy rollout (c3)")
+    ap.add_argument("--train-envs", type=int, default=4096, help="envs per GPU of the train-SPS sections")
     return ap.parse_args()
 
 
@@ -172,6 +175,96 @@ def workload_config(envs_total, cpu=False):
             "envs_total": envs_total, "n_agents": N_AGENTS, "n_channels": N_CHANNELS, "episode_length": 200,
             "rng": "numpy Generator" if cpu else "philox4x32-10",
             "l2": "n/a" if cpu else "per-step working set ~1.06 GB per GPU >> 126 MB L2 (no flush needed)"}
+
+
+# ------------------------------------------------------------------------------------------------
+# learner sections (extra keys of the JSON line): env + learned-policy rollout, PPO train SPS
+# ------------------------------------------------------------------------------------------------
+FFMA_PEAK_TFLOPS = 148 * 128 * 2 * 1.965e9 / 1e12     # 148 SMs x 128 FP32 FMA lanes x 2 flop x 1.965 GHz = 74.4
+
+
+def gru_flops_per_agent_step(I, H, L, O):
+    """Forward flops of one GRU-window net evaluation as the kernels execute it at rollout time: L input
+    projections, L hidden projections, head (225,792 for I=30, H=64, L=6, O=8)."""
+    return 2 * L * 3 * H * (I + H) + 2 * H * H + 2 * H * O
+
+
+def bench_learner(args, dev, world, rank, barrier, max_over_ranks):
+    import torch
+
+    from d2d_ppo_b200 import _lib, presets
+    from d2d_ppo_b200.algorithms.d2d_ppo import D2DPPO
+    from d2d_ppo_b200.algorithms.ippo import iPPO
+    from d2d_ppo_b200.envs import CombinatorialEnv, D2DEnv
+    out = {}
+
+    def timed(fn):
+        barrier()
+        n0 = _lib.launch_count()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        fn()
+        e1.record()
+        barrier()
+        return max_over_ranks(e0.elapsed_time(e1)) * 1e-3, _lib.launch_count() - n0
+
+    # (ii) env + learned-policy rollout: config c3 = MCA-iPPO of xp_load.py:92-104 (GRU actor + GRU critic per agent,
+    #      H = 64, history_len = 6) on the 8-channel combinatorial env, 65,536 lockstep envs per GPU
+    B = args.rollout_envs
+    kw = presets.combinatorial_kwargs("setup_8_channels", load=LOAD)
+    T = kw["episode_length"]
+    env = CombinatorialEnv(n_envs=B, device=dev, seed=7, env_offset=rank * B, **kw)
+    agent = iPPO(env, hidden_size=64, gamma=0.4, policy_lr=3e-4, value_lr=1e-3, useRNN=True, combinatorial=True,
+                 history_len=6, early_stopping=False, seed=1, scratch_bytes=6 << 30)
+    agent._run_episode(_lib.ACT_SAMPLE, per_step=None)          # warm-up episode (allocations, clocks)
+    dt, launches = timed(lambda: agent.create_rollouts(B))
+    flops = 2 * gru_flops_per_agent_step(30, 64, 6, 8) - (2 * 64 * 8 - 2 * 64)   # actor (O=8) + critic (O=1)
+    steps = world * B * N_AGENTS * T
+    out["rollout_learned"] = {
+        "metric": "agent-steps/sec (env step + GRU actor + GRU critic, sampled actions, log-probs, values, "
+                  "lambda-returns)", "value": steps / dt, "unit": "agent-steps/s", "envs_per_gpu": B,
+        "config": "c3: iPPO useRNN=True hidden 64 history_len 6 on CombinatorialEnv setup_8_channels.p",
+        "seconds_per_episode": dt, "gpu_launches": int(launches),
+        "roofline": {"bound": "fp32 FMA (CUDA cores; fp32 parity path, no tensor cores yet)",
+                     "achieved": steps * flops / dt / 1e12, "peak": FFMA_PEAK_TFLOPS, "unit": "TFLOP/s",
+                     "frac": steps * flops / dt / 1e12 / FFMA_PEAK_TFLOPS,
+                     "flops_per_agent_step": flops, "peak_source": "148 SM x 128 lanes x 2 x 1.965 GHz (nominal)"}}
+    del agent, env
+    torch.cuda.empty_cache()
+
+    # (iii) PPO train SPS = agent-steps consumed per second of train() (rollout + n_epoch = 5 full-batch updates)
+    def train_sps(make_env, make_agent, B, n_agents, label, n_epoch=5, iters=2):
+        env = make_env(B)
+        ag = make_agent(env)
+        kwargs = dict(num_iter=1, n_epoch=n_epoch, num_episodes=B, test_freq=10 ** 9)
+        ag._maybe_test = lambda *a, **k: False                   # SPS excludes the periodic evaluation episodes
+        ag.train(**kwargs)                                       # warm-up iteration
+        kwargs["num_iter"] = iters
+        dt, launches = timed(lambda: ag.train(**kwargs))
+        return {"metric": "PPO train SPS (agent-steps consumed per second of train(): rollout + 5 epochs)",
+                "value": world * iters * B * n_agents * env.episode_length / dt, "unit": "agent-steps/s",
+                "envs_per_gpu": B, "config": label, "seconds_per_iteration": dt / iters, "gpu_launches": int(launches)}
+
+    Bt = args.train_envs
+    out["train_ippo_c3"] = train_sps(
+        lambda B: CombinatorialEnv(n_envs=B, device=dev, seed=8, env_offset=rank * B, **kw),
+        lambda e: iPPO(e, hidden_size=64, gamma=0.4, policy_lr=3e-4, value_lr=1e-3, useRNN=True, combinatorial=True,
+                       history_len=6, early_stopping=False, seed=2, scratch_bytes=6 << 30),
+        Bt, N_AGENTS, "c3 shape: iPPO GRU (H 64, L 6) on CombinatorialEnv setup_8_channels.p")
+    torch.cuda.empty_cache()
+    out["train_d2dppo_c3"] = train_sps(
+        lambda B: CombinatorialEnv(n_envs=B, device=dev, seed=9, env_offset=rank * B, **kw),
+        lambda e: D2DPPO(e, hidden_size=64, gamma=0.6, policy_lr=3e-4, value_lr=1e-3, useRNN=True, combinatorial=True,
+                         history_len=6, early_stopping=False, seed=3, scratch_bytes=6 << 30),
+        Bt, N_AGENTS, "xp_load.py:78-106: D2DPPO GRU (H 64, L 6, gamma .6) on CombinatorialEnv setup_8_channels.p")
+    torch.cuda.empty_cache()
+    c2 = presets.d2d_c2_kwargs()
+    out["train_d2dppo_c2"] = train_sps(
+        lambda B: D2DEnv(n_envs=B, device=dev, seed=10, env_offset=rank * B, **c2),
+        lambda e: D2DPPO(e, hidden_size=64, gamma=0.6, policy_lr=3e-4, value_lr=1e-3, useRNN=True, combinatorial=False,
+                         history_len=4, early_stopping=False, seed=4, scratch_bytes=6 << 30),
+        4096, 4, "c2: D2DPPO GRU (H 64, L 4) on D2DEnv N=4, 4096 lockstep envs")
+    return out
 
 
 # ------------------------------------------------------------------------------------------------
@@ -304,6 +397,10 @@ def run_native(args):
                 "api": "CombinatorialEnv.step(actions u8 [B,N,C] in pinned host memory) -> rewards read on host"},
         "gpu_launches": int(launches), "resets_in_timed_region": n_resets, "clocks": clocks,
     }
+    del obs_buf, env, host_actions
+    torch.cuda.empty_cache()
+    if not args.no_learner:
+        line.update(bench_learner(args, dev, world, rank, barrier, max_over_ranks))
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         steps_cpu = 600
         v, dt = cpu_throughput(args.cpu_envs, steps_cpu, 20, 1)
