@@ -47,8 +47,35 @@ static View make_view(float* p, long long t_stride, int t_off, int N, int feat_p
   return v;
 }
 
+template <int RPT, int OPT>
+static int launch_dense_tile(const d2d_net* n, const DenseArgs& a, int max_in, cudaStream_t s) {
+  constexpr int ROWS = 32 * RPT;
+  const size_t smem = ((size_t)std::max(max_in, 1) * 8 * OPT + 8 * OPT + 2 * kDenseKC * ROWS) * sizeof(float);
+  static bool attr = false;
+  if (!attr) {
+    D2D_CUDA(cudaFuncSetAttribute(dense_tile_kernel<RPT, OPT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  200 * 1024));
+    attr = true;
+  }
+  const int tiles = (a.t1 - a.t0) * ((n->B + ROWS - 1) / ROWS);
+  if (tiles <= 0) return D2D_OK;
+  // persistent grid: exactly the number of blocks that are resident at once (registers + shared memory)
+  int per_sm = 1;
+  D2D_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, dense_tile_kernel<RPT, OPT>, 256, smem));
+  per_sm = std::max(per_sm, 1);
+  const int gx = std::max(1, std::min(tiles, (148 * per_sm) / n->N));
+  dense_tile_kernel<RPT, OPT><<<dim3(gx, n->N), 256, smem, s>>>(a);
+  D2D_LAUNCHED();
+  return D2D_OK;
+}
+
 static int launch_dense(const d2d_net* n, DenseArgs& a, int max_in, cudaStream_t s) {
   a.B = n->B;
+  if (n->B % 4 == 0 && a.out_dim <= 192) {   // register-tiled path (rows are moved as float4)
+    if (a.out_dim > 64) return launch_dense_tile<4, 24>(n, a, max_in, s);
+    if (a.out_dim > 32) return launch_dense_tile<8, 8>(n, a, max_in, s);
+    return launch_dense_tile<8, 4>(n, a, max_in, s);
+  }
   const int OC = a.out_dim >= 64 ? 64 : 16;
   const int out_pad = (a.out_dim + OC - 1) / OC * OC;
   const size_t smem = ((size_t)max_in * out_pad + out_pad) * sizeof(float);

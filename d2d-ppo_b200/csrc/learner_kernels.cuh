@@ -113,6 +113,143 @@ __global__ void __launch_bounds__(kRowsPerBlock) dense_kernel(const DenseArgs a)
 }
 
 // ------------------------------------------------------------------------------------------------
+// dense, register-tiled: the same contract as dense_kernel for B % 4 == 0.
+// Block = 8 warps; every warp works on the SAME 32 * RPT rows (lane l owns rows 4-aligned [l*RPT, l*RPT + RPT)) and
+// warp w owns outputs [w * OPT, w * OPT + OPT).  Per input k a thread issues RPT/4 LDS.128 for its rows and OPT/4
+// broadcast LDS.128 for its weights against RPT * OPT FMAs (1 : 14 at <4, 24>, vs 1 : 4 for one row per thread).
+// Input rows are streamed global -> shared with cp.async in chunks of 32 inputs, double buffered across
+// (row tile, input chunk), so the global latency hides behind the FMAs of the previous chunk.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void cp_async16(float* smem_dst, const float* gsrc) {
+  const uint32_t d = (uint32_t)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+constexpr int kDenseKC = 32;
+
+template <int RPT, int OPT>
+__global__ void __launch_bounds__(256) dense_tile_kernel(const DenseArgs a) {
+  constexpr int ROWS = 32 * RPT, KC = kDenseKC, OUT_PAD = 8 * OPT;
+  extern __shared__ __align__(16) float sm[];
+  const int g = blockIdx.y;
+  const int in_dim = a.in_dim[g], out_dim = a.out_dim;
+  float* Ms = sm;                               // [in_dim][OUT_PAD]
+  float* bs = Ms + (size_t)max(in_dim, 1) * OUT_PAD;   // [OUT_PAD]
+  float* Xs = bs + OUT_PAD;                     // [2][KC][ROWS]
+  const float* W = a.w + g * a.w_agent_stride + a.w_off[g];
+  const int ld = a.w_ld[g];
+  for (int i = threadIdx.x; i < in_dim * OUT_PAD; i += 256) {
+    const int in = i / OUT_PAD, o = i % OUT_PAD;
+    float v = 0.f;
+    if (o < out_dim) v = a.trans ? W[(long long)in * ld + o] : W[(long long)o * ld + in];
+    Ms[i] = v;
+  }
+  for (int o = threadIdx.x; o < OUT_PAD; o += 256)
+    bs[o] = (o < out_dim && a.b_off[g] >= 0) ? a.w[g * a.w_agent_stride + a.b_off[g] + o] : 0.f;
+
+  const int lane = threadIdx.x & 31, og = threadIdx.x >> 5;
+  const int tiles_per_t = (a.B + ROWS - 1) / ROWS;
+  const int n_tiles = (a.t1 - a.t0) * tiles_per_t;
+  const int nkc = max(1, (in_dim + KC - 1) / KC);
+  const int my_tiles = blockIdx.x < n_tiles ? (n_tiles - 1 - blockIdx.x) / gridDim.x + 1 : 0;
+  const int total = my_tiles * nkc;
+
+  auto issue = [&](int c) {   // chunk c -> buffer c & 1
+    const int tile = blockIdx.x + (c / nkc) * gridDim.x;
+    const int kc = c % nkc;
+    const int t = a.t0 + tile / tiles_per_t, b0 = (tile % tiles_per_t) * ROWS;
+    float* dst = Xs + (size_t)(c & 1) * KC * ROWS;
+    const float* src = view_ptr(a.x, g, t, a.B, b0);
+    for (int i = threadIdx.x; i < KC * (ROWS / 4); i += 256) {
+      const int kk = i / (ROWS / 4), r4 = (i % (ROWS / 4)) * 4;
+      const int k = kc * KC + kk;
+      float* d = dst + kk * ROWS + r4;
+      if (k < in_dim && b0 + r4 < a.B) cp_async16(d, src + (long long)k * a.B + r4);
+      else *reinterpret_cast<float4*>(d) = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    cp_async_commit();
+  };
+
+  if (total > 0) issue(0);
+  float acc[RPT][OPT];
+  for (int c = 0; c < total; ++c) {
+    if (c + 1 < total) {
+      issue(c + 1);
+      cp_async_wait<1>();
+    } else {
+      cp_async_wait<0>();
+    }
+    __syncthreads();   // chunk c (and, the first time, the staged weights) visible to every warp
+    const int kc = c % nkc;
+    if (kc == 0) {
+#pragma unroll
+      for (int j = 0; j < OPT; ++j) {
+        const float bv = bs[og * OPT + j];
+#pragma unroll
+        for (int r = 0; r < RPT; ++r) acc[r][j] = bv;
+      }
+    }
+    const float* xs = Xs + (size_t)(c & 1) * KC * ROWS + lane * RPT;
+    const int kmax = min(KC, in_dim - kc * KC);
+    const float* mrow = Ms + (size_t)kc * KC * OUT_PAD + og * OPT;
+#pragma unroll 2
+    for (int kk = 0; kk < kmax; ++kk) {
+      float xv[RPT];
+#pragma unroll
+      for (int q = 0; q < RPT / 4; ++q) {
+        const float4 v = *reinterpret_cast<const float4*>(xs + kk * ROWS + 4 * q);
+        xv[4 * q] = v.x, xv[4 * q + 1] = v.y, xv[4 * q + 2] = v.z, xv[4 * q + 3] = v.w;
+      }
+#pragma unroll
+      for (int q = 0; q < OPT / 4; ++q) {
+        const float4 m = *reinterpret_cast<const float4*>(mrow + kk * OUT_PAD + 4 * q);
+#pragma unroll
+        for (int r = 0; r < RPT; ++r) {
+          acc[r][4 * q + 0] = fmaf(xv[r], m.x, acc[r][4 * q + 0]);
+          acc[r][4 * q + 1] = fmaf(xv[r], m.y, acc[r][4 * q + 1]);
+          acc[r][4 * q + 2] = fmaf(xv[r], m.z, acc[r][4 * q + 2]);
+          acc[r][4 * q + 3] = fmaf(xv[r], m.w, acc[r][4 * q + 3]);
+        }
+      }
+    }
+    if (kc == nkc - 1) {
+      const int tile = blockIdx.x + (c / nkc) * gridDim.x;
+      const int t = a.t0 + tile / tiles_per_t, b = (tile % tiles_per_t) * ROWS + lane * RPT;
+      if (b < a.B) {
+        float* yp = view_ptr(a.y, g, t, a.B, b);
+        const float* ap = a.epilogue == kEpiReluBwd ? view_ptr(a.aux, g, t, a.B, b) : nullptr;
+#pragma unroll
+        for (int j = 0; j < OPT; ++j) {
+          const int o = og * OPT + j;
+          if (o < out_dim) {
+#pragma unroll
+            for (int q = 0; q < RPT / 4; ++q) {
+              float4 v = make_float4(acc[4 * q][j], acc[4 * q + 1][j], acc[4 * q + 2][j], acc[4 * q + 3][j]);
+              float4* dst = reinterpret_cast<float4*>(yp + (long long)o * a.B + 4 * q);
+              if (a.epilogue == kEpiRelu) {
+                v.x = fmaxf(v.x, 0.f), v.y = fmaxf(v.y, 0.f), v.z = fmaxf(v.z, 0.f), v.w = fmaxf(v.w, 0.f);
+              } else if (a.epilogue == kEpiAccum) {
+                const float4 o4 = *dst;
+                v.x += o4.x, v.y += o4.y, v.z += o4.z, v.w += o4.w;
+              } else if (a.epilogue == kEpiReluBwd) {
+                const float4 m4 = *reinterpret_cast<const float4*>(ap + (long long)o * a.B + 4 * q);
+                v.x = m4.x > 0.f ? v.x : 0.f, v.y = m4.y > 0.f ? v.y : 0.f;
+                v.z = m4.z > 0.f ? v.z : 0.f, v.w = m4.w > 0.f ? v.w : 0.f;
+              }
+              *dst = v;
+            }
+          }
+        }
+      }
+    }
+    __syncthreads();   // every warp is done with buffer c & 1 before chunk c + 2 overwrites it
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
 // weight gradient: dW[o][k] (+ db[o]) = sum over rows of dy[o][row] * x[k][row]   (partial sums per row strip)
 // ------------------------------------------------------------------------------------------------
 struct WgradArgs {
