@@ -85,7 +85,7 @@ class PPOBase:
 
     def _act(self, t, mode, forced=None):
         """select_action for all agents at time t: actions into act_buf[t], log-probs into logp_buf[t]."""
-        logits = self.policies.forward(self.obs_buf, self.lead, t, t + 1, padded=0)
+        logits = self.policies.rollout_step(self.obs_buf, self.lead, t)
         if forced is not None:
             self.act_buf[t].copy_(forced)
             mode = L.ACT_GIVEN

@@ -133,6 +133,16 @@ class NetSet:
                                               int(padded), L.ptr(out), L.current_stream()))
         return out
 
+    def rollout_step(self, x, x_lead, t, out=None):
+        """Pre-activation outputs [1, N, O, B] of time block t (unpadded window), input projections cached across
+        the steps of an episode.  Call with t = 0, 1, ... in order; parameters must stay fixed within the episode."""
+        if out is None:
+            out = torch.empty((1, self.N, self.O, self.B), dtype=torch.float32, device=self.device)
+        with torch.cuda.device(self.device):
+            L.check(self._lib.d2d_net_rollout_step(self._h, L.ptr(self.params), L.ptr(x), int(x_lead), int(t),
+                                                   L.ptr(out), L.current_stream()))
+        return out
+
     def zero_grad(self):
         self.grads.zero_()
 

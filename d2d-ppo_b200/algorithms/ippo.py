@@ -32,7 +32,7 @@ class iPPO(PPOBase):
         self._check_episodes(num_episodes)
 
         def critic(t):    # agent.value_network(history) on the UNPADDED rollout window (ippo.py:305)
-            out = self.values.forward(self.obs_buf, self.lead, t, t + 1, padded=0)
+            out = self.values.rollout_step(self.obs_buf, self.lead, t)
             self.value_buf[t].copy_(out[0, :, 0, :])
         scores = self._run_episode(L.ACT_SAMPLE, forced_actions, per_step=critic)
         adv_raw, ret_raw, stats = returns_scan(self.reward_buf, self.value_buf, self.gamma, 0.97,

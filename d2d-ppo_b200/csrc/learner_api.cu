@@ -30,6 +30,7 @@ struct d2d_net {
   long long scratch_bytes;
   float* scratch = nullptr;
   long long scratch_cap = 0;  // floats
+  float* gi_ring = nullptr;   // [L][N][3H][B] input projections of the last L observations (rollout)
   float* partial = nullptr;   // wgrad partial sums
   long long part_stride = 0;
   int n_strips = 0;
@@ -169,6 +170,27 @@ static int launch_wgrad(d2d_net* n, const View& dy, const View& x, const Wt& w, 
   return D2D_OK;
 }
 
+// fused hidden projection + gates (B % 4 == 0)
+static int launch_gru_step(const d2d_net* n, GruStepArgs& a, const float* params, cudaStream_t s) {
+  a.w = params, a.w_agent_stride = n->stride, a.H = n->H, a.B = n->B;
+  for (int g = 0; g < n->N; ++g) a.whh_off[g] = n->o_whh[g], a.bhh_off[g] = n->o_bhh[g];
+  constexpr int ROWS = 128, OUT_PAD = 192;
+  const size_t smem = ((size_t)std::max(a.first ? 0 : n->H, 1) * OUT_PAD + OUT_PAD + 2 * kDenseKC * ROWS) * sizeof(float);
+  static bool attr = false;
+  if (!attr) {
+    D2D_CUDA(cudaFuncSetAttribute(gru_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    attr = true;
+  }
+  const int tiles = (a.t1 - a.t0) * ((n->B + ROWS - 1) / ROWS);
+  if (tiles <= 0) return D2D_OK;
+  int per_sm = 1;
+  D2D_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, gru_step_kernel, 256, smem));
+  const int gx = std::max(1, std::min(tiles, (148 * std::max(per_sm, 1)) / n->N));
+  gru_step_kernel<<<dim3(gx, n->N), 256, smem, s>>>(a);
+  D2D_LAUNCHED();
+  return D2D_OK;
+}
+
 static int launch_gate(const GateArgs& a, int N, bool bwd, cudaStream_t s) {
   const long long n = (long long)(a.t1 - a.t0) * a.H * a.B;
   if (n <= 0) return D2D_OK;
@@ -281,6 +303,15 @@ static int forward_chunk(d2d_net* n, const float* params, const float* x, int x_
     for (int st = 0; st < L; ++st) {
       const View hprev = make_view(hs_ptr(n, c, train, st - 1 < 0 ? 0 : st - 1), H * NB, -c0, N, H, B);
       const View hout = make_view(hs_ptr(n, c, train, st), H * NB, -c0, N, H, B);
+      if (B % 4 == 0) {
+        GruStepArgs fa;
+        memset(&fa, 0, sizeof(fa));
+        fa.h_prev = hprev, fa.h_out = hout, fa.gi = gi, fa.gi.t_off = gi.t_off - (L - 1 - st);
+        if (train) fa.acts = make_view(c.acts + (long long)st * c.Tc * 4 * H * NB, 4 * H * NB, -c0, N, 4 * H, B);
+        fa.t0 = c0, fa.t1 = c1, fa.back = L - 1 - st, fa.padded = padded, fa.first = st == 0, fa.store = train;
+        if ((rc = launch_gru_step(n, fa, params, s))) return rc;
+        continue;
+      }
       {
         DenseArgs a;
         memset(&a, 0, sizeof(a));
@@ -454,7 +485,7 @@ extern "C" int d2d_net_create(const d2d_net_config* cfg, d2d_net** out) {
 
 extern "C" int d2d_net_destroy(d2d_net* n) {
   if (!n) return D2D_OK;
-  cudaFree(n->scratch), cudaFree(n->partial);
+  cudaFree(n->scratch), cudaFree(n->partial), cudaFree(n->gi_ring);
   delete n;
   return D2D_OK;
 }
@@ -502,6 +533,66 @@ extern "C" int d2d_net_forward(d2d_net* n, const float* params, const float* x, 
     if ((rc = forward_chunk(n, params, x, x_lead, c0, c1, padded, false, c, s))) return rc;
     D2D_CUDA(cudaMemcpyAsync(out + (long long)(c0 - t0) * per_t, c.logits, (size_t)(c1 - c0) * per_t * 4,
                              cudaMemcpyDeviceToDevice, s));
+  }
+  return D2D_OK;
+}
+
+extern "C" int d2d_net_rollout_step(d2d_net* n, const float* params, const float* x, int x_lead, int t, float* out,
+                                    void* stream) {
+  D2D_REQUIRE(n && params && x && out, "d2d_net_rollout_step: null argument");
+  if (n->arch == D2D_NET_MLP || n->B % 4 != 0) return d2d_net_forward(n, params, x, x_lead, t, t + 1, 0, out, stream);
+  int rc = check_range(n, x_lead, t, t + 1, "d2d_net_rollout_step");
+  if (rc) return rc;
+  cudaStream_t s = as_stream(stream);
+  const int N = n->N, B = n->B, H = n->H, O = n->O, L = n->L;
+  const long long NB = (long long)N * B;
+  if (!n->gi_ring) D2D_CUDA(cudaMalloc((void**)&n->gi_ring, (size_t)L * 3 * H * NB * 4));
+  Chunk c;
+  if ((rc = plan_chunk(n, false, 1, c))) return rc;
+  View xin;
+  memset(&xin, 0, sizeof(xin));
+  xin.p = const_cast<float*>(x), xin.t_stride = (long long)n->in_rows * B, xin.t_off = x_lead;
+  for (int g = 0; g < N; ++g) xin.f_off[g] = n->in_off[g];
+  {   // input projection of the NEW observation only; the previous L - 1 are still in the ring
+    DenseArgs a;
+    memset(&a, 0, sizeof(a));
+    Wt wih{&n->o_wih, &n->o_bih, &n->in_dim, 0, 3 * H};
+    fill_dense_w(n, a, params, wih, 0);
+    a.x = xin, a.y = make_view(n->gi_ring, 3 * H * NB, (t % L) - t, N, 3 * H, B), a.epilogue = kEpiNone;
+    a.t0 = t, a.t1 = t + 1;
+    if ((rc = launch_dense(n, a, n->max_in, s))) return rc;
+  }
+  for (int st = 0; st < L; ++st) {
+    const int back = L - 1 - st;
+    if (t - back < 0 && st < L - 1) continue;   // the step does not exist and h stays zero: nothing to do
+    GruStepArgs fa;
+    memset(&fa, 0, sizeof(fa));
+    const bool first = (t - back <= 0) || st == 0;   // first EXISTING step starts from h = 0
+    fa.h_prev = make_view(hs_ptr(n, c, false, st - 1 < 0 ? 0 : st - 1), H * NB, -t, N, H, B);
+    fa.h_out = make_view(hs_ptr(n, c, false, st), H * NB, -t, N, H, B);
+    fa.gi = make_view(n->gi_ring, 3 * H * NB, -back, N, 3 * H, B);
+    fa.t_mod_gi = L;
+    fa.t0 = t, fa.t1 = t + 1, fa.back = back, fa.padded = 0, fa.first = first, fa.store = 0;
+    if ((rc = launch_gru_step(n, fa, params, s))) return rc;
+  }
+  const View y1 = make_view(c.y1, H * NB, -t, N, H, B);
+  const View lg = make_view(out, O * NB, -t, N, O, B);
+  Wt w1{&n->o_w1, &n->o_b1, nullptr, H, H};
+  Wt w2{&n->o_w2, &n->o_b2, nullptr, H, O};
+  {
+    DenseArgs a;
+    memset(&a, 0, sizeof(a));
+    fill_dense_w(n, a, params, w1, 0);
+    a.x = make_view(hs_ptr(n, c, false, L - 1), H * NB, -t, N, H, B), a.y = y1, a.epilogue = kEpiRelu;
+    a.t0 = t, a.t1 = t + 1;
+    if ((rc = launch_dense(n, a, H, s))) return rc;
+  }
+  {
+    DenseArgs a;
+    memset(&a, 0, sizeof(a));
+    fill_dense_w(n, a, params, w2, 0);
+    a.x = y1, a.y = lg, a.epilogue = kEpiNone, a.t0 = t, a.t1 = t + 1;
+    if ((rc = launch_dense(n, a, H, s))) return rc;
   }
   return D2D_OK;
 }

@@ -227,6 +227,7 @@ __global__ void __launch_bounds__(256) dense_tile_kernel(const DenseArgs a) {
           if (o < out_dim) {
 #pragma unroll
             for (int q = 0; q < RPT / 4; ++q) {
+              if (b + 4 * q >= a.B) continue;   // RPT = 8: the second quad of rows may lie past the last env
               float4 v = make_float4(acc[4 * q][j], acc[4 * q + 1][j], acc[4 * q + 2][j], acc[4 * q + 3][j]);
               float4* dst = reinterpret_cast<float4*>(yp + (long long)o * a.B + 4 * q);
               if (a.epilogue == kEpiRelu) {
@@ -246,6 +247,155 @@ __global__ void __launch_bounds__(256) dense_tile_kernel(const DenseArgs a) {
       }
     }
     __syncthreads();   // every warp is done with buffer c & 1 before chunk c + 2 overwrites it
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Fused GRU step: gh = h_prev W_hh^T + b_hh (register-tiled as dense_tile_kernel<4, 24>) with the gate maths in
+// the epilogue, so the [rows x 3H] hidden projection never goes to HBM.  Warp w owns hidden units
+// [8 w, 8 w + 8); its 24 accumulator columns are (r, z, n) x 8 units.  H <= 64.
+// ------------------------------------------------------------------------------------------------
+struct GruStepArgs {
+  View h_prev, h_out, gi, acts;   // gi: input projections at time t - back (view.t_off carries the shift)
+  int t_mod_gi;                   // > 0: gi is a ring of that many time blocks (rollout), index taken modulo
+  const float* w;
+  long long w_agent_stride;
+  int whh_off[D2D_MAX_AGENTS];
+  int bhh_off[D2D_MAX_AGENTS];
+  int H, B, t0, t1;
+  int back, padded, first, store, t_episode0;
+};
+
+__device__ __forceinline__ float4 sigmoid4(float4 v) {
+  return make_float4(1.0f / (1.0f + expf(-v.x)), 1.0f / (1.0f + expf(-v.y)), 1.0f / (1.0f + expf(-v.z)),
+                     1.0f / (1.0f + expf(-v.w)));
+}
+
+__global__ void __launch_bounds__(256) gru_step_kernel(const GruStepArgs a) {
+  constexpr int RPT = 4, OPT = 24, ROWS = 32 * RPT, KC = kDenseKC, OUT_PAD = 8 * OPT;
+  extern __shared__ __align__(16) float sm[];
+  const int g = blockIdx.y, H = a.H;
+  const int in_dim = a.first ? 0 : H;
+  float* Ms = sm;                                        // [in_dim][OUT_PAD], column = warp * 24 + gate * 8 + unit
+  float* bs = Ms + (size_t)max(in_dim, 1) * OUT_PAD;
+  float* Xs = bs + OUT_PAD;                              // [2][KC][ROWS]
+  const float* W = a.w + g * a.w_agent_stride + a.whh_off[g];
+  const float* bias = a.w + g * a.w_agent_stride + a.bhh_off[g];
+  for (int i = threadIdx.x; i < in_dim * OUT_PAD; i += 256) {
+    const int k = i / OUT_PAD, col = i % OUT_PAD;
+    const int u = (col / OPT) * 8 + (col % 8), gate = (col % OPT) / 8;
+    Ms[i] = u < H ? W[(long long)(gate * H + u) * H + k] : 0.f;
+  }
+  for (int col = threadIdx.x; col < OUT_PAD; col += 256) {
+    const int u = (col / OPT) * 8 + (col % 8), gate = (col % OPT) / 8;
+    bs[col] = u < H ? bias[gate * H + u] : 0.f;
+  }
+  const int lane = threadIdx.x & 31, og = threadIdx.x >> 5;
+  const int tiles_per_t = (a.B + ROWS - 1) / ROWS;
+  const int n_tiles = (a.t1 - a.t0) * tiles_per_t;
+  const int nkc = max(1, (in_dim + KC - 1) / KC);
+  const int my_tiles = blockIdx.x < n_tiles ? (n_tiles - 1 - blockIdx.x) / gridDim.x + 1 : 0;
+  const int total = my_tiles * nkc;
+  const long long HB = (long long)H * a.B;
+
+  auto issue = [&](int c) {
+    const int tile = blockIdx.x + (c / nkc) * gridDim.x;
+    const int kc = c % nkc;
+    const int t = a.t0 + tile / tiles_per_t, b0 = (tile % tiles_per_t) * ROWS;
+    float* dst = Xs + (size_t)(c & 1) * KC * ROWS;
+    const float* src = view_ptr(a.h_prev, g, t, a.B, b0);
+    for (int i = threadIdx.x; i < KC * (ROWS / 4); i += 256) {
+      const int kk = i / (ROWS / 4), r4 = (i % (ROWS / 4)) * 4;
+      const int k = kc * KC + kk;
+      float* d = dst + kk * ROWS + r4;
+      if (k < in_dim && b0 + r4 < a.B) cp_async16(d, src + (long long)k * a.B + r4);
+      else *reinterpret_cast<float4*>(d) = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    cp_async_commit();
+  };
+
+  if (total > 0) issue(0);
+  float acc[RPT][OPT];
+  for (int c = 0; c < total; ++c) {
+    if (c + 1 < total) {
+      issue(c + 1);
+      cp_async_wait<1>();
+    } else {
+      cp_async_wait<0>();
+    }
+    __syncthreads();
+    const int kc = c % nkc;
+    if (kc == 0) {
+#pragma unroll
+      for (int j = 0; j < OPT; ++j) {
+        const float bv = bs[og * OPT + j];
+#pragma unroll
+        for (int r = 0; r < RPT; ++r) acc[r][j] = bv;
+      }
+    }
+    const float* xs = Xs + (size_t)(c & 1) * KC * ROWS + lane * RPT;
+    const int kmax = min(KC, in_dim - kc * KC);
+    const float* mrow = Ms + (size_t)kc * KC * OUT_PAD + og * OPT;
+#pragma unroll 2
+    for (int kk = 0; kk < kmax; ++kk) {
+      const float4 v = *reinterpret_cast<const float4*>(xs + kk * ROWS);
+      const float xv[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+      for (int q = 0; q < OPT / 4; ++q) {
+        const float4 m = *reinterpret_cast<const float4*>(mrow + kk * OUT_PAD + 4 * q);
+#pragma unroll
+        for (int r = 0; r < RPT; ++r) {
+          acc[r][4 * q + 0] = fmaf(xv[r], m.x, acc[r][4 * q + 0]);
+          acc[r][4 * q + 1] = fmaf(xv[r], m.y, acc[r][4 * q + 1]);
+          acc[r][4 * q + 2] = fmaf(xv[r], m.z, acc[r][4 * q + 2]);
+          acc[r][4 * q + 3] = fmaf(xv[r], m.w, acc[r][4 * q + 3]);
+        }
+      }
+    }
+    if (kc == nkc - 1) {
+      const int tile = blockIdx.x + (c / nkc) * gridDim.x;
+      const int t = a.t0 + tile / tiles_per_t, b = (tile % tiles_per_t) * ROWS + lane * RPT;
+      if (b < a.B) {
+        const bool exists = a.padded || (t - a.back >= a.t_episode0);
+        const float* hp = a.first ? nullptr : view_ptr(a.h_prev, g, t, a.B, b);
+        float* ho = view_ptr(a.h_out, g, t, a.B, b);
+        int tg = t + a.gi.t_off;
+        if (a.t_mod_gi > 0) tg = ((tg % a.t_mod_gi) + a.t_mod_gi) % a.t_mod_gi;
+        const float* gi = a.gi.p + (long long)tg * a.gi.t_stride + (long long)a.gi.f_off[g] * a.B + b;
+        float* ac = a.store ? view_ptr(a.acts, g, t, a.B, b) : nullptr;
+#pragma unroll
+        for (int uu = 0; uu < 8; ++uu) {
+          const int u = og * 8 + uu;
+          if (u < H) {
+            const long long uB = (long long)u * a.B;
+            const float4 hpv = hp ? *reinterpret_cast<const float4*>(hp + uB) : make_float4(0.f, 0.f, 0.f, 0.f);
+            float4 hn = hpv;
+            if (exists) {
+              const float4 gir = *reinterpret_cast<const float4*>(gi + uB);
+              const float4 giz = *reinterpret_cast<const float4*>(gi + HB + uB);
+              const float4 gin = *reinterpret_cast<const float4*>(gi + 2 * HB + uB);
+              const float4 ghr = make_float4(acc[0][uu], acc[1][uu], acc[2][uu], acc[3][uu]);
+              const float4 ghz = make_float4(acc[0][8 + uu], acc[1][8 + uu], acc[2][8 + uu], acc[3][8 + uu]);
+              const float4 ghn = make_float4(acc[0][16 + uu], acc[1][16 + uu], acc[2][16 + uu], acc[3][16 + uu]);
+              const float4 r = sigmoid4(make_float4(gir.x + ghr.x, gir.y + ghr.y, gir.z + ghr.z, gir.w + ghr.w));
+              const float4 z = sigmoid4(make_float4(giz.x + ghz.x, giz.y + ghz.y, giz.z + ghz.z, giz.w + ghz.w));
+              const float4 nn = make_float4(tanhf(gin.x + r.x * ghn.x), tanhf(gin.y + r.y * ghn.y),
+                                            tanhf(gin.z + r.z * ghn.z), tanhf(gin.w + r.w * ghn.w));
+              hn = make_float4((1.0f - z.x) * nn.x + z.x * hpv.x, (1.0f - z.y) * nn.y + z.y * hpv.y,
+                               (1.0f - z.z) * nn.z + z.z * hpv.z, (1.0f - z.w) * nn.w + z.w * hpv.w);
+              if (ac) {
+                *reinterpret_cast<float4*>(ac + uB) = r;
+                *reinterpret_cast<float4*>(ac + HB + uB) = z;
+                *reinterpret_cast<float4*>(ac + 2 * HB + uB) = nn;
+                *reinterpret_cast<float4*>(ac + 3 * HB + uB) = ghn;
+              }
+            }
+            *reinterpret_cast<float4*>(ho + uB) = hn;
+          }
+        }
+      }
+    }
+    __syncthreads();
   }
 }
 

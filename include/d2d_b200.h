@@ -206,6 +206,13 @@ int d2d_net_tensor(const d2d_net* net, int agent, int index, int64_t* offset, in
 int d2d_net_forward(d2d_net* net, const float* params, const float* x, int x_lead, int t0, int t1, int padded,
                     float* out, void* stream);
 
+/* Rollout step (PPO.select_action's network call, d2d_ppo.py:302-303): forward of the single time block t on
+ * the UNPADDED window.  The input projections of the previous L - 1 observations are kept in a ring inside the
+ * handle, so each observation is projected once per episode instead of L times.  Call with t = 0, 1, 2, ... in
+ * order within an episode; `params` must not change between the calls of one episode.  out f32 [1][N][O][B].   */
+int d2d_net_rollout_step(d2d_net* net, const float* params, const float* x, int x_lead, int t, float* out,
+                         void* stream);
+
 /* Distribution head on pre-activation outputs (PPO.select_action / PPO.evaluate, d2d_ppo.py:159-196).
  *   logits   f32 [n_t][N][O][B]
  *   actions  Bernoulli: channel bitmask [n_t][N][B] (1/2/4 bytes for O <= 8/16/32); Categorical: u8 index.

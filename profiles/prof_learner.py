@@ -18,6 +18,7 @@ env = CombinatorialEnv(n_envs=B, device=dev, seed=7, **kw)
 agent = iPPO(env, hidden_size=64, gamma=0.4, policy_lr=3e-4, value_lr=1e-3, useRNN=True, combinatorial=True,
              history_len=6, early_stopping=False, seed=1, scratch_bytes=6 << 30)
 agent.create_rollouts(B)
+agent.update_epoch()          # warm-up: scratch allocation happens here
 torch.cuda.synchronize()
 e0, e1, e2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
 e0.record()

@@ -131,15 +131,28 @@ def test_returns_scan_and_normalise(cuda_device):
                 assert rel_err(_rows(r32)[:, 0], g[f"{tag}/g{gamma}/ret"][:, col]) < TOL
 
 
+def _pick_envs(a, E, T, envs):
+    """[R = E*T, ...] episode-major rows -> the rows of the listed episodes, in that order."""
+    a = np.asarray(a)
+    return a.reshape((E, T) + a.shape[1:])[envs].reshape((len(envs) * T,) + a.shape[1:])
+
+
 @pytest.mark.parametrize("tag", ["small_gru", "small_mlp", "c3_gru"])
-@pytest.mark.parametrize("scratch", [0, 1 << 18])
-def test_ippo_gradients_and_adam(tag, scratch, cuda_device):
-    """PPO surrogate / critic MSE gradients of all agents in one launch vs torch autograd on the oracle; then Adam."""
+@pytest.mark.parametrize("scratch,pad4", [(0, False), (1 << 18, False), (0, True), (1 << 20, True)])
+def test_ippo_gradients_and_adam(tag, scratch, pad4, cuda_device):
+    """PPO surrogate / critic MSE gradients of all agents in one launch vs torch autograd on the oracle; then Adam.
+    pad4 repeats episodes up to a multiple of 4 envs, which selects the float4 register-tiled / fused-GRU kernels
+    (the fixtures' 5 or 3 episodes take the generic one-row-per-thread kernels)."""
     from d2d_ppo_b200 import _lib as L
     from d2d_ppo_b200.algorithms._nets import action_dtype, policy_head
     g = load_ppo_case(f"ippo_{tag}")
     m = g["meta"]
-    N, arch, E, T, H, Lh = m["N"], m["arch"], m["E"], m["T"], m["hidden"], m["L"]
+    N, arch, E0, T, H, Lh = m["N"], m["arch"], m["E"], m["T"], m["hidden"], m["L"]
+    envs = list(range(E0)) + ([i % E0 for i in range((-E0) % 4)] if pad4 else [])
+    E = len(envs)
+    g = dict(g)
+    for key in ("obs", "actions", "logp_old", "values", "advantages", "returns"):
+        g[key] = _pick_envs(g[key], E0, T, envs)
     cfg = g["config"]
     C = cfg["n_channels"]
     I = g["obs"].shape[2]
@@ -155,15 +168,20 @@ def test_ippo_gradients_and_adam(tag, scratch, cuda_device):
         val.load_state_dict(i, params_from(g, f"init/value{i}"))
     okind = L.OUT_SIGMOID if arch == "gru" else L.OUT_SOFTMAX
 
-    # rollout quantities: unpadded windows -> log-probs and values of the recorded actions
+    # rollout quantities: unpadded windows -> log-probs and values of the recorded actions, through both the
+    # chunked forward and the step-by-step rollout path with cached input projections
     packed = (g["actions"].astype(np.int64) * (1 << np.arange(C))).sum(-1)                      # [R, N]
     actions = torch.tensor(packed).reshape(E, T, N).permute(1, 2, 0).contiguous().to(action_dtype(0, C)).to(cuda_device)
     logits = pol.forward(x, lead, 0, T, padded=0)
+    stepwise = torch.cat([pol.rollout_step(x, lead, t) for t in range(T)])
+    assert rel_err(stepwise, logits) < 1e-6
     logp = torch.empty((T, N, E), device=cuda_device)
     policy_head(logits, N, E, C, okind, L.DIST_BERNOULLI, L.ACT_GIVEN, actions, logp)
     assert rel_err(_rows(logp), g["logp_old"]) < TOL
     values = val.forward(x, lead, 0, T, padded=0)[:, :, 0, :]
     assert rel_err(_rows(values), g["values"]) < TOL
+    vstep = torch.cat([val.rollout_step(x, lead, t) for t in range(T)])[:, :, 0, :]
+    assert rel_err(_rows(vstep), g["values"]) < TOL
 
     # gradients on padded windows
     def em(a):   # [R, N] -> [T, N, E]
@@ -189,13 +207,13 @@ def test_ippo_gradients_and_adam(tag, scratch, cuda_device):
             mine = pol.tensor_view(pol.grads, i, name)
             assert rel_err(mine, gr) < 2e-5, (i, name)
         mine_loss = -(sums[i, 0].item() / R) - 0.01 * sums[i, 1].item() / R
-        assert abs(mine_loss - float(loss)) <= 1e-5 * max(1.0, abs(float(loss)))
+        assert abs(mine_loss - float(loss.detach())) <= 1e-5 * max(1.0, abs(float(loss.detach())))
         vp = {k: v.clone().requires_grad_(True) for k, v in params_from(g, f"init/value{i}").items()}
         vloss = ((P.net_forward(vp, xi, "identity", valid).squeeze(-1) - torch.tensor(g["returns"][:, i])) ** 2).mean()
         vgrads = torch.autograd.grad(vloss, list(vp.values()))
         for (name, _), gr in zip(vp.items(), vgrads):
             assert rel_err(val.tensor_view(val.grads, i, name), gr) < 2e-5, (i, name)
-        assert abs(vsum[i].item() / R - float(vloss)) <= 1e-5 * max(1.0, float(vloss))
+        assert abs(vsum[i].item() / R - float(vloss.detach())) <= 1e-5 * max(1.0, float(vloss.detach()))
 
     # Adam: one step from the oracle's gradient == one device step (same gradient buffer)
     before = pol.params.clone()
