@@ -40,6 +40,7 @@ class NetConfig(C.Structure):
         ("arch", C.c_int32), ("out_kind", C.c_int32), ("n_agents", C.c_int32), ("n_envs", C.c_int32),
         ("hidden", C.c_int32), ("n_out", C.c_int32), ("history_len", C.c_int32), ("in_rows", C.c_int32),
         ("in_dim", C.POINTER(C.c_int32)), ("in_off", C.POINTER(C.c_int32)), ("scratch_bytes", C.c_int64),
+        ("inputs_bf16_exact", C.c_int32), ("reserved0", C.c_int32),
     ]
 
 

@@ -30,7 +30,7 @@ class NetSet:
     """N independent networks of one architecture evaluated in one launch (grid.y = agent)."""
 
     def __init__(self, arch, out_kind, n_agents, n_envs, in_dim, in_off, in_rows, hidden, n_out, history_len, device,
-                 lr, scratch_bytes=0, generator=None):
+                 lr, scratch_bytes=0, generator=None, inputs_bf16_exact=False):
         self.arch, self.out_kind = arch, out_kind
         self.N, self.B, self.H, self.O = int(n_agents), int(n_envs), int(hidden), int(n_out)
         self.L = int(history_len) if arch == L.NET_GRU else 1
@@ -45,7 +45,8 @@ class NetSet:
         cfg = L.NetConfig(arch=arch, out_kind=out_kind, n_agents=self.N, n_envs=self.B, hidden=self.H, n_out=self.O,
                           history_len=self.L, in_rows=self.in_rows,
                           in_dim=a_dim.ctypes.data_as(C.POINTER(C.c_int32)),
-                          in_off=a_off.ctypes.data_as(C.POINTER(C.c_int32)), scratch_bytes=int(scratch_bytes))
+                          in_off=a_off.ctypes.data_as(C.POINTER(C.c_int32)), scratch_bytes=int(scratch_bytes),
+                          inputs_bf16_exact=int(bool(inputs_bf16_exact)), reserved0=0)
         h = C.c_void_p()
         with torch.cuda.device(self.device):
             L.check(self._lib.d2d_net_create(C.byref(cfg), C.byref(h)))

@@ -1,0 +1,334 @@
+// Fused GRU window on the 5th-generation tensor cores (tcgen05 + TMEM), sm_100a.
+//
+//   h_last[row] = GRU(x[t-L+1 .. t][row]; W_ih, W_hh, b_ih, b_hh)   for every row (time t, env b) of every agent
+//
+// replaces, for the rollout / inference direction, L x (hidden-projection GEMM + gate kernel) and the input
+// projection GEMM (reference: RNN.forward, algorithms/d2d_ppo.py:46-54, called once per env step by
+// PPO.select_action at :302-303).  Nothing but the observations (L x I floats per row) is read and nothing but
+// h_last (H floats per row) is written: the [rows x 3H] projections live in TMEM, h lives in registers and in
+// shared memory as the next step's A operand.
+//
+// fp32 parity on tensor cores: every fp32 operand is split into three bf16 planes (v = p0 + p1 + p2, 24 mantissa
+// bits), and a product keeps the six plane pairs with i + j <= 2 (error ~2^-24 per term, measured 1.1e-6 norm-wise
+// on a K = 64 GEMM incl. the tensor core's own accumulation).  Observations are small integers (exact in bf16), so
+// the input projection needs only x(1 plane) x W_ih(3 planes).
+//
+// CTA = 9 warps.  Two 128-row tiles ("slots") are in flight per CTA so that the tensor pipe works on one slot while
+// the other slot's gates are evaluated:
+//   warps 0-3 : slot 0 rows (TMEM lane quadrant = warp % 4): stage x, read gate pre-activations with tcgen05.ld,
+//               gate maths, write h (3 bf16 planes) + next x into the canonical K-major smem layout
+//   warps 4-7 : the same for slot 1
+//   warp  8   : one elected lane issues tcgen05.mma (x W_ih^T into TMEM columns [0, 3H), h W_hh^T accumulated into
+//               [0, 2H) for r, z and into [3H, 4H) for the n gate, which needs gi_n and gh_n separately)
+// Hand-offs are mbarriers: a_ready[slot] (128 arrivals: operands staged) and d_ready[slot] (tcgen05.commit).
+// Shared memory (H = 64, I <= 32): W_ih planes 36 KB + W_hh planes 72 KB + h planes 2 x 48 KB + x 2 x 8 KB = 221 KB;
+// TMEM: 2 slots x 4H = 512 columns.
+#pragma once
+#include <cuda_bf16.h>
+
+#include "learner_kernels.cuh"
+
+namespace d2d {
+
+struct GruTcArgs {
+  View x;        // observations: element (agent g, feature f, time t, env b); time blocks before 0 are zero
+  View h_out;    // [.. H ..] last hidden state
+  const float* w;
+  long long w_agent_stride;
+  int wih_off[D2D_MAX_AGENTS], whh_off[D2D_MAX_AGENTS], bih_off[D2D_MAX_AGENTS], bhh_off[D2D_MAX_AGENTS];
+  int in_dim[D2D_MAX_AGENTS];
+  int L, B, t0, t1;
+  int padded;    // 1: steps before the episode start run on zero inputs; 0: they do not exist (rollout windows)
+};
+
+namespace tc {
+
+constexpr int kM = 128;       // rows per slot
+constexpr int kKx = 32;       // padded input size (I <= 32)
+constexpr int kThreads = 288;
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+// canonical K-major, no-swizzle UMMA layout of a [rows][kc] bf16 tile: 8-row x 16-byte core matrices,
+// K-adjacent core matrices contiguous (LBO = 128 B), 8-row groups (kc / 8) * 128 B apart (SBO)
+__device__ __forceinline__ int canon16(int r, int k, int kc) {
+  return ((r >> 3) * (kc >> 3) + (k >> 3)) * 64 + (r & 7) * 8 + (k & 7);
+}
+__device__ __forceinline__ uint64_t desc16(uint32_t saddr, int kc) {
+  const uint64_t start = (saddr & 0x3FFFFu) >> 4;
+  const uint64_t lbo = 128 >> 4, sbo = (uint64_t)((kc >> 3) * 128) >> 4;
+  return start | (lbo << 16) | (sbo << 32) | (1ull << 46);   // version 1 (Blackwell), no swizzle, base offset 0
+}
+// instruction descriptor: D = F32, A = B = BF16, both K-major, M = 128
+__device__ __forceinline__ uint32_t idesc_bf16(int n) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(kM >> 4) << 24);
+}
+__device__ __forceinline__ void mma_bf16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, bool accum) {
+  const uint32_t acc = accum ? 1u : 0u;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
+      : "memory");
+}
+__device__ __forceinline__ void mbar_init(uint64_t* b, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(b)), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* b) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(b)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* b, uint32_t parity) {
+  uint32_t done = 0;
+  while (!done) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(smem_u32(b)), "r"(parity)
+        : "memory");
+  }
+}
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, float* v) {
+  uint32_t r[8];
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+               : "r"(taddr));
+#pragma unroll
+  for (int j = 0; j < 8; ++j) v[j] = __uint_as_float(r[j]);
+}
+__device__ __forceinline__ void split3(float v, __nv_bfloat16& p0, __nv_bfloat16& p1, __nv_bfloat16& p2) {
+  p0 = __float2bfloat16_rn(v);
+  float r = v - __bfloat162float(p0);
+  p1 = __float2bfloat16_rn(r);
+  r -= __bfloat162float(p1);
+  p2 = __float2bfloat16_rn(r);
+}
+__device__ __forceinline__ uint32_t pack2(__nv_bfloat16 a, __nv_bfloat16 b) {
+  return (uint32_t)__bfloat16_as_ushort(a) | ((uint32_t)__bfloat16_as_ushort(b) << 16);
+}
+
+template <int H>
+struct Smem {
+  static constexpr int kWih = 3 * H * kKx;        // bf16 elements per plane
+  static constexpr int kWhh = 3 * H * H;
+  static constexpr int kAh = kM * H;
+  static constexpr int kAx = kM * kKx;
+  static constexpr size_t bytes = (size_t)(3 * kWih + 3 * kWhh + 2 * 3 * kAh + 2 * kAx) * 2 + 4 * H * 4 + 64;
+};
+
+}  // namespace tc
+
+template <int H>
+__global__ void __launch_bounds__(tc::kThreads, 1) gru_window_tc_kernel(const GruTcArgs a) {
+  using namespace tc;
+  using S = Smem<H>;
+  static_assert(H % 16 == 0 && H >= 16 && H <= 64, "H in {16, 32, 48, 64}");
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  __nv_bfloat16* wih = reinterpret_cast<__nv_bfloat16*>(smem_raw);      // [3 planes][3H][kKx]
+  __nv_bfloat16* whh = wih + 3 * S::kWih;                               // [3 planes][3H][H]
+  __nv_bfloat16* ah = whh + 3 * S::kWhh;                                // [2 slots][3 planes][128][H]
+  __nv_bfloat16* ax = ah + 2 * 3 * S::kAh;                              // [2 slots][128][kKx]
+  float* bias = reinterpret_cast<float*>(ax + 2 * S::kAx);              // [2H] b_ih + b_hh (r, z), [H] b_in, [H] b_hn
+  uint64_t* bars = reinterpret_cast<uint64_t*>(bias + 4 * H);           // a_ready[2], d_ready[2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 4);
+  uint64_t* a_ready = bars;
+  uint64_t* d_ready = bars + 2;
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int g = blockIdx.y;
+  const int I = a.in_dim[g];
+  const float* Wih = a.w + g * a.w_agent_stride + a.wih_off[g];
+  const float* Whh = a.w + g * a.w_agent_stride + a.whh_off[g];
+  const float* bih = a.w + g * a.w_agent_stride + a.bih_off[g];
+  const float* bhh = a.w + g * a.w_agent_stride + a.bhh_off[g];
+
+  // ---- one-time setup: weights -> three bf16 planes in the canonical layout, biases, barriers, TMEM ----
+  for (int i = tid; i < 3 * H * kKx; i += kThreads) {
+    const int n = i / kKx, k = i % kKx;
+    __nv_bfloat16 p0, p1, p2;
+    split3(k < I ? Wih[(long long)n * I + k] : 0.f, p0, p1, p2);
+    const int o = canon16(n, k, kKx);
+    wih[o] = p0, wih[S::kWih + o] = p1, wih[2 * S::kWih + o] = p2;
+  }
+  for (int i = tid; i < 3 * H * H; i += kThreads) {
+    const int n = i / H, k = i % H;
+    __nv_bfloat16 p0, p1, p2;
+    split3(Whh[i], p0, p1, p2);
+    const int o = canon16(n, k, H);
+    whh[o] = p0, whh[S::kWhh + o] = p1, whh[2 * S::kWhh + o] = p2;
+  }
+  for (int i = tid; i < 4 * H; i += kThreads) {
+    float v;
+    if (i < 2 * H) v = bih[i] + bhh[i];
+    else if (i < 3 * H) v = bih[i];            // b_in
+    else v = bhh[i - H];                       // b_hn
+    bias[i] = v;
+  }
+  if (tid == 0) {
+    mbar_init(&a_ready[0], kM), mbar_init(&a_ready[1], kM);
+    mbar_init(&d_ready[0], 1), mbar_init(&d_ready[1], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 8) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(tmem_slot)));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem = *tmem_slot;
+
+  const int L = a.L;
+  const int pairs_per_t = (a.B + 2 * kM - 1) / (2 * kM);
+  const int n_pairs = (a.t1 - a.t0) * pairs_per_t;
+
+  if (warp == 8) {
+    // =================== MMA issuer ===================
+    if (lane == 0) {
+      uint32_t ph[2] = {0, 0};
+      const uint32_t id3 = idesc_bf16(3 * H), id2 = idesc_bf16(2 * H), id1 = idesc_bf16(H);
+      const uint32_t sbo_h = (H >> 3) * 128;   // bytes between 8-row groups of a [.][H] tile
+      for (int p = blockIdx.x; p < n_pairs; p += gridDim.x) {
+        const int t = a.t0 + p / pairs_per_t;
+        const int s0 = a.padded ? 0 : max(0, L - 1 - t);
+        for (int s = s0; s < L; ++s) {
+          for (int slot = 0; slot < 2; ++slot) {
+            mbar_wait(&a_ready[slot], ph[slot]);
+            ph[slot] ^= 1u;
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const uint32_t d = tmem + (uint32_t)slot * (4 * H);
+            const uint32_t ax_addr = smem_u32(ax + slot * S::kAx);
+            // input projection: x (exact in bf16) against the three planes of W_ih -> columns [0, 3H)
+#pragma unroll
+            for (int j = 0; j < 3; ++j)
+#pragma unroll
+              for (int k16 = 0; k16 < kKx / 16; ++k16)
+                mma_bf16(d, desc16(ax_addr + k16 * 256, kKx), desc16(smem_u32(wih + j * S::kWih) + k16 * 256, kKx), id3,
+                         !(j == 0 && k16 == 0));
+            if (s > s0) {
+              // hidden projection, plane pairs (i, j) with i + j <= 2: r, z accumulate onto the input projection,
+              // the n gate gets its own columns [3H, 4H)
+              bool first = true;
+#pragma unroll
+              for (int i = 0; i < 3; ++i)
+#pragma unroll
+                for (int j = 0; j < 3; ++j) {
+                  if (i + j > 2) continue;
+                  const uint32_t ah_addr = smem_u32(ah + (slot * 3 + i) * S::kAh);
+                  const uint32_t wb = smem_u32(whh + j * S::kWhh);
+#pragma unroll
+                  for (int k16 = 0; k16 < H / 16; ++k16) {
+                    const uint64_t ad = desc16(ah_addr + k16 * 256, H);
+                    mma_bf16(d, ad, desc16(wb + k16 * 256, H), id2, true);
+                    mma_bf16(d + 3 * H, ad, desc16(wb + (2 * H / 8) * sbo_h + k16 * 256, H), id1, !first);
+                    first = false;
+                  }
+                }
+            }
+            asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];"
+                         ::"r"(smem_u32(&d_ready[slot]))
+                         : "memory");
+          }
+        }
+      }
+    }
+  } else {
+    // =================== gate warps: slot = warp / 4, row = 32 (warp % 4) + lane ===================
+    const int slot = warp >> 2;
+    const int row = ((warp & 3) << 5) + lane;
+    const uint32_t lane_addr = (uint32_t)((warp & 3) << 5) << 16;
+    __nv_bfloat16* my_ax = ax + slot * S::kAx;
+    __nv_bfloat16* my_ah = ah + slot * 3 * S::kAh;
+    uint32_t ph = 0;
+    float h[H];
+
+    auto load_x = [&](int t_obs, int b, float* xr) {   // observation of this row at time t_obs -> registers
+      const bool ok = b < a.B;
+      const float* xp = view_ptr(a.x, g, t_obs, a.B, ok ? b : 0);
+#pragma unroll
+      for (int k = 0; k < kKx; ++k) xr[k] = (ok && k < I) ? xp[(long long)k * a.B] : 0.f;
+    };
+    auto stage_x = [&](const float* xr) {              // registers -> bf16 A tile (canonical layout), 16 B per store
+#pragma unroll
+      for (int kc = 0; kc < kKx / 8; ++kc) {
+        uint4 v;
+        v.x = pack2(__float2bfloat16_rn(xr[kc * 8 + 0]), __float2bfloat16_rn(xr[kc * 8 + 1]));
+        v.y = pack2(__float2bfloat16_rn(xr[kc * 8 + 2]), __float2bfloat16_rn(xr[kc * 8 + 3]));
+        v.z = pack2(__float2bfloat16_rn(xr[kc * 8 + 4]), __float2bfloat16_rn(xr[kc * 8 + 5]));
+        v.w = pack2(__float2bfloat16_rn(xr[kc * 8 + 6]), __float2bfloat16_rn(xr[kc * 8 + 7]));
+        *reinterpret_cast<uint4*>(my_ax + canon16(row, kc * 8, kKx)) = v;
+      }
+    };
+    auto publish = [&]() {   // operands of the next MMA batch are in place (and our TMEM reads are done)
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      mbar_arrive(&a_ready[slot]);
+    };
+
+    for (int p = blockIdx.x; p < n_pairs; p += gridDim.x) {
+      const int t = a.t0 + p / pairs_per_t;
+      const int b = (p % pairs_per_t) * (2 * kM) + slot * kM + row;
+      const int s0 = a.padded ? 0 : max(0, L - 1 - t);
+      float xr[kKx];
+      load_x(t - (L - 1 - s0), b, xr);
+      stage_x(xr);
+      publish();
+#pragma unroll
+      for (int u = 0; u < H; ++u) h[u] = 0.f;
+      for (int s = s0; s < L; ++s) {
+        const bool has_next = s + 1 < L;
+        if (has_next) load_x(t - (L - 2 - s), b, xr);   // in flight during the gate maths
+        mbar_wait(&d_ready[slot], ph);
+        ph ^= 1u;
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const uint32_t d = tmem + (uint32_t)slot * (4 * H) + lane_addr;
+        const bool first = s == s0;
+#pragma unroll
+        for (int c = 0; c < H / 8; ++c) {
+          float pr[8], pz[8], pin[8], phn[8];
+          tmem_ld8(d + c * 8, pr);
+          tmem_ld8(d + H + c * 8, pz);
+          tmem_ld8(d + 2 * H + c * 8, pin);
+          if (!first) tmem_ld8(d + 3 * H + c * 8, phn);
+          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+          __nv_bfloat16 q0[8], q1[8], q2[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const int u = c * 8 + j;
+            const float r = 1.0f / (1.0f + expf(-(pr[j] + bias[u])));
+            const float z = 1.0f / (1.0f + expf(-(pz[j] + bias[H + u])));
+            const float ghn = (first ? 0.f : phn[j]) + bias[3 * H + u];
+            const float nn = tanhf(pin[j] + bias[2 * H + u] + r * ghn);
+            h[u] = (1.0f - z) * nn + z * h[u];
+            split3(h[u], q0[j], q1[j], q2[j]);
+          }
+          if (has_next) {
+            const int o = canon16(row, c * 8, H);
+            *reinterpret_cast<uint4*>(my_ah + o) =
+                make_uint4(pack2(q0[0], q0[1]), pack2(q0[2], q0[3]), pack2(q0[4], q0[5]), pack2(q0[6], q0[7]));
+            *reinterpret_cast<uint4*>(my_ah + S::kAh + o) =
+                make_uint4(pack2(q1[0], q1[1]), pack2(q1[2], q1[3]), pack2(q1[4], q1[5]), pack2(q1[6], q1[7]));
+            *reinterpret_cast<uint4*>(my_ah + 2 * S::kAh + o) =
+                make_uint4(pack2(q2[0], q2[1]), pack2(q2[2], q2[3]), pack2(q2[4], q2[5]), pack2(q2[6], q2[7]));
+          }
+        }
+        if (has_next) {
+          stage_x(xr);
+          publish();
+        } else {
+          // TMEM reads of this tile are complete before the next tile's first MMA: its publish() fences them
+          if (b < a.B) {
+            float* ho = view_ptr(a.h_out, g, t, a.B, b);
+#pragma unroll
+            for (int u = 0; u < H; ++u) ho[(long long)u * a.B] = h[u];
+          }
+        }
+      }
+    }
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 8) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem));
+}
+
+}  // namespace d2d

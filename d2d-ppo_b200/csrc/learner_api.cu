@@ -16,12 +16,14 @@
 #include <new>
 #include <vector>
 
+#include "gru_tc.cuh"
 #include "learner_pointwise.cuh"
 
 using namespace d2d;
 
 struct d2d_net {
   int arch, out_kind, N, B, H, O, L, in_rows;
+  int x_exact = 0;   // inputs are exactly representable in bf16 (integer observations): tensor-core GRU path allowed
   std::vector<int> in_dim, in_off;
   int max_in;
   long long stride;  // floats per agent block
@@ -191,6 +193,51 @@ static int launch_gru_step(const d2d_net* n, GruStepArgs& a, const float* params
   return D2D_OK;
 }
 
+// tensor-core fused GRU window (gru_tc.cuh): x windows -> last hidden state, no intermediate in HBM
+static bool gru_tc_eligible(const d2d_net* n) {
+  static int disabled = -1;
+  if (disabled < 0) {
+    const char* e = getenv("D2D_DISABLE_TCGEN05");
+    disabled = (e && e[0] == '1') ? 1 : 0;
+  }
+  return !disabled && n->arch == D2D_NET_GRU && n->x_exact && n->max_in <= tc::kKx &&
+         (n->H == 16 || n->H == 32 || n->H == 48 || n->H == 64);
+}
+
+template <int H>
+static int launch_gru_tc_h(const d2d_net* n, const GruTcArgs& a, cudaStream_t s) {
+  static bool attr = false;
+  if (!attr) {
+    D2D_CUDA(cudaFuncSetAttribute(gru_window_tc_kernel<H>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  (int)tc::Smem<H>::bytes));
+    attr = true;
+  }
+  const int pairs = (a.t1 - a.t0) * ((n->B + 2 * tc::kM - 1) / (2 * tc::kM));
+  if (pairs <= 0) return D2D_OK;
+  const int gx = std::max(1, std::min(pairs, 148 / n->N));   // one CTA per SM (all of its shared memory and TMEM)
+  gru_window_tc_kernel<H><<<dim3(gx, n->N), tc::kThreads, tc::Smem<H>::bytes, s>>>(a);
+  D2D_LAUNCHED();
+  return D2D_OK;
+}
+
+static int launch_gru_tc(const d2d_net* n, const float* params, const View& x, const View& h_out, int t0, int t1,
+                         int padded, cudaStream_t s) {
+  GruTcArgs a;
+  memset(&a, 0, sizeof(a));
+  a.x = x, a.h_out = h_out, a.w = params, a.w_agent_stride = n->stride;
+  for (int g = 0; g < n->N; ++g) {
+    a.wih_off[g] = n->o_wih[g], a.whh_off[g] = n->o_whh[g], a.bih_off[g] = n->o_bih[g], a.bhh_off[g] = n->o_bhh[g];
+    a.in_dim[g] = n->in_dim[g];
+  }
+  a.L = n->L, a.B = n->B, a.t0 = t0, a.t1 = t1, a.padded = padded;
+  switch (n->H) {
+    case 16: return launch_gru_tc_h<16>(n, a, s);
+    case 32: return launch_gru_tc_h<32>(n, a, s);
+    case 48: return launch_gru_tc_h<48>(n, a, s);
+    default: return launch_gru_tc_h<64>(n, a, s);
+  }
+}
+
 static int launch_gate(const GateArgs& a, int N, bool bwd, cudaStream_t s) {
   const long long n = (long long)(a.t1 - a.t0) * a.H * a.B;
   if (n <= 0) return D2D_OK;
@@ -289,9 +336,14 @@ static int forward_chunk(d2d_net* n, const float* params, const float* x, int x_
     last = xin;
   } else {
     const int L = n->L, halo = c.halo;
+    const bool use_tc = !train && gru_tc_eligible(n);   // inference direction: tcgen05 fused window (gru_tc.cuh)
+    if (use_tc) {
+      const View hl = make_view(hs_ptr(n, c, train, L - 1), H * NB, -c0, N, H, B);
+      if ((rc = launch_gru_tc(n, params, xin, hl, c0, c1, padded, s))) return rc;
+    }
     // input projections of every observation the chunk's windows touch: times [c0 - halo, c1)
     const View gi = make_view(c.gi, 3 * H * NB, -(c0 - halo), N, 3 * H, B);
-    {
+    if (!use_tc) {
       DenseArgs a;
       memset(&a, 0, sizeof(a));
       Wt wih{&n->o_wih, &n->o_bih, &n->in_dim, 0, 3 * H};
@@ -300,7 +352,7 @@ static int forward_chunk(d2d_net* n, const float* params, const float* x, int x_
       if ((rc = launch_dense(n, a, n->max_in, s))) return rc;
     }
     const View gh = make_view(c.gh, 3 * H * NB, -c0, N, 3 * H, B);
-    for (int st = 0; st < L; ++st) {
+    for (int st = 0; st < L && !use_tc; ++st) {
       const View hprev = make_view(hs_ptr(n, c, train, st - 1 < 0 ? 0 : st - 1), H * NB, -c0, N, H, B);
       const View hout = make_view(hs_ptr(n, c, train, st), H * NB, -c0, N, H, B);
       if (B % 4 == 0) {
@@ -444,6 +496,7 @@ extern "C" int d2d_net_create(const d2d_net_config* cfg, d2d_net** out) {
   n->arch = cfg->arch, n->out_kind = cfg->out_kind, n->N = cfg->n_agents, n->B = cfg->n_envs, n->H = cfg->hidden;
   n->O = cfg->n_out, n->L = cfg->arch == D2D_NET_GRU ? cfg->history_len : 1, n->in_rows = cfg->in_rows;
   n->scratch_bytes = cfg->scratch_bytes > 0 ? cfg->scratch_bytes : (2ll << 30);
+  n->x_exact = cfg->inputs_bf16_exact != 0;
   n->max_in = 0, n->stride = 0;
   const int H = n->H, O = n->O;
   for (int g = 0; g < n->N; ++g) {
@@ -546,14 +599,19 @@ extern "C" int d2d_net_rollout_step(d2d_net* n, const float* params, const float
   cudaStream_t s = as_stream(stream);
   const int N = n->N, B = n->B, H = n->H, O = n->O, L = n->L;
   const long long NB = (long long)N * B;
-  if (!n->gi_ring) D2D_CUDA(cudaMalloc((void**)&n->gi_ring, (size_t)L * 3 * H * NB * 4));
   Chunk c;
   if ((rc = plan_chunk(n, false, 1, c))) return rc;
   View xin;
   memset(&xin, 0, sizeof(xin));
   xin.p = const_cast<float*>(x), xin.t_stride = (long long)n->in_rows * B, xin.t_off = x_lead;
   for (int g = 0; g < N; ++g) xin.f_off[g] = n->in_off[g];
-  {   // input projection of the NEW observation only; the previous L - 1 are still in the ring
+  const bool use_tc = gru_tc_eligible(n);
+  if (use_tc) {   // the tensor-core window kernel re-reads the L observations (L x I floats per row): no ring needed
+    const View hl = make_view(hs_ptr(n, c, false, L - 1), H * NB, -t, N, H, B);
+    if ((rc = launch_gru_tc(n, params, xin, hl, t, t + 1, 0, s))) return rc;
+  }
+  if (!use_tc && !n->gi_ring) D2D_CUDA(cudaMalloc((void**)&n->gi_ring, (size_t)L * 3 * H * NB * 4));
+  if (!use_tc) {   // input projection of the NEW observation only; the previous L - 1 are still in the ring
     DenseArgs a;
     memset(&a, 0, sizeof(a));
     Wt wih{&n->o_wih, &n->o_bih, &n->in_dim, 0, 3 * H};
@@ -562,7 +620,7 @@ extern "C" int d2d_net_rollout_step(d2d_net* n, const float* params, const float
     a.t0 = t, a.t1 = t + 1;
     if ((rc = launch_dense(n, a, n->max_in, s))) return rc;
   }
-  for (int st = 0; st < L; ++st) {
+  for (int st = 0; st < L && !use_tc; ++st) {
     const int back = L - 1 - st;
     if (t - back < 0 && st < L - 1) continue;   // the step does not exist and h stays zero: nothing to do
     GruStepArgs fa;

@@ -187,6 +187,10 @@ typedef struct d2d_net_config {
   const int32_t* in_dim;   /* [N] host: input size of agent k                                   */
   const int32_t* in_off;   /* [N] host: first feature row of agent k inside a time block        */
   int64_t scratch_bytes;   /* activation scratch budget per call (0: 2 GiB)                     */
+  int32_t inputs_bf16_exact; /* 1: every input value is exactly representable in bf16 (the integer-valued
+                                observations of CombinatorialEnv / D2DEnv): allows the tcgen05 GRU-window
+                                kernel, whose input projection uses a single bf16 plane for x            */
+  int32_t reserved0;
 } d2d_net_config;
 
 typedef struct d2d_net d2d_net;
