@@ -53,9 +53,12 @@ class PPOBase:
         self.seed = int(seed)
         self._gen = torch.Generator().manual_seed(self.seed)      # identical initial weights on every rank
         self._scratch = int(scratch_bytes)
+        # integer-valued observations (buffers, channel bits, ack in {-1, 0, 1}) are exact in bf16, which lets the
+        # networks' rollout forward run on the tcgen05 GRU-window kernel; the selection env's 1/count acks are not
+        self.exact_obs = kind in ("bernoulli_mask", "binary")
         self.policies = NetSet(self.arch, self.policy_out, self.n_agents, self.B, self.obs_dim, self.obs_off,
                                self.obs_rows, self.hidden_size, self.n_actions, self.history_len, self.device,
-                               policy_lr, scratch_bytes, self._gen)
+                               policy_lr, scratch_bytes, self._gen, inputs_bf16_exact=self.exact_obs)
         self._act_dtype = action_dtype(self.dist_kind, self.n_actions)
         self._iter = 0
         T, B, N, dev = self.T, self.B, self.n_agents, self.device

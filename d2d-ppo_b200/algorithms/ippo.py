@@ -22,7 +22,7 @@ class iPPO(PPOBase):
         # every agent owns a critic of the policy's architecture with one identity output (ippo.py:143,146)
         self.values = NetSet(self.arch, L.OUT_IDENTITY, self.n_agents, self.B, self.obs_dim, self.obs_off,
                              self.obs_rows, self.hidden_size, 1, self.history_len, self.device, value_lr,
-                             scratch_bytes, self._gen)
+                             scratch_bytes, self._gen, inputs_bf16_exact=self.exact_obs)
         self.value_buf = torch.zeros((self.T, self.n_agents, self.B), dtype=torch.float32, device=self.device)
 
     # ------------------------------------------------------------------ rollout (ippo.py:277-343)

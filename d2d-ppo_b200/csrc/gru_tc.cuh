@@ -13,14 +13,17 @@
 // on a K = 64 GEMM incl. the tensor core's own accumulation).  Observations are small integers (exact in bf16), so
 // the input projection needs only x(1 plane) x W_ih(3 planes).
 //
-// CTA = 9 warps.  Two 128-row tiles ("slots") are in flight per CTA so that the tensor pipe works on one slot while
+// CTA = 17 warps.  Two 128-row tiles ("slots") are in flight per CTA so that the tensor pipe works on one slot while
 // the other slot's gates are evaluated:
-//   warps 0-3 : slot 0 rows (TMEM lane quadrant = warp % 4): stage x, read gate pre-activations with tcgen05.ld,
-//               gate maths, write h (3 bf16 planes) + next x into the canonical K-major smem layout
-//   warps 4-7 : the same for slot 1
-//   warp  8   : one elected lane issues tcgen05.mma (x W_ih^T into TMEM columns [0, 3H), h W_hh^T accumulated into
-//               [0, 2H) for r, z and into [3H, 4H) for the n gate, which needs gi_n and gh_n separately)
-// Hand-offs are mbarriers: a_ready[slot] (128 arrivals: operands staged) and d_ready[slot] (tcgen05.commit).
+//   warps 0-7  : slot 0; warp w serves TMEM lane quadrant w % 4 (rows 32 (w % 4) + lane) and the hidden units of
+//                half (w / 4) % 2: stage x, read gate pre-activations with tcgen05.ld, gate maths, write h
+//                (3 bf16 planes) + next x into the canonical K-major smem layout
+//   warps 8-15 : the same for slot 1
+//   warp  16   : one elected lane issues tcgen05.mma (x W_ih^T into TMEM columns [0, 3H), h W_hh^T accumulated
+//                into [0, 2H) for r, z and into [3H, 4H) for the n gate, which needs gi_n and gh_n separately)
+// Hand-offs are mbarriers: a_ready[slot] (256 arrivals: operands staged) and d_ready[slot] (tcgen05.commit).
+// The kernel is bound by the gate maths (6 MUFU per (row, unit, step)), not by the tensor pipe: sigmoid / tanh use
+// ex2.approx + rcp.approx (rel. error ~2^-21), the bf16 planes are cut by integer masking instead of F2F.
 // Shared memory (H = 64, I <= 32): W_ih planes 36 KB + W_hh planes 72 KB + h planes 2 x 48 KB + x 2 x 8 KB = 221 KB;
 // TMEM: 2 slots x 4H = 512 columns.
 #pragma once
@@ -45,7 +48,8 @@ namespace tc {
 
 constexpr int kM = 128;       // rows per slot
 constexpr int kKx = 32;       // padded input size (I <= 32)
-constexpr int kThreads = 288;
+constexpr int kThreads = 544;
+constexpr int kGateThreads = 256;   // per slot
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -102,6 +106,26 @@ __device__ __forceinline__ void split3(float v, __nv_bfloat16& p0, __nv_bfloat16
   r -= __bfloat162float(p1);
   p2 = __float2bfloat16_rn(r);
 }
+// v = t0 + t1 + t2 (+ < 2^-24 |v|) with every t the top 16 bits of an fp32 word, i.e. a bf16 value: cut by masking
+// (ALU pipe) rather than by F2F conversions (quarter-rate XU pipe, which the gate maths already saturates)
+__device__ __forceinline__ void split3_trunc(float v, uint32_t& t0, uint32_t& t1, uint32_t& t2) {
+  t0 = __float_as_uint(v) & 0xFFFF0000u;
+  const float r1 = v - __uint_as_float(t0);
+  t1 = __float_as_uint(r1) & 0xFFFF0000u;
+  t2 = __float_as_uint(r1 - __uint_as_float(t1));
+}
+// two fp32 words -> their top halves packed as two bf16 (element 0 in the low half)
+__device__ __forceinline__ uint32_t pack_hi(uint32_t a, uint32_t b) { return __byte_perm(a, b, 0x7632); }
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float rcp_approx(float x) {
+  float y;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
 __device__ __forceinline__ uint32_t pack2(__nv_bfloat16 a, __nv_bfloat16 b) {
   return (uint32_t)__bfloat16_as_ushort(a) | ((uint32_t)__bfloat16_as_ushort(b) << 16);
 }
@@ -156,19 +180,20 @@ __global__ void __launch_bounds__(tc::kThreads, 1) gru_window_tc_kernel(const Gr
     const int o = canon16(n, k, H);
     whh[o] = p0, whh[S::kWhh + o] = p1, whh[2 * S::kWhh + o] = p2;
   }
+  // biases, pre-scaled for the ex2-based gates: sigmoid(a) = 1 / (1 + 2^(-a log2 e))
   for (int i = tid; i < 4 * H; i += kThreads) {
     float v;
-    if (i < 2 * H) v = bih[i] + bhh[i];
+    if (i < 2 * H) v = -1.4426950408889634f * (bih[i] + bhh[i]);   // r, z: -(b_i + b_h) log2 e
     else if (i < 3 * H) v = bih[i];            // b_in
     else v = bhh[i - H];                       // b_hn
     bias[i] = v;
   }
   if (tid == 0) {
-    mbar_init(&a_ready[0], kM), mbar_init(&a_ready[1], kM);
+    mbar_init(&a_ready[0], kGateThreads), mbar_init(&a_ready[1], kGateThreads);
     mbar_init(&d_ready[0], 1), mbar_init(&d_ready[1], 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == 8) {
+  if (warp == 16) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(tmem_slot)));
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
   }
@@ -182,7 +207,7 @@ __global__ void __launch_bounds__(tc::kThreads, 1) gru_window_tc_kernel(const Gr
   const int pairs_per_t = (a.B + 2 * kM - 1) / (2 * kM);
   const int n_pairs = (a.t1 - a.t0) * pairs_per_t;
 
-  if (warp == 8) {
+  if (warp == 16) {
     // =================== MMA issuer ===================
     if (lane == 0) {
       uint32_t ph[2] = {0, 0};
@@ -233,30 +258,37 @@ __global__ void __launch_bounds__(tc::kThreads, 1) gru_window_tc_kernel(const Gr
       }
     }
   } else {
-    // =================== gate warps: slot = warp / 4, row = 32 (warp % 4) + lane ===================
-    const int slot = warp >> 2;
+    // =================== gate warps: slot = warp / 8, lane quadrant = warp % 4, unit half = (warp / 4) % 2 ====
+    constexpr int HH = H / 2;          // hidden units per thread
+    constexpr int KH = kKx / 2;        // input features staged per thread
+    const int slot = warp >> 3;
+    const int half = (warp >> 2) & 1;
     const int row = ((warp & 3) << 5) + lane;
     const uint32_t lane_addr = (uint32_t)((warp & 3) << 5) << 16;
     __nv_bfloat16* my_ax = ax + slot * S::kAx;
     __nv_bfloat16* my_ah = ah + slot * 3 * S::kAh;
+    const int u0 = half * HH;
     uint32_t ph = 0;
-    float h[H];
+    float h[HH];
 
-    auto load_x = [&](int t_obs, int b, float* xr) {   // observation of this row at time t_obs -> registers
+    auto load_x = [&](int t_obs, int b, float* xr) {   // this thread's half of the row's observation -> registers
       const bool ok = b < a.B;
       const float* xp = view_ptr(a.x, g, t_obs, a.B, ok ? b : 0);
 #pragma unroll
-      for (int k = 0; k < kKx; ++k) xr[k] = (ok && k < I) ? xp[(long long)k * a.B] : 0.f;
+      for (int k = 0; k < KH; ++k) {
+        const int kk = half * KH + k;
+        xr[k] = (ok && kk < I) ? xp[(long long)kk * a.B] : 0.f;
+      }
     };
-    auto stage_x = [&](const float* xr) {              // registers -> bf16 A tile (canonical layout), 16 B per store
+    auto stage_x = [&](const float* xr) {              // exact in bf16: the top halves of the fp32 words
 #pragma unroll
-      for (int kc = 0; kc < kKx / 8; ++kc) {
+      for (int kc = 0; kc < KH / 8; ++kc) {
         uint4 v;
-        v.x = pack2(__float2bfloat16_rn(xr[kc * 8 + 0]), __float2bfloat16_rn(xr[kc * 8 + 1]));
-        v.y = pack2(__float2bfloat16_rn(xr[kc * 8 + 2]), __float2bfloat16_rn(xr[kc * 8 + 3]));
-        v.z = pack2(__float2bfloat16_rn(xr[kc * 8 + 4]), __float2bfloat16_rn(xr[kc * 8 + 5]));
-        v.w = pack2(__float2bfloat16_rn(xr[kc * 8 + 6]), __float2bfloat16_rn(xr[kc * 8 + 7]));
-        *reinterpret_cast<uint4*>(my_ax + canon16(row, kc * 8, kKx)) = v;
+        v.x = pack_hi(__float_as_uint(xr[kc * 8 + 0]), __float_as_uint(xr[kc * 8 + 1]));
+        v.y = pack_hi(__float_as_uint(xr[kc * 8 + 2]), __float_as_uint(xr[kc * 8 + 3]));
+        v.z = pack_hi(__float_as_uint(xr[kc * 8 + 4]), __float_as_uint(xr[kc * 8 + 5]));
+        v.w = pack_hi(__float_as_uint(xr[kc * 8 + 6]), __float_as_uint(xr[kc * 8 + 7]));
+        *reinterpret_cast<uint4*>(my_ax + canon16(row, half * KH + kc * 8, kKx)) = v;
       }
     };
     auto publish = [&]() {   // operands of the next MMA batch are in place (and our TMEM reads are done)
@@ -269,47 +301,58 @@ __global__ void __launch_bounds__(tc::kThreads, 1) gru_window_tc_kernel(const Gr
       const int t = a.t0 + p / pairs_per_t;
       const int b = (p % pairs_per_t) * (2 * kM) + slot * kM + row;
       const int s0 = a.padded ? 0 : max(0, L - 1 - t);
-      float xr[kKx];
+      float xr[KH];
       load_x(t - (L - 1 - s0), b, xr);
       stage_x(xr);
       publish();
 #pragma unroll
-      for (int u = 0; u < H; ++u) h[u] = 0.f;
+      for (int u = 0; u < HH; ++u) h[u] = 0.f;
       for (int s = s0; s < L; ++s) {
         const bool has_next = s + 1 < L;
         if (has_next) load_x(t - (L - 2 - s), b, xr);   // in flight during the gate maths
         mbar_wait(&d_ready[slot], ph);
         ph ^= 1u;
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        const uint32_t d = tmem + (uint32_t)slot * (4 * H) + lane_addr;
+        const uint32_t d = tmem + (uint32_t)slot * (4 * H) + lane_addr + (uint32_t)u0;
         const bool first = s == s0;
 #pragma unroll
-        for (int c = 0; c < H / 8; ++c) {
+        for (int c = 0; c < HH / 8; ++c) {
           float pr[8], pz[8], pin[8], phn[8];
           tmem_ld8(d + c * 8, pr);
           tmem_ld8(d + H + c * 8, pz);
           tmem_ld8(d + 2 * H + c * 8, pin);
           if (!first) tmem_ld8(d + 3 * H + c * 8, phn);
           asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-          __nv_bfloat16 q0[8], q1[8], q2[8];
+          uint32_t q0[8], q1[8], q2[8];
+          const float4* bz = reinterpret_cast<const float4*>(bias + u0 + c * 8);   // 16-byte aligned: u0 + 8c
+          const float4 br0 = bz[0], br1 = bz[1];
+          const float4 bz0 = bz[H / 4], bz1 = bz[H / 4 + 1];
+          const float4 bi0 = bz[2 * H / 4], bi1 = bz[2 * H / 4 + 1];
+          const float4 bh0 = bz[3 * H / 4], bh1 = bz[3 * H / 4 + 1];
+          const float b_r[8] = {br0.x, br0.y, br0.z, br0.w, br1.x, br1.y, br1.z, br1.w};
+          const float b_z[8] = {bz0.x, bz0.y, bz0.z, bz0.w, bz1.x, bz1.y, bz1.z, bz1.w};
+          const float b_i[8] = {bi0.x, bi0.y, bi0.z, bi0.w, bi1.x, bi1.y, bi1.z, bi1.w};
+          const float b_h[8] = {bh0.x, bh0.y, bh0.z, bh0.w, bh1.x, bh1.y, bh1.z, bh1.w};
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
-            const int u = c * 8 + j;
-            const float r = 1.0f / (1.0f + expf(-(pr[j] + bias[u])));
-            const float z = 1.0f / (1.0f + expf(-(pz[j] + bias[H + u])));
-            const float ghn = (first ? 0.f : phn[j]) + bias[3 * H + u];
-            const float nn = tanhf(pin[j] + bias[2 * H + u] + r * ghn);
-            h[u] = (1.0f - z) * nn + z * h[u];
-            split3(h[u], q0[j], q1[j], q2[j]);
+            const float r = rcp_approx(1.0f + ex2_approx(fmaf(pr[j], -1.4426950408889634f, b_r[j])));
+            const float z = rcp_approx(1.0f + ex2_approx(fmaf(pz[j], -1.4426950408889634f, b_z[j])));
+            const float ghn = (first ? 0.f : phn[j]) + b_h[j];
+            const float pre = fmaf(r, ghn, pin[j] + b_i[j]);
+            // tanh(v) = 1 - 2 / (1 + 2^(2 v log2 e))
+            const float nn = fmaf(-2.0f, rcp_approx(1.0f + ex2_approx(2.8853900817779268f * pre)), 1.0f);
+            const float hv = fmaf(z, h[c * 8 + j] - nn, nn);   // (1 - z) n + z h
+            h[c * 8 + j] = hv;
+            split3_trunc(hv, q0[j], q1[j], q2[j]);
           }
           if (has_next) {
-            const int o = canon16(row, c * 8, H);
+            const int o = canon16(row, u0 + c * 8, H);
             *reinterpret_cast<uint4*>(my_ah + o) =
-                make_uint4(pack2(q0[0], q0[1]), pack2(q0[2], q0[3]), pack2(q0[4], q0[5]), pack2(q0[6], q0[7]));
+                make_uint4(pack_hi(q0[0], q0[1]), pack_hi(q0[2], q0[3]), pack_hi(q0[4], q0[5]), pack_hi(q0[6], q0[7]));
             *reinterpret_cast<uint4*>(my_ah + S::kAh + o) =
-                make_uint4(pack2(q1[0], q1[1]), pack2(q1[2], q1[3]), pack2(q1[4], q1[5]), pack2(q1[6], q1[7]));
+                make_uint4(pack_hi(q1[0], q1[1]), pack_hi(q1[2], q1[3]), pack_hi(q1[4], q1[5]), pack_hi(q1[6], q1[7]));
             *reinterpret_cast<uint4*>(my_ah + 2 * S::kAh + o) =
-                make_uint4(pack2(q2[0], q2[1]), pack2(q2[2], q2[3]), pack2(q2[4], q2[5]), pack2(q2[6], q2[7]));
+                make_uint4(pack_hi(q2[0], q2[1]), pack_hi(q2[2], q2[3]), pack_hi(q2[4], q2[5]), pack_hi(q2[6], q2[7]));
           }
         }
         if (has_next) {
@@ -320,7 +363,7 @@ __global__ void __launch_bounds__(tc::kThreads, 1) gru_window_tc_kernel(const Gr
           if (b < a.B) {
             float* ho = view_ptr(a.h_out, g, t, a.B, b);
 #pragma unroll
-            for (int u = 0; u < H; ++u) ho[(long long)u * a.B] = h[u];
+            for (int u = 0; u < HH; ++u) ho[(long long)(u0 + u) * a.B] = h[u];
           }
         }
       }
@@ -328,7 +371,7 @@ __global__ void __launch_bounds__(tc::kThreads, 1) gru_window_tc_kernel(const Gr
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
-  if (warp == 8) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem));
+  if (warp == 16) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem));
 }
 
 }  // namespace d2d
