@@ -17,6 +17,7 @@
 #include <vector>
 
 #include "gru_tc.cuh"
+#include "wgrad_tc.cuh"
 #include "learner_pointwise.cuh"
 
 using namespace d2d;
@@ -127,6 +128,16 @@ static void fill_dense_w(const d2d_net* n, DenseArgs& a, const float* params, co
   a.out_dim = trans ? (w.in_dim ? 0 : w.in_const) : w.out_dim;
 }
 
+// D2D_DISABLE_TCGEN05=1 keeps every GEMM on the FP32 CUDA-core kernels (A/B comparison, debugging)
+static bool tc_enabled() {
+  static int disabled = -1;
+  if (disabled < 0) {
+    const char* e = getenv("D2D_DISABLE_TCGEN05");
+    disabled = (e && e[0] == '1') ? 1 : 0;
+  }
+  return !disabled;
+}
+
 template <int TO, int TK>
 static void launch_wgrad_t(const WgradArgs& a, dim3 grid, cudaStream_t s) {
   const size_t smem = (size_t)(16 * TO + 16 * TK) * (kWgRows + 1) * sizeof(float);
@@ -145,21 +156,34 @@ static int launch_wgrad(d2d_net* n, const View& dy, const View& x, const Wt& w, 
     a.in_dim[g] = zero_in ? 0 : (w.in_dim ? (*w.in_dim)[g] : w.in_const);
     maxK = std::max(maxK, a.in_dim[g]);
   }
-  dim3 grid(n->n_strips, n->N);
+  int strips = n->n_strips;
   const int O = w.out_dim;
   if (O > 192 || maxK > 128) {
     set_error("learner: weight-gradient tile %d x %d exceeds the supported 192 x 128", O, maxK);
     return D2D_ERR_INVALID;
   }
-  const int to = O > 64 ? 12 : (O > 16 ? 4 : 1);
-  const int tk = maxK > 64 ? 8 : (maxK > 32 ? 4 : 2);
+  if (tc_enabled() && n->B % 8 == 0) {
+    // tensor-core path (wgrad_tc.cuh): bf16 x 3 planes on tcgen05, accumulators in TMEM
+    strips = std::max(1, std::min(n->n_strips, 296 / n->N));   // two CTAs per SM
+    const size_t smem = tcw::smem_bytes(maxK);
+    static bool attr = false;
+    if (!attr) {
+      D2D_CUDA(cudaFuncSetAttribute(wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+      attr = true;
+    }
+    wgrad_tc_kernel<<<dim3(strips, n->N), tcw::kThreads, smem, s>>>(a);
+  } else {
+    dim3 grid(strips, n->N);
+    const int to = O > 64 ? 12 : (O > 16 ? 4 : 1);
+    const int tk = maxK > 64 ? 8 : (maxK > 32 ? 4 : 2);
 #define WG(TO_, TK_) if (to == TO_ && tk == TK_) launch_wgrad_t<TO_, TK_>(a, grid, s)
-  WG(12, 2); WG(12, 4); WG(12, 8); WG(4, 2); WG(4, 4); WG(4, 8); WG(1, 2); WG(1, 4); WG(1, 8);
+    WG(12, 2); WG(12, 4); WG(12, 8); WG(4, 2); WG(4, 4); WG(4, 8); WG(1, 2); WG(1, 4); WG(1, 8);
 #undef WG
+  }
   D2D_LAUNCHED();
   WreduceArgs r;
   memset(&r, 0, sizeof(r));
-  r.partial = n->partial, r.part_stride = n->part_stride, r.n_strips = n->n_strips, r.grads = grads;
+  r.partial = n->partial, r.part_stride = n->part_stride, r.n_strips = strips, r.grads = grads;
   r.g_agent_stride = n->stride, r.out_dim = O, r.with_bias = a.with_bias;
   for (int g = 0; g < n->N; ++g) {
     r.w_off[g] = (*w.w_off)[g];
@@ -195,12 +219,7 @@ static int launch_gru_step(const d2d_net* n, GruStepArgs& a, const float* params
 
 // tensor-core fused GRU window (gru_tc.cuh): x windows -> last hidden state, no intermediate in HBM
 static bool gru_tc_eligible(const d2d_net* n) {
-  static int disabled = -1;
-  if (disabled < 0) {
-    const char* e = getenv("D2D_DISABLE_TCGEN05");
-    disabled = (e && e[0] == '1') ? 1 : 0;
-  }
-  return !disabled && n->arch == D2D_NET_GRU && n->x_exact && n->max_in <= tc::kKx &&
+  return tc_enabled() && n->arch == D2D_NET_GRU && n->x_exact && n->max_in <= tc::kKx &&
          (n->H == 16 || n->H == 32 || n->H == 48 || n->H == 64);
 }
 

@@ -114,7 +114,8 @@ __global__ void __launch_bounds__(kRowsPerBlock) dense_kernel(const DenseArgs a)
 
 // ------------------------------------------------------------------------------------------------
 // dense, register-tiled: the same contract as dense_kernel for B % 4 == 0.
-// Block = 8 warps; every warp works on the SAME 32 * RPT rows (lane l owns rows 4-aligned [l*RPT, l*RPT + RPT)) and
+// Block = 8 warps; every warp works on the SAME 32 * RPT rows (lane l owns the row quads [128 q + 4 l, +4), q < RPT/4:
+// a 16-byte lane stride keeps the LDS.128 of the row tile conflict-free) and
 // warp w owns outputs [w * OPT, w * OPT + OPT).  Per input k a thread issues RPT/4 LDS.128 for its rows and OPT/4
 // broadcast LDS.128 for its weights against RPT * OPT FMAs (1 : 14 at <4, 24>, vs 1 : 4 for one row per thread).
 // Input rows are streamed global -> shared with cp.async in chunks of 32 inputs, double buffered across
@@ -192,7 +193,7 @@ __global__ void __launch_bounds__(256) dense_tile_kernel(const DenseArgs a) {
         for (int r = 0; r < RPT; ++r) acc[r][j] = bv;
       }
     }
-    const float* xs = Xs + (size_t)(c & 1) * KC * ROWS + lane * RPT;
+    const float* xs = Xs + (size_t)(c & 1) * KC * ROWS + lane * 4;   // quad q of this lane: rows 128 q + 4 lane
     const int kmax = min(KC, in_dim - kc * KC);
     const float* mrow = Ms + (size_t)kc * KC * OUT_PAD + og * OPT;
 #pragma unroll 2
@@ -200,7 +201,7 @@ __global__ void __launch_bounds__(256) dense_tile_kernel(const DenseArgs a) {
       float xv[RPT];
 #pragma unroll
       for (int q = 0; q < RPT / 4; ++q) {
-        const float4 v = *reinterpret_cast<const float4*>(xs + kk * ROWS + 4 * q);
+        const float4 v = *reinterpret_cast<const float4*>(xs + kk * ROWS + 128 * q);
         xv[4 * q] = v.x, xv[4 * q + 1] = v.y, xv[4 * q + 2] = v.z, xv[4 * q + 3] = v.w;
       }
 #pragma unroll
@@ -217,7 +218,7 @@ __global__ void __launch_bounds__(256) dense_tile_kernel(const DenseArgs a) {
     }
     if (kc == nkc - 1) {
       const int tile = blockIdx.x + (c / nkc) * gridDim.x;
-      const int t = a.t0 + tile / tiles_per_t, b = (tile % tiles_per_t) * ROWS + lane * RPT;
+      const int t = a.t0 + tile / tiles_per_t, b = (tile % tiles_per_t) * ROWS + lane * 4;
       if (b < a.B) {
         float* yp = view_ptr(a.y, g, t, a.B, b);
         const float* ap = a.epilogue == kEpiReluBwd ? view_ptr(a.aux, g, t, a.B, b) : nullptr;
@@ -227,16 +228,16 @@ __global__ void __launch_bounds__(256) dense_tile_kernel(const DenseArgs a) {
           if (o < out_dim) {
 #pragma unroll
             for (int q = 0; q < RPT / 4; ++q) {
-              if (b + 4 * q >= a.B) continue;   // RPT = 8: the second quad of rows may lie past the last env
+              if (b + 128 * q >= a.B) continue;   // RPT = 8: the second quad of rows may lie past the last env
               float4 v = make_float4(acc[4 * q][j], acc[4 * q + 1][j], acc[4 * q + 2][j], acc[4 * q + 3][j]);
-              float4* dst = reinterpret_cast<float4*>(yp + (long long)o * a.B + 4 * q);
+              float4* dst = reinterpret_cast<float4*>(yp + (long long)o * a.B + 128 * q);
               if (a.epilogue == kEpiRelu) {
                 v.x = fmaxf(v.x, 0.f), v.y = fmaxf(v.y, 0.f), v.z = fmaxf(v.z, 0.f), v.w = fmaxf(v.w, 0.f);
               } else if (a.epilogue == kEpiAccum) {
                 const float4 o4 = *dst;
                 v.x += o4.x, v.y += o4.y, v.z += o4.z, v.w += o4.w;
               } else if (a.epilogue == kEpiReluBwd) {
-                const float4 m4 = *reinterpret_cast<const float4*>(ap + (long long)o * a.B + 4 * q);
+                const float4 m4 = *reinterpret_cast<const float4*>(ap + (long long)o * a.B + 128 * q);
                 v.x = m4.x > 0.f ? v.x : 0.f, v.y = m4.y > 0.f ? v.y : 0.f;
                 v.z = m4.z > 0.f ? v.z : 0.f, v.w = m4.w > 0.f ? v.w : 0.f;
               }
