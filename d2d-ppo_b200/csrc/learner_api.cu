@@ -18,6 +18,7 @@
 
 #include "gru_tc.cuh"
 #include "wgrad_tc.cuh"
+#include "dense_tc.cuh"
 #include "learner_pointwise.cuh"
 
 using namespace d2d;
@@ -51,6 +52,16 @@ static View make_view(float* p, long long t_stride, int t_off, int N, int feat_p
   return v;
 }
 
+// D2D_DISABLE_TCGEN05=1 keeps every GEMM on the FP32 CUDA-core kernels (A/B comparison, debugging)
+static bool tc_enabled() {
+  static int disabled = -1;
+  if (disabled < 0) {
+    const char* e = getenv("D2D_DISABLE_TCGEN05");
+    disabled = (e && e[0] == '1') ? 1 : 0;
+  }
+  return !disabled;
+}
+
 template <int RPT, int OPT>
 static int launch_dense_tile(const d2d_net* n, const DenseArgs& a, int max_in, cudaStream_t s) {
   constexpr int ROWS = 32 * RPT;
@@ -73,8 +84,24 @@ static int launch_dense_tile(const d2d_net* n, const DenseArgs& a, int max_in, c
   return D2D_OK;
 }
 
-static int launch_dense(const d2d_net* n, DenseArgs& a, int max_in, cudaStream_t s) {
+static int launch_dense(const d2d_net* n, DenseArgs& a, int max_in, cudaStream_t s, int x_exact = 0) {
   a.B = n->B;
+  // tensor-core path (dense_tc.cuh) for single-chunk reductions (K <= 64); with K = 3H the three stage -> MMA round
+  // trips per tile serialise inside a slot and the register-tiled FP32 kernel is faster (measured 212 vs 480 us)
+  if (tc_enabled() && n->B >= 256 && a.out_dim <= 192 && max_in <= tcd::kKc &&
+      tcd::smem_bytes(max_in, a.out_dim) <= 225 * 1024) {
+    static bool attr = false;
+    if (!attr) {
+      D2D_CUDA(cudaFuncSetAttribute(dense_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 225 * 1024));
+      attr = true;
+    }
+    const int pairs = (a.t1 - a.t0) * ((n->B + 255) / 256);
+    if (pairs <= 0) return D2D_OK;
+    const int gx = std::max(1, std::min(pairs, 148 / n->N));
+    dense_tc_kernel<<<dim3(gx, n->N), tcd::kThreads, tcd::smem_bytes(max_in, a.out_dim), s>>>(a, x_exact);
+    D2D_LAUNCHED();
+    return D2D_OK;
+  }
   if (n->B % 4 == 0 && a.out_dim <= 192) {   // register-tiled path (rows are moved as float4)
     if (a.out_dim > 64) return launch_dense_tile<4, 24>(n, a, max_in, s);
     if (a.out_dim > 32) return launch_dense_tile<8, 8>(n, a, max_in, s);
@@ -126,16 +153,6 @@ static void fill_dense_w(const d2d_net* n, DenseArgs& a, const float* params, co
     a.in_dim[g] = trans ? w.out_dim : K;
   }
   a.out_dim = trans ? (w.in_dim ? 0 : w.in_const) : w.out_dim;
-}
-
-// D2D_DISABLE_TCGEN05=1 keeps every GEMM on the FP32 CUDA-core kernels (A/B comparison, debugging)
-static bool tc_enabled() {
-  static int disabled = -1;
-  if (disabled < 0) {
-    const char* e = getenv("D2D_DISABLE_TCGEN05");
-    disabled = (e && e[0] == '1') ? 1 : 0;
-  }
-  return !disabled;
 }
 
 template <int TO, int TK>
@@ -368,7 +385,7 @@ static int forward_chunk(d2d_net* n, const float* params, const float* x, int x_
       Wt wih{&n->o_wih, &n->o_bih, &n->in_dim, 0, 3 * H};
       fill_dense_w(n, a, params, wih, 0);
       a.x = xin, a.y = gi, a.epilogue = kEpiNone, a.t0 = c0 - halo, a.t1 = c1;
-      if ((rc = launch_dense(n, a, n->max_in, s))) return rc;
+      if ((rc = launch_dense(n, a, n->max_in, s, n->x_exact))) return rc;
     }
     const View gh = make_view(c.gh, 3 * H * NB, -c0, N, 3 * H, B);
     for (int st = 0; st < L && !use_tc; ++st) {
