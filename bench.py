@@ -47,6 +47,7 @@ def parse():
     ap.add_argument("--envs", type=int, default=1 << 20, help="lockstep envs per GPU")
     ap.add_argument("--cpu-envs", type=int, default=4096, help="envs per process of the CPU arm")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-learner-envs", type=int, default=64, help="envs of the CPU iPPO iteration baseline")
     ap.add_argument("--no-learner", action="store_true", help="skip the learned-policy rollout / train SPS sections")
     ap.add_argument("--rollout-envs", type=int, default=65536, help="envs per GPU of the learned-policy rollout (c3)")
     ap.add_argument("--train-envs", type=int, default=4096, help="envs per GPU of the train-SPS sections")
@@ -181,6 +182,22 @@ def workload_config(envs_total, cpu=False):
 # learner sections (extra keys of the JSON line): env + learned-policy rollout, PPO train SPS
 # ------------------------------------------------------------------------------------------------
 FFMA_PEAK_TFLOPS = 148 * 128 * 2 * 1.965e9 / 1e12     # 148 SMs x 128 FP32 FMA lanes x 2 flop x 1.965 GHz = 74.4
+FALLBACK_BF16 = 1500.0
+
+
+def measured_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        j = json.load(open(path))
+        return float(j["hbm_gbs"]), float(j["bf16_tflops"]), "of measured (MEASURED_PEAKS.json)"
+    return FALLBACK_HBM, FALLBACK_BF16, "of fallback (B200_PROFILING.md)"
+
+
+def gru_tc_issued_flops(I_pad, H, L):
+    """bf16 tensor-pipe flops the fused GRU-window kernel ISSUES per row (csrc/gru_tc.cuh): every fp32 operand is
+    three bf16 planes; x (exact in one plane) x W_ih (3 planes) = 3 MMAs of K = I_pad, h (3) x W_hh (3) keeps the 6
+    plane pairs with i + j <= 2, K = H; both produce 3H columns per step."""
+    return 2 * L * 3 * H * (3 * I_pad + 6 * H)
 
 
 def gru_flops_per_agent_step(I, H, L, O):
@@ -190,6 +207,7 @@ def gru_flops_per_agent_step(I, H, L, O):
 
 
 def bench_learner(args, dev, world, rank, barrier, max_over_ranks):
+    import numpy as np
     import torch
 
     from d2d_ppo_b200 import _lib, presets
@@ -220,15 +238,63 @@ def bench_learner(args, dev, world, rank, barrier, max_over_ranks):
     dt, launches = timed(lambda: agent.create_rollouts(B))
     flops = 2 * gru_flops_per_agent_step(30, 64, 6, 8) - (2 * 64 * 8 - 2 * 64)   # actor (O=8) + critic (O=1)
     steps = world * B * N_AGENTS * T
+    hbm_peak, bf16_peak, peak_src = measured_peaks()
+    issued = 2 * gru_tc_issued_flops(32, 64, 6)              # actor + critic windows on the tensor pipe
     out["rollout_learned"] = {
         "metric": "agent-steps/sec (env step + GRU actor + GRU critic, sampled actions, log-probs, values, "
                   "lambda-returns)", "value": steps / dt, "unit": "agent-steps/s", "envs_per_gpu": B,
         "config": "c3: iPPO useRNN=True hidden 64 history_len 6 on CombinatorialEnv setup_8_channels.p",
         "seconds_per_episode": dt, "gpu_launches": int(launches),
-        "roofline": {"bound": "fp32 FMA (CUDA cores; fp32 parity path, no tensor cores yet)",
-                     "achieved": steps * flops / dt / 1e12, "peak": FFMA_PEAK_TFLOPS, "unit": "TFLOP/s",
-                     "frac": steps * flops / dt / 1e12 / FFMA_PEAK_TFLOPS,
-                     "flops_per_agent_step": flops, "peak_source": "148 SM x 128 lanes x 2 x 1.965 GHz (nominal)"}}
+        "roofline": {"bound": "tensor",
+                     "note": "GRU windows on tcgen05 with fp32 operands split into 3 bf16 planes (fp32 parity at 1e-5): "
+                             "`achieved` counts the bf16 MMA flops the kernels issue (6 plane pairs for h W_hh, 3 for "
+                             "x W_ih, K padded 30 -> 32) over the WHOLE rollout time (env step, heads, sampling and "
+                             "returns included); fp32_equivalent_tflops counts the algorithmic flops once",
+                     "achieved": steps / world * issued / dt / 1e12, "peak": bf16_peak, "unit": "TFLOP/s",
+                     "frac": steps / world * issued / dt / 1e12 / bf16_peak, "traffic": None,
+                     "issued_bf16_flops_per_agent_step": issued, "flops_per_agent_step": flops,
+                     "fp32_equivalent_tflops": steps / world * flops / dt / 1e12,
+                     "fp32_ffma_peak_tflops": FFMA_PEAK_TFLOPS, "peak_source": peak_src + " bf16_tflops (burst)"}}
+
+    # GAE / returns scans of that rollout: lambda-returns + discounted returns for T x N x B elements, two passes
+    # (statistics; normalised fp32 emit), HBM-bound.  Algorithmic bytes per element: SURVEY.md section 8d
+    from d2d_ppo_b200.algorithms._nets import returns_emit, returns_stats
+
+    def gae_once():
+        st = returns_stats(agent.reward_buf, agent.value_buf, 0.4, 0.97, 1)
+        na = agent._norm_stats(st, (0, 1), ddof=0)
+        nr = agent._norm_stats(st, (2, 3), ddof=1)
+        returns_emit(agent.reward_buf, agent.value_buf, 0.4, 0.97, 1, na, nr, agent.adv_buf, agent.ret_buf)
+    for _ in range(3):
+        gae_once()
+    reps = 20
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)      # > 126 MB L2, rewritten between repetitions
+    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(reps)]
+    for a, b in evs:
+        flush.fill_(1)
+        a.record()
+        gae_once()
+        b.record()
+    torch.cuda.synchronize()
+    gae_ms = float(np.median([a.elapsed_time(b) for a, b in evs]))
+    elems = T * N_AGENTS * B
+    alg = 28 + 5 / N_AGENTS
+    moved = 2 * (4 + 4 / N_AGENTS) + 8                                  # what the two passes actually read + write
+    out["gae_returns"] = {
+        "metric": "elements/s of compute_gae + discount_rewards + both normalisations (d2d_ppo.py:100-124)",
+        "value": elems / (gae_ms * 1e-3), "unit": "(t, agent, env) elements/s", "elements": elems, "ms": gae_ms,
+        "l2": "256 MB flush buffer rewritten before every repetition; working set 0.9 GB",
+        "roofline": {"bound": "hbm", "achieved": elems * alg / (gae_ms * 1e-3) / 1e9, "peak": hbm_peak,
+                     "unit": "GB/s", "frac": elems * alg / (gae_ms * 1e-3) / 1e9 / hbm_peak, "traffic": None,
+                     "alg_bytes_per_element": alg, "moved_bytes_per_element": moved,
+                     "moved_gbs": elems * moved / (gae_ms * 1e-3) / 1e9,
+                     "note": "algorithmic bytes per SURVEY.md 8d (28 + 5/N: separate scan and normalise passes); the "
+                             "kernels recompute the scan in the emit pass instead and move 17.3 B per element, so "
+                             "`achieved` may exceed what the DRAM moved; includes the host-side statistics step "
+                             "between the two launches", "kernel": "returns_scan_kernel<1>, <2>",
+                     "peak_source": peak_src + " hbm_gbs"}}
+    del flush
+
     del agent, env
     torch.cuda.empty_cache()
 
@@ -347,29 +413,42 @@ def run_native(args):
     value = world * B * N_AGENTS * K / (total_ms * 1e-3)
 
     # ---- end to end through the public API with HOST buffers ------------------------------------
+    # env.step_host() = d2d_env_step_host of the C ABI: every step copies that step's actions from pinned host
+    # memory (H2D), packs + steps on the device, and copies the step's rewards back into pinned host memory (D2H);
+    # the host reads the rewards of step i - 1 after issuing step i (two calls in flight, copies overlap kernels).
     n_host = 4
-    host_actions = [torch.from_numpy(np.random.default_rng(i).binomial(1, TP, (B, N_AGENTS, N_CHANNELS))
-                                     .astype(np.uint8)).pin_memory() for i in range(n_host)]
-    host_reward = torch.empty(B, dtype=torch.int32).pin_memory()
-    Ke = max(10, min(K, 100))
+    rng_host = [np.random.default_rng(i) for i in range(n_host)]
+    host_actions = [torch.from_numpy(g.binomial(1, TP, (B, N_AGENTS, N_CHANNELS)).astype(np.uint8)).pin_memory()
+                    for g in rng_host]
+    w8 = (1 << np.arange(N_CHANNELS)).astype(np.uint8)
+    host_masks = [torch.from_numpy(np.ascontiguousarray(((a.numpy() * w8).sum(-1).astype(np.uint8)).T)).pin_memory()
+                  for a in host_actions]                                       # device layout: bitmask [N, B]
+    host_reward = [torch.empty(B, dtype=torch.int32).pin_memory() for _ in range(2)]
+    Ke = max(10, min(K, 200))
 
-    def e2e_step(i):
-        if env.timestep >= T:
-            env.reset(with_state=False)
-        _, _, rew, done, _ = env.step(host_actions[i % n_host], with_state=False, out_obs=obs_buf)   # H2D inside
-        host_reward.copy_(rew[:, 0], non_blocking=True)                                            # D2H result
-        torch.cuda.current_stream().synchronize()
-        return int(host_reward[0])
+    def e2e_run(acts, layout, n):
+        checksum, pending = 0, None
+        for i in range(n):
+            if env.timestep >= T:
+                env.reset(with_state=False)
+            tk = env.step_host(acts[i % n_host], host_reward[i % 2], layout=layout, with_state=False, out_obs=obs_buf)
+            if pending is not None:
+                env.host_wait(pending[0])
+                checksum += int(pending[1][0]) + int(pending[1][-1])          # the host consumes the result
+            pending = (tk, host_reward[i % 2])
+        env.host_wait(pending[0])
+        return checksum + int(pending[1][0])
 
-    for i in range(3):
-        e2e_step(i)
-    barrier()
-    t0 = time.perf_counter()
-    for i in range(Ke):
-        e2e_step(i)
-    barrier()
-    e2e_s = max_over_ranks(time.perf_counter() - t0)
-    e2e_value = world * B * N_AGENTS * Ke / e2e_s
+    def e2e_time(acts, layout):
+        e2e_run(acts, layout, 4)
+        barrier()
+        t0 = time.perf_counter()
+        e2e_run(acts, layout, Ke)
+        barrier()
+        return world * B * N_AGENTS * Ke / max_over_ranks(time.perf_counter() - t0)
+
+    e2e_value = e2e_time(host_actions, "reference")
+    e2e_masks = e2e_time(host_masks, "device")
 
     # ---- roofline of the dominant kernel ---------------------------------------------------------
     peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
@@ -394,10 +473,16 @@ def run_native(args):
                      "peak_source": peak_src},
         "e2e": {"value": e2e_value, "unit": "agent-steps/s",
                 "h2d_bytes_per_step": B * N_AGENTS * N_CHANNELS, "d2h_bytes_per_step": B * 4, "steps": Ke,
-                "api": "CombinatorialEnv.step(actions u8 [B,N,C] in pinned host memory) -> rewards read on host"},
+                "api": "CombinatorialEnv.step_host (C ABI d2d_env_step_host): actions u8 [B,N,C] 0/1, the reference's "
+                       "(N,C) array per env, in pinned host memory -> i32 [B] rewards in pinned host memory, read by "
+                       "the host every step; two calls in flight",
+                "bound": "PCIe: 48 B of actions per env-step",
+                "packed_actions": {"value": e2e_masks, "unit": "agent-steps/s", "h2d_bytes_per_step": B * N_AGENTS,
+                                   "d2h_bytes_per_step": B * 4,
+                                   "api": "same call with the device action layout (u8 channel bitmask [N,B])"}},
         "gpu_launches": int(launches), "resets_in_timed_region": n_resets, "clocks": clocks,
     }
-    del obs_buf, env, host_actions
+    del obs_buf, env, host_actions, host_masks
     torch.cuda.empty_cache()
     if not args.no_learner:
         line.update(bench_learner(args, dev, world, rank, barrier, max_over_ranks))
@@ -411,6 +496,19 @@ def run_native(args):
                       f"vectorised over envs) + numpy random-access policy, {dt:.1f} s",
             "single_env_value": v1,
             "single_env_sample": f"1 env x 3000 steps (the reference's own shape: one instance per process), {dt1:.1f} s"}
+        if not args.no_learner:
+            from oracle.ippo_cpu import ippo_iteration_cpu
+            threads = torch.get_num_threads()
+            r = ippo_iteration_cpu(args.cpu_learner_envs, presets.combinatorial_kwargs("setup_8_channels", load=LOAD),
+                                   n_epoch=5)
+            line["cpu_baseline_learner"] = {
+                "rollout_value": r["agent_steps"] / r["rollout_s"],
+                "train_value": r["agent_steps"] / (r["rollout_s"] + r["update_s"]), "unit": "agent-steps/s",
+                "cores": threads, "kind": "port",
+                "sample": f"one iPPO iteration (c3: GRU actor + critic per agent, H 64, L 6) of "
+                          f"oracle/ippo_cpu.ippo_iteration_cpu on {args.cpu_learner_envs} lockstep envs x 200 steps, "
+                          f"5 epochs, torch CPU with {threads} threads: rollout {r['rollout_s']:.1f} s, "
+                          f"updates {r['update_s']:.1f} s"}
     if rank == 0:
         print(json.dumps(line), flush=True)
     if world > 1:

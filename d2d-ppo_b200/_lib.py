@@ -48,6 +48,7 @@ NET_MLP, NET_GRU = 0, 1
 OUT_SOFTMAX, OUT_SIGMOID, OUT_IDENTITY = 0, 1, 2
 DIST_BERNOULLI, DIST_CATEGORICAL = 0, 1
 ACT_SAMPLE, ACT_GREEDY, ACT_GIVEN = 0, 1, 2
+ACT_HOST_REFERENCE, ACT_HOST_DEVICE_LAYOUT = 0, 1
 
 _lib = None
 
@@ -70,6 +71,8 @@ _SIGNATURES = {
     "d2d_env_reset": (C.c_int, [_P, _P, _P, _P]),
     "d2d_env_step": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, _P]),
     "d2d_env_step_random_access": (C.c_int, [_P, C.c_double, _P, _P, _P, _P, _P, _P, _P]),
+    "d2d_env_step_host": (C.c_int, [_P, _P, C.c_int, _P, _P, _P, _P, _P, _P, C.POINTER(C.c_uint64)]),
+    "d2d_env_host_wait": (C.c_int, [_P, C.c_uint64]),
     "d2d_pack_actions": (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_int, _P]),
     "d2d_env_export_state": (C.c_int, [_P, _P, _P, _P, _P, _P, _P]),
     "d2d_env_import_state": (C.c_int, [_P, _P, _P, _P, _P, _P, C.c_int, _P]),
@@ -91,6 +94,10 @@ _SIGNATURES = {
     "d2d_adam_step": (C.c_int, [_P, _P, _P, _P, C.c_int, C.c_int64, C.c_float, C.c_int, C.c_float, _P, _P]),
     "d2d_returns_scan": (C.c_int, [_P, _P, _P, _P, _P, C.c_int, C.c_int, C.c_int, C.c_double, C.c_double, C.c_int,
                                    _P]),
+    "d2d_returns_stats": (C.c_int, [_P, _P, _P, C.c_int, C.c_int, C.c_int, C.c_double, C.c_double, C.c_int, C.c_int,
+                                    C.c_int, _P]),
+    "d2d_returns_emit": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, C.c_int, C.c_int, C.c_int, C.c_double,
+                                   C.c_double, C.c_int, _P]),
     "d2d_normalize": (C.c_int, [_P, _P, _P, _P, _P, C.c_int, C.c_int, C.c_int, C.c_int, _P]),
 }
 

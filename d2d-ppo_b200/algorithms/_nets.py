@@ -203,6 +203,38 @@ def returns_scan(reward, value, gamma, lam, last_shard, want_adv=True, want_ret=
     return adv, ret, stats
 
 
+def returns_stats(reward, value, gamma, lam, last_shard, want_adv=True, want_ret=True):
+    """Pass 1 of the two-pass scans: normalisation statistics only -> stats f64 [n_cols, 4]."""
+    T, B = reward.shape
+    n_cols = value.shape[1] if value is not None else 1
+    stats = torch.zeros((n_cols, 4), dtype=torch.float64, device=reward.device)
+    with torch.cuda.device(reward.device):
+        L.check(L.lib().d2d_returns_stats(L.ptr(reward), L.ptr(value), L.ptr(stats), T, B, n_cols, float(gamma),
+                                          float(lam), int(last_shard), int(want_adv), int(want_ret),
+                                          L.current_stream()))
+    return stats
+
+
+def returns_emit(reward, value, gamma, lam, last_shard, adv_norm=None, ret_norm=None, adv_out=None, ret_out=None):
+    """Pass 2: repeat the scans and write the normalised fp32 lambda-returns / returns [T, n_cols, B].
+    adv_norm / ret_norm: (mean, std, flags) of ``PPOBase._norm_stats`` or None to skip that scan."""
+    T, B = reward.shape
+    n_cols = value.shape[1] if value is not None else 1
+    dev = reward.device
+    if adv_norm is not None and adv_out is None:
+        adv_out = torch.empty((T, n_cols, B), dtype=torch.float32, device=dev)
+    if ret_norm is not None and ret_out is None:
+        ret_out = torch.empty((T, n_cols, B), dtype=torch.float32, device=dev)
+    a = adv_norm if adv_norm is not None else (None, None, None)
+    r = ret_norm if ret_norm is not None else (None, None, None)
+    with torch.cuda.device(dev):
+        L.check(L.lib().d2d_returns_emit(L.ptr(reward), L.ptr(value), L.ptr(adv_out if adv_norm is not None else None),
+                                         L.ptr(ret_out if ret_norm is not None else None), L.ptr(a[0]), L.ptr(a[1]),
+                                         L.ptr(a[2]), L.ptr(r[0]), L.ptr(r[1]), L.ptr(r[2]), T, B, n_cols,
+                                         float(gamma), float(lam), int(last_shard), L.current_stream()))
+    return adv_out, ret_out
+
+
 def normalize(raw, mean, std, do_norm, fp32_math):
     T, n_cols, B = raw.shape
     out = torch.empty((T, n_cols, B), dtype=torch.float32, device=raw.device)

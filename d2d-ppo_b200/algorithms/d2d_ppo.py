@@ -12,7 +12,7 @@ import torch
 from .. import _lib as L
 from . import _dist
 from ._base import PPOBase
-from ._nets import NetSet, normalize, returns_scan
+from ._nets import NetSet, returns_emit, returns_stats
 
 
 class D2DPPO(PPOBase):
@@ -34,12 +34,12 @@ class D2DPPO(PPOBase):
         returns [T, B], scores [B], dones [T]) -- device tensors, env-minor."""
         self._check_episodes(num_episodes)
         scores = self._run_episode(L.ACT_SAMPLE, forced_actions, state_buf=self.state_buf)
-        _, ret_raw, stats = returns_scan(self.reward_buf, None, self.gamma, 0.97, _dist.is_last_shard(),
-                                         want_adv=False)
+        last = _dist.is_last_shard()
+        stats = returns_stats(self.reward_buf, None, self.gamma, 0.97, last, want_adv=False)
         _dist.all_reduce_sum_(stats)
-        mean_r, std_r, flag_r = self._norm_stats(stats, (2, 3), ddof=1)
         # discount_rewards on N identical columns, then .mean(1) (d2d_ppo.py:333,339): one column suffices
-        self.ret_buf = normalize(ret_raw, mean_r, std_r, flag_r, fp32_math=1)[:, 0, :].contiguous()
+        self.ret_buf = returns_emit(self.reward_buf, None, self.gamma, 0.97, last, None,
+                                    self._norm_stats(stats, (2, 3), ddof=1))[1][:, 0, :]
         dones = [t == self.T - 1 for t in range(self.T)]
         return (self.obs_buf[self.lead:], self.state_buf[:self.T], self.act_buf, self.logp_buf, self.reward_buf,
                 self.ret_buf, scores, dones)
@@ -56,11 +56,11 @@ class D2DPPO(PPOBase):
         cyc = _dist.broadcast_order(cycle, dev)
         # global advantage estimate at the BS with the critic BEFORE this epoch's updates (:425-427)
         values = self.critic.forward(self.state_buf, 0, 0, T, padded=1)[:, :, 0, :].contiguous()   # [T, 1, B]
-        adv_raw, _, stats = returns_scan(self.reward_buf, values, self.gamma, 0.97, _dist.is_last_shard(),
-                                         want_ret=False)
+        last = _dist.is_last_shard()
+        stats = returns_stats(self.reward_buf, values, self.gamma, 0.97, last, want_ret=False)
         _dist.all_reduce_sum_(stats)
-        mean_a, std_a, flag_a = self._norm_stats(stats, (0, 1), ddof=0)
-        M0 = normalize(adv_raw, mean_a, std_a, flag_a, fp32_math=0)[:, 0, :].contiguous()           # [T, B]
+        M0 = returns_emit(self.reward_buf, values, self.gamma, 0.97, last,
+                          self._norm_stats(stats, (0, 1), ddof=0), None)[0][:, 0, :]                 # [T, B]
         sums = torch.zeros((N, 2), dtype=torch.float64, device=dev)
         self.policies.zero_grad()
         self.policies.policy_grad(self.obs_buf, self.lead, 0, T, self.dist_kind, self.act_buf, self.logp_buf, M0, 0,

@@ -11,7 +11,7 @@ import torch
 from .. import _lib as L
 from . import _dist
 from ._base import PPOBase
-from ._nets import NetSet, normalize, returns_scan
+from ._nets import NetSet, returns_emit, returns_stats
 
 
 class iPPO(PPOBase):
@@ -35,13 +35,14 @@ class iPPO(PPOBase):
             out = self.values.rollout_step(self.obs_buf, self.lead, t)
             self.value_buf[t].copy_(out[0, :, 0, :])
         scores = self._run_episode(L.ACT_SAMPLE, forced_actions, per_step=critic)
-        adv_raw, ret_raw, stats = returns_scan(self.reward_buf, self.value_buf, self.gamma, 0.97,
-                                               _dist.is_last_shard())
+        last = _dist.is_last_shard()
+        stats = returns_stats(self.reward_buf, self.value_buf, self.gamma, 0.97, last)
         _dist.all_reduce_sum_(stats)
-        mean_a, std_a, flag_a = self._norm_stats(stats, (0, 1), ddof=0)     # numpy std (ippo.py:100-101)
-        mean_r, std_r, flag_r = self._norm_stats(stats, (2, 3), ddof=1)     # torch std  (ippo.py:114-115)
-        self.adv_buf = normalize(adv_raw, mean_a, std_a, flag_a, fp32_math=0)
-        self.ret_buf = normalize(ret_raw, mean_r, std_r, flag_r, fp32_math=1)
+        norm_a = self._norm_stats(stats, (0, 1), ddof=0)     # numpy std (ippo.py:100-101)
+        norm_r = self._norm_stats(stats, (2, 3), ddof=1)     # torch std  (ippo.py:114-115)
+        self.adv_buf, self.ret_buf = returns_emit(self.reward_buf, self.value_buf, self.gamma, 0.97, last,
+                                                  norm_a, norm_r, getattr(self, "adv_buf", None),
+                                                  getattr(self, "ret_buf", None))
         dones = [t == self.T - 1 for t in range(self.T)]
         return (self.obs_buf[self.lead:], self.act_buf, self.logp_buf, self.ret_buf, self.value_buf, self.adv_buf,
                 scores, dones)

@@ -413,11 +413,41 @@ struct d2d_env {
   const uint8_t* rp_arr = nullptr;
   const void* rp_sw = nullptr;
   int rp_len = 0;
+  struct HostPipe* pipe = nullptr;   // lazily created by d2d_env_step_host
   size_t chan_elems() const { return kind == D2D_ENV_CHANNEL_SELECTION ? (size_t)B : (size_t)N * B; }
 };
 
+// Staging of the host-buffer step (d2d_env_step_host): two calls in flight, copies on their own streams so the
+// H2D of call k + 1 and the D2H of call k - 1 overlap the kernels of call k.
+struct HostPipe {
+  static constexpr int kSlots = 2;
+  cudaStream_t h2d = nullptr, d2h = nullptr;
+  uint8_t* stage[kSlots] = {nullptr, nullptr};    // device copy of the host actions, as the host laid them out
+  void* masks[kSlots] = {nullptr, nullptr};       // device-layout actions [N][B] (packed from `stage` if needed)
+  int32_t* reward[kSlots] = {nullptr, nullptr};
+  uint8_t* done[kSlots] = {nullptr, nullptr};
+  cudaEvent_t in_ready[kSlots], step_done[kSlots], out_done[kSlots];
+  bool events = false;
+  uint64_t calls = 0;
+  size_t stage_bytes = 0;
+};
+
+static void pipe_free(HostPipe* p) {
+  if (!p) return;
+  if (p->h2d) cudaStreamSynchronize(p->h2d);
+  if (p->d2h) cudaStreamSynchronize(p->d2h);
+  for (int i = 0; i < HostPipe::kSlots; ++i) {
+    cudaFree(p->stage[i]), cudaFree(p->masks[i]), cudaFree(p->reward[i]), cudaFree(p->done[i]);
+    if (p->events) cudaEventDestroy(p->in_ready[i]), cudaEventDestroy(p->step_done[i]), cudaEventDestroy(p->out_done[i]);
+  }
+  if (p->h2d) cudaStreamDestroy(p->h2d);
+  if (p->d2h) cudaStreamDestroy(p->d2h);
+  delete p;
+}
+
 static int env_free(d2d_env* e) {
   if (!e) return D2D_OK;
+  pipe_free(e->pipe);
   cudaFree(e->buf), cudaFree(e->chan), cudaFree(e->disc), cudaFree(e->recv), cudaFree(e->stats), cudaFree(e->params);
   delete e;
   return D2D_OK;
@@ -697,6 +727,91 @@ extern "C" int d2d_pack_actions(const uint8_t* src, void* dst, int B, int N, int
   else if (C <= 16) pack_actions_kernel<uint16_t><<<grid, block, 0, as_stream(stream)>>>(src, (uint16_t*)dst, B, N, C);
   else pack_actions_kernel<uint32_t><<<grid, block, 0, as_stream(stream)>>>(src, (uint32_t*)dst, B, N, C);
   D2D_LAUNCHED();
+  return D2D_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// host-buffer step: the call a host-side caller of the reference's env.step(actions) makes
+// ------------------------------------------------------------------------------------------------
+static int pipe_create(d2d_env* e) {
+  HostPipe* p = new (std::nothrow) HostPipe();
+  D2D_REQUIRE(p, "d2d_env_step_host: out of host memory");
+  e->pipe = p;
+  const size_t nb = (size_t)e->N * e->B;
+  p->stage_bytes = e->kind == D2D_ENV_COMBINATORIAL ? nb * e->C : nb;
+  D2D_CUDA(cudaStreamCreateWithFlags(&p->h2d, cudaStreamNonBlocking));
+  D2D_CUDA(cudaStreamCreateWithFlags(&p->d2h, cudaStreamNonBlocking));
+  for (int i = 0; i < HostPipe::kSlots; ++i) {
+    D2D_CUDA(cudaMalloc((void**)&p->stage[i], p->stage_bytes));
+    D2D_CUDA(cudaMalloc(&p->masks[i], nb * (e->kind == D2D_ENV_COMBINATORIAL ? e->CB : 1)));
+    D2D_CUDA(cudaMalloc((void**)&p->reward[i], (size_t)e->B * 4));
+    D2D_CUDA(cudaMalloc((void**)&p->done[i], (size_t)e->B));
+    D2D_CUDA(cudaEventCreateWithFlags(&p->in_ready[i], cudaEventDisableTiming));
+    D2D_CUDA(cudaEventCreateWithFlags(&p->step_done[i], cudaEventDisableTiming));
+    D2D_CUDA(cudaEventCreateWithFlags(&p->out_done[i], cudaEventDisableTiming));
+  }
+  p->events = true;
+  return D2D_OK;
+}
+
+extern "C" int d2d_env_step_host(d2d_env* e, const void* actions_host, int layout, float* obs, float* state,
+                                 int32_t* reward_host, uint8_t* done_host, void* ack, void* stream,
+                                 uint64_t* ticket) {
+  D2D_REQUIRE(e && actions_host && reward_host, "d2d_env_step_host: null env, actions or reward");
+  D2D_REQUIRE(layout == D2D_ACT_HOST_REFERENCE || layout == D2D_ACT_HOST_DEVICE_LAYOUT,
+              "d2d_env_step_host: unknown action layout %d", layout);
+  if (!e->is_reset) {
+    set_error("d2d_env_step_host: reset() has not been called");
+    return D2D_ERR_STATE;
+  }
+  if (e->t >= e->T) {
+    set_error("d2d_env_step_host: episode is over (timestep %d >= episode_length %d); call reset()", e->t, e->T);
+    return D2D_ERR_STATE;
+  }
+  int rc;
+  if (!e->pipe && (rc = pipe_create(e))) return rc;
+  HostPipe* p = e->pipe;
+  const int slot = (int)(p->calls % HostPipe::kSlots);
+  const bool reused = p->calls >= HostPipe::kSlots;
+  const size_t nb = (size_t)e->N * e->B;
+  const bool comb = e->kind == D2D_ENV_COMBINATORIAL;
+  D2D_REQUIRE(comb || layout == D2D_ACT_HOST_DEVICE_LAYOUT,
+              "d2d_env_step_host: D2D_ACT_HOST_REFERENCE is defined for the combinatorial env only");
+  const bool need_pack = comb && layout == D2D_ACT_HOST_REFERENCE;
+  cudaStream_t s = as_stream(stream);
+  // 1. host -> device on the copy-in stream, once the step of call k - 2 has consumed this slot
+  if (reused) D2D_CUDA(cudaStreamWaitEvent(p->h2d, p->step_done[slot], 0));
+  void* dst = need_pack ? (void*)p->stage[slot] : p->masks[slot];
+  const size_t bytes = need_pack ? nb * e->C : nb * (comb ? e->CB : 1);
+  D2D_CUDA(cudaMemcpyAsync(dst, actions_host, bytes, cudaMemcpyHostToDevice, p->h2d));
+  D2D_CUDA(cudaEventRecord(p->in_ready[slot], p->h2d));
+  // 2. pack + step on the caller's stream
+  D2D_CUDA(cudaStreamWaitEvent(s, p->in_ready[slot], 0));
+  if (reused) D2D_CUDA(cudaStreamWaitEvent(s, p->out_done[slot], 0));
+  if (need_pack && (rc = d2d_pack_actions(p->stage[slot], p->masks[slot], e->B, e->N, e->C, stream))) return rc;
+  StepArgs a;
+  if ((rc = fill_args(e, a, (uint32_t)(e->t + 1), "d2d_env_step_host"))) return rc;
+  a.actions = p->masks[slot], a.obs = obs, a.state = state, a.reward = p->reward[slot], a.done = p->done[slot];
+  a.ack = ack, a.act_mode = 0;
+  if ((rc = env_step_impl(e, a, stream))) return rc;
+  D2D_CUDA(cudaEventRecord(p->step_done[slot], s));
+  // 3. device -> host on the copy-out stream
+  D2D_CUDA(cudaStreamWaitEvent(p->d2h, p->step_done[slot], 0));
+  D2D_CUDA(cudaMemcpyAsync(reward_host, p->reward[slot], (size_t)e->B * 4, cudaMemcpyDeviceToHost, p->d2h));
+  if (done_host) D2D_CUDA(cudaMemcpyAsync(done_host, p->done[slot], (size_t)e->B, cudaMemcpyDeviceToHost, p->d2h));
+  D2D_CUDA(cudaEventRecord(p->out_done[slot], p->d2h));
+  if (ticket) *ticket = p->calls;
+  p->calls += 1;
+  return D2D_OK;
+}
+
+extern "C" int d2d_env_host_wait(d2d_env* e, uint64_t ticket) {
+  D2D_REQUIRE(e && e->pipe, "d2d_env_host_wait: no host-buffer step has been issued on this env");
+  HostPipe* p = e->pipe;
+  D2D_REQUIRE(ticket < p->calls, "d2d_env_host_wait: ticket %llu has not been issued", (unsigned long long)ticket);
+  // a slot's event is re-recorded by call ticket + kSlots, whose copy-out is stream-ordered after this one's:
+  // waiting on the newest record of the slot therefore always covers `ticket`
+  D2D_CUDA(cudaEventSynchronize(p->out_done[ticket % HostPipe::kSlots]));
   return D2D_OK;
 }
 

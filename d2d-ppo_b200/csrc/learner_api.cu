@@ -811,7 +811,42 @@ extern "C" int d2d_returns_scan(const int32_t* reward, const float* value, doubl
   memset(&a, 0, sizeof(a));
   a.reward_i = reward, a.value = value, a.adv_raw = adv_raw, a.ret_raw = ret_raw, a.stats = stats;
   a.T = T, a.B = B, a.n_cols = n_cols, a.gamma = gamma, a.lam = lam, a.last_env_is_global_last = last_shard;
-  returns_scan_kernel<<<dim3(grid_for(B, 128), n_cols), 128, 0, as_stream(stream)>>>(a);
+  returns_scan_kernel<kScanRaw><<<dim3(grid_for(B, 128), n_cols), 128, 0, as_stream(stream)>>>(a);
+  D2D_LAUNCHED();
+  return D2D_OK;
+}
+
+// two-pass variant: pass 1 accumulates the normalisation statistics only, pass 2 (after the caller reduced the
+// statistics over ranks) repeats the scan and writes the normalised fp32 results; no fp64 intermediates in HBM
+extern "C" int d2d_returns_stats(const int32_t* reward, const float* value, double* stats, int T, int B, int n_cols,
+                                 double gamma, double lam, int last_shard, int want_adv, int want_ret, void* stream) {
+  D2D_REQUIRE(reward && stats && T >= 1 && B >= 1 && n_cols >= 1 && n_cols <= D2D_MAX_AGENTS,
+              "d2d_returns_stats: bad argument");
+  D2D_REQUIRE(!want_adv || value, "d2d_returns_stats: lambda-returns need values");
+  ScanArgs a;
+  memset(&a, 0, sizeof(a));
+  a.reward_i = reward, a.value = value, a.stats = stats, a.want_adv = want_adv, a.want_ret = want_ret;
+  a.T = T, a.B = B, a.n_cols = n_cols, a.gamma = gamma, a.lam = lam, a.last_env_is_global_last = last_shard;
+  returns_scan_kernel<kScanStats><<<dim3(grid_for(B, 128), n_cols), 128, 0, as_stream(stream)>>>(a);
+  D2D_LAUNCHED();
+  return D2D_OK;
+}
+
+extern "C" int d2d_returns_emit(const int32_t* reward, const float* value, float* adv_out, float* ret_out,
+                                const double* adv_mean, const double* adv_std, const int32_t* adv_norm,
+                                const double* ret_mean, const double* ret_std, const int32_t* ret_norm, int T, int B,
+                                int n_cols, double gamma, double lam, int last_shard, void* stream) {
+  D2D_REQUIRE(reward && T >= 1 && B >= 1 && n_cols >= 1 && n_cols <= D2D_MAX_AGENTS, "d2d_returns_emit: bad argument");
+  D2D_REQUIRE(!adv_out || (value && adv_mean && adv_std && adv_norm),
+              "d2d_returns_emit: lambda-returns need values and their statistics");
+  D2D_REQUIRE(!ret_out || (ret_mean && ret_std && ret_norm), "d2d_returns_emit: returns need their statistics");
+  ScanArgs a;
+  memset(&a, 0, sizeof(a));
+  a.reward_i = reward, a.value = value, a.adv_out = adv_out, a.ret_out = ret_out;
+  a.adv_mean = adv_mean, a.adv_std = adv_std, a.adv_norm = adv_norm;
+  a.ret_mean = ret_mean, a.ret_std = ret_std, a.ret_norm = ret_norm;
+  a.T = T, a.B = B, a.n_cols = n_cols, a.gamma = gamma, a.lam = lam, a.last_env_is_global_last = last_shard;
+  returns_scan_kernel<kScanEmit><<<dim3(grid_for(B, 128), n_cols), 128, 0, as_stream(stream)>>>(a);
   D2D_LAUNCHED();
   return D2D_OK;
 }

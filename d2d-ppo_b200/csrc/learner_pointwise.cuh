@@ -378,18 +378,44 @@ struct ScanArgs {
   int T, B, n_cols;
   double gamma, lam;
   int last_env_is_global_last;  // this shard holds the globally last env (multi-GPU)
+  // two-pass mode (kScanStats then kScanEmit): nothing but the normalised fp32 results ever reaches HBM
+  int want_adv, want_ret;
+  float* adv_out;            // [T][N][B] normalised lambda-returns (fp64 maths, numpy semantics)
+  float* ret_out;            // [T][N][B] normalised discounted returns (cast to fp32 first, torch semantics)
+  const double *adv_mean, *adv_std, *ret_mean, *ret_std;   // [N]
+  const int *adv_norm, *ret_norm;                          // [N] normalise flags
 };
 
-__global__ void returns_scan_kernel(const ScanArgs a) {
+enum { kScanRaw = 0, kScanStats = 1, kScanEmit = 2 };
+
+template <int MODE>
+__global__ void __launch_bounds__(128) returns_scan_kernel(const ScanArgs a) {
   const int g = blockIdx.y;
+  const bool do_adv = MODE == kScanRaw ? a.adv_raw != nullptr : (MODE == kScanStats ? a.want_adv : a.adv_out != nullptr);
+  const bool do_ret = MODE == kScanRaw ? a.ret_raw != nullptr : (MODE == kScanStats ? a.want_ret : a.ret_out != nullptr);
   double s_adv = 0, q_adv = 0, s_ret = 0, q_ret = 0;
+  double am = 0, as = 1, rm_ = 0, rs_ = 1;
+  bool an = false, rn = false;
+  if (MODE == kScanEmit) {
+    if (do_adv) am = a.adv_mean[g], as = a.adv_std[g], an = a.adv_norm[g] != 0;
+    if (do_ret) rm_ = a.ret_mean[g], rs_ = a.ret_std[g], rn = a.ret_norm[g] != 0;
+  }
+  const float rmf = (float)rm_, rsf = (float)rs_;
   for (int b = blockIdx.x * blockDim.x + threadIdx.x; b < a.B; b += gridDim.x * blockDim.x) {
     double gae = 0.0, run = 0.0, v_next = 0.0;
-    for (int t = a.T - 1; t >= 0; --t) {
-      const long long idx = ((long long)t * a.n_cols + g) * a.B + b;
-      const double r = a.reward_i ? (double)a.reward_i[(long long)t * a.B + b] : (double)a.reward_f[idx];
-      if (a.adv_raw) {
-        const double v = (double)a.value[idx];
+    // the loads of the next row are issued before the dependent fp64 chain of this row
+    long long idx = ((long long)(a.T - 1) * a.n_cols + g) * a.B + b;
+    const long long step = (long long)a.n_cols * a.B;
+    double r_nx = a.reward_i ? (double)__ldg(a.reward_i + (long long)(a.T - 1) * a.B + b) : (double)__ldg(a.reward_f + idx);
+    float v_nx = do_adv ? __ldg(a.value + idx) : 0.f;
+    for (int t = a.T - 1; t >= 0; --t, idx -= step) {
+      const double r = r_nx;
+      const double v = (double)v_nx;
+      if (t > 0) {
+        r_nx = a.reward_i ? (double)__ldg(a.reward_i + (long long)(t - 1) * a.B + b) : (double)__ldg(a.reward_f + idx - step);
+        if (do_adv) v_nx = __ldg(a.value + idx - step);
+      }
+      if (do_adv) {
         double out;
         if (t == a.T - 1) {
           // done: delta = r - v, gae = delta, out = gae + v = r;  the globally last row keeps r - v (:102)
@@ -402,17 +428,21 @@ __global__ void returns_scan_kernel(const ScanArgs a) {
           out = gae + v;
         }
         v_next = v;
-        a.adv_raw[idx] = out;
-        s_adv += out, q_adv += out * out;
+        if (MODE == kScanRaw) a.adv_raw[idx] = out;
+        if (MODE == kScanEmit) a.adv_out[idx] = (float)(an ? (out - am) / as : out);
+        if (MODE != kScanEmit) s_adv += out, q_adv += out * out;
       }
-      if (a.ret_raw) {
+      if (do_ret) {
         run = (t == a.T - 1) ? r : r + run * a.gamma;
-        a.ret_raw[idx] = run;
-        const double rf = (double)(float)run;   // the reference casts to fp32 before normalising (:119)
-        s_ret += rf, q_ret += rf * rf;
+        if (MODE == kScanRaw) a.ret_raw[idx] = run;
+        const float xf = (float)run;               // the reference casts to fp32 before normalising (:119)
+        if (MODE == kScanEmit) a.ret_out[idx] = rn ? (xf - rmf) / rsf : xf;
+        const double rf = (double)xf;
+        if (MODE != kScanEmit) s_ret += rf, q_ret += rf * rf;
       }
     }
   }
+  if (MODE == kScanEmit) return;
   double vals[4] = {s_adv, q_adv, s_ret, q_ret};
   for (int k = 0; k < 4; ++k) {
     double v = vals[k];

@@ -230,6 +230,51 @@ class LockstepEnv:
     def _new_ack(self):
         return None
 
+    # ------------------------------------------------------------------ host-buffer step (pipelined copies)
+    def step_host(self, host_actions, host_reward, *, layout="reference", host_done=None, with_obs=True,
+                  with_state=False, out_obs=None, out_state=None):
+        """step(actions) for callers whose actions and rewards live in HOST memory (d2d_env_step_host).
+
+        host_actions: pinned CPU tensor; layout "reference" = u8 [B, N, C] 0/1 (the reference's (N, C) array per
+        env, combinatorial env only), layout "device" = the [N, B] device layout (masks / flags / channel ids).
+        host_reward: pinned int32 [B] CPU tensor that receives the per-env reward; host_done: optional pinned u8 [B].
+        Asynchronous: returns a ticket; ``host_wait(ticket)`` blocks until host_reward of that call is valid.  The
+        H2D copy, the kernels and the D2H copy of consecutive calls overlap (two calls in flight), so issue call
+        k + 1 before waiting for call k.  Observations / state stay on the device (``obs_rows_tensor``)."""
+        if host_actions.device.type != "cpu" or host_reward.device.type != "cpu":
+            raise ValueError("step_host takes CPU (pinned) tensors; use step() for device tensors")
+        if host_reward.dtype != torch.int32 or host_reward.numel() != self.n_envs or not host_reward.is_contiguous():
+            raise ValueError("host_reward must be a contiguous int32 [B] tensor")
+        if not host_actions.is_contiguous():
+            raise ValueError("host_actions must be contiguous")
+        N, B = self.n_agents, self.n_envs
+        if layout == "reference":
+            want, code = (B * N * self.n_channels, torch.uint8), L.ACT_HOST_REFERENCE
+        elif layout == "device":
+            comb = self.KIND == L.ENV_COMBINATORIAL
+            want, code = (N * B, self._mask_dtype if comb else torch.uint8), L.ACT_HOST_DEVICE_LAYOUT
+        else:
+            raise ValueError("layout must be 'reference' or 'device'")
+        if host_actions.numel() != want[0] or host_actions.dtype != want[1]:
+            raise ValueError(f"host_actions must hold {want[0]} elements of {want[1]} for layout '{layout}'")
+        obs, state = self._new_outputs(with_obs and out_obs is None, with_state and out_state is None)
+        obs = out_obs if out_obs is not None else obs
+        state = out_state if out_state is not None else state
+        ack = self._new_ack()
+        ticket = C.c_uint64()
+        with torch.cuda.device(self.device):
+            L.check(self._lib.d2d_env_step_host(self._h, L.ptr(host_actions), code, L.ptr(obs), L.ptr(state),
+                                                L.ptr(host_reward), L.ptr(host_done), L.ptr(ack),
+                                                L.current_stream(), C.byref(ticket)))
+        self.timestep += 1
+        self.last_ack = ack
+        self.obs_rows_tensor, self.state_rows_tensor = obs, state
+        return int(ticket.value)
+
+    def host_wait(self, ticket):
+        """Block until the host buffers of the step_host call `ticket` are valid."""
+        L.check(self._lib.d2d_env_host_wait(self._h, int(ticket)))
+
     # ------------------------------------------------------------------ zero-copy entry points for the learners
     def reset_into(self, out_obs, out_state=None):
         """reset() writing the env-minor observation block [obs_rows, B] (and state block) in place."""

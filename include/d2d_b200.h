@@ -132,6 +132,24 @@ int d2d_env_step_random_access(d2d_env* env, double transmission_prob, void* act
 int d2d_pack_actions(const uint8_t* actions_bnc, void* packed, int n_envs, int n_agents, int n_channels,
                      void* stream);
 
+/* step(actions) with HOST buffers: what a host-side caller of the reference's env.step(actions)
+ * (combinatorial_env.py:127) hands over and gets back, with the host<->device copies done by the library.
+ *   actions_host  D2D_ACT_HOST_REFERENCE (combinatorial only): u8 [B][N][C] 0/1, the reference's (N, C) action
+ *                 array of every env back to back;  D2D_ACT_HOST_DEVICE_LAYOUT: the `actions` layout of
+ *                 d2d_env_step ([N][B] masks / flags / channel ids).  Pinned memory for asynchronous copies.
+ *   reward_host   i32 [B] (required), done_host u8 [B] (may be NULL): pinned host memory
+ *   obs / state / ack: DEVICE pointers as in d2d_env_step (may be NULL)
+ * The call is asynchronous and pipelined: the H2D copy runs on the handle's copy-in stream, pack + step on
+ * `stream`, the D2H copy on the copy-out stream, so consecutive calls overlap.  Up to two calls are in flight;
+ * actions_host must stay untouched until the call's step ran (d2d_env_host_wait of the same ticket suffices).
+ * *ticket (may be NULL) identifies the call; d2d_env_host_wait(env, ticket) blocks the host thread until
+ * reward_host / done_host of that call are valid. */
+#define D2D_ACT_HOST_REFERENCE 0
+#define D2D_ACT_HOST_DEVICE_LAYOUT 1
+int d2d_env_step_host(d2d_env* env, const void* actions_host, int layout, float* obs, float* state,
+                      int32_t* reward_host, uint8_t* done_host, void* ack, void* stream, uint64_t* ticket);
+int d2d_env_host_wait(d2d_env* env, uint64_t ticket);
+
 /* Counters and raw state, env-minor: buffers u8 [N][Dmax][B]... exported as
  *   buffers  u8  [N][B][rec]   rec = d2d_env_record_bytes() (8/16/32), byte d = packets with d slots left
  *   channel  combinatorial: mask [N][B]; single-channel u8 [N][B]; selection u32 [B]
@@ -262,6 +280,18 @@ int d2d_adam_step(float* params, float* m, float* v, const float* grads, int n_a
  *   last_shard  1 if this GPU holds the globally last env (its final row keeps the r - v quirk of :102)  */
 int d2d_returns_scan(const int32_t* reward, const float* value, double* adv_raw, double* ret_raw, double* stats,
                      int T, int n_envs, int n_cols, double gamma, double lam, int last_shard, void* stream);
+/* The same scans in two passes without fp64 intermediates in HBM (17 B per element instead of 45):
+ * d2d_returns_stats accumulates `stats` only (want_adv / want_ret select the scans); after the caller has
+ * reduced the statistics over ranks, d2d_returns_emit repeats the scans and writes the NORMALISED results
+ *   adv_out f32 [T][n_cols][B] = (lambda-return - mean) / std in float64, numpy semantics (d2d_ppo.py:107-109)
+ *   ret_out f32 [T][n_cols][B] = ((float)return - mean) / std in float32, torch semantics (d2d_ppo.py:119-123)
+ * (either may be NULL; *_norm[col] == 0 skips the normalisation of that column, :108 / :122). */
+int d2d_returns_stats(const int32_t* reward, const float* value, double* stats, int T, int n_envs, int n_cols,
+                      double gamma, double lam, int last_shard, int want_adv, int want_ret, void* stream);
+int d2d_returns_emit(const int32_t* reward, const float* value, float* adv_out, float* ret_out,
+                     const double* adv_mean, const double* adv_std, const int32_t* adv_norm,
+                     const double* ret_mean, const double* ret_std, const int32_t* ret_norm, int T, int n_envs,
+                     int n_cols, double gamma, double lam, int last_shard, void* stream);
 /* out[i] = (raw[i] - mean[col]) / std[col] as f32 (do_norm[col] == 0: plain cast); fp32_math = 1 reproduces
  * discount_rewards (cast to f32 first, normalise in f32).  mean/std f64 device [n_cols], do_norm i32 device. */
 int d2d_normalize(const double* raw, float* out, const double* mean, const double* std, const int32_t* do_norm,

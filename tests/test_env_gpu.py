@@ -141,6 +141,47 @@ def test_fused_random_access_policy(cuda_device):
     assert np.array_equal(to_np(env.discarded_packets), orc.discarded)
 
 
+@pytest.mark.parametrize("layout", ["reference", "device"])
+def test_host_buffer_step_matches_oracle(layout, cuda_device):
+    """step_host (d2d_env_step_host: pinned host actions in, pinned host rewards out, pipelined copies) against the
+    oracle on Philox streams; the host reads step i - 1 after issuing step i, as bench.py's e2e loop does."""
+    import torch
+    from oracle.envs_np import PhiloxSource
+    g = load_env_case("comb_c3_load0.33")
+    kw = g["config"]
+    B, T, seed = 777, 40, 5
+    env = make_cuda_env("combinatorial", kw, B, rng="philox", seed=seed, device=cuda_device)
+    orc = make_oracle("combinatorial", kw, B, PhiloxSource(B, seed))
+    env.reset(), orc.reset()
+    rng = np.random.default_rng(3)
+    acts = rng.binomial(1, 0.3, (T, B, 6, 8)).astype(np.uint8)
+    w = (1 << np.arange(8)).astype(np.uint8)
+    host_a = [torch.from_numpy(acts[t] if layout == "reference"
+                               else np.ascontiguousarray((acts[t] * w).sum(-1).astype(np.uint8).T)).pin_memory()
+              for t in range(T)]
+    host_r = [torch.empty(B, dtype=torch.int32).pin_memory() for _ in range(2)]
+    host_d = [torch.empty(B, dtype=torch.uint8).pin_memory() for _ in range(2)]
+    expected, pending = [], None
+    for t in range(T):
+        tk = env.step_host(host_a[t], host_r[t % 2], layout=layout, host_done=host_d[t % 2], with_state=True)
+        obs_rows, state_rows = env.obs_rows_tensor, env.state_rows_tensor
+        o_obs, o_state, o_rew, o_done, _ = orc.step(acts[t])
+        expected.append((o_rew[:, 0].copy(), o_done))
+        if pending is not None:
+            env.host_wait(pending)
+            assert np.array_equal(host_r[(t - 1) % 2].numpy(), expected[t - 1][0]), ("reward", t - 1)
+            assert np.array_equal(host_d[(t - 1) % 2].numpy(), np.full(B, int(expected[t - 1][1]), np.uint8))
+        pending = tk
+        assert np.array_equal(to_np(obs_rows.t()), np.concatenate(o_obs, axis=1)), ("obs", t)
+        assert np.array_equal(to_np(state_rows.t()), o_state), ("state", t)
+    env.host_wait(pending)
+    assert np.array_equal(host_r[(T - 1) % 2].numpy(), expected[T - 1][0])
+    assert np.array_equal(to_np(env.received_packets), orc.received)
+    assert np.array_equal(to_np(env.discarded_packets), orc.discarded)
+    with pytest.raises(ValueError):
+        env.step_host(host_a[0][:1], host_r[0])
+
+
 def test_reference_compatible_single_env_mode(cuda_device):
     """n_envs=None: host numpy outputs with the reference's shapes and dtypes."""
     g = load_env_case("comb_c3_load1_ragged_obs")

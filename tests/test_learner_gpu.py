@@ -104,7 +104,7 @@ def test_sampling_statistics(cuda_device):
 
 
 def test_returns_scan_and_normalise(cuda_device):
-    from d2d_ppo_b200.algorithms._nets import normalize, returns_scan
+    from d2d_ppo_b200.algorithms._nets import normalize, returns_emit, returns_scan, returns_stats
     g = load_ppo_case("returns")
     for tag, E in (("a", 5), ("c", 3)):
         T = int(g[f"{tag}/T"])
@@ -129,6 +129,14 @@ def test_returns_scan_and_normalise(cuda_device):
                                          values[:, col].astype(np.float32), gamma, 0.97)
                 assert rel_err(_rows(a32)[:, 0], ref_a) < TOL
                 assert rel_err(_rows(r32)[:, 0], g[f"{tag}/g{gamma}/ret"][:, col]) < TOL
+                # two-pass path (statistics, then normalised fp32 straight from a second scan): same bits
+                stats2 = returns_stats(r, v, gamma, 0.97, 1)
+                assert torch.equal(stats2, stats)
+                a2, r2 = returns_emit(r, v, gamma, 0.97, 1, (mean_a, std_a, one), (mean_r, std_r, one))
+                assert torch.equal(a2, a32) and torch.equal(r2, r32)
+                zero = torch.zeros(1, dtype=torch.int32, device=cuda_device)
+                a3, r3 = returns_emit(r, v, gamma, 0.97, 1, (mean_a, std_a, zero), (mean_r, std_r, zero))
+                assert torch.equal(a3, adv.float()) and torch.equal(r3, ret.float())
 
 
 def _pick_envs(a, E, T, envs):
