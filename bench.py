@@ -48,6 +48,7 @@ def parse():
     ap.add_argument("--cpu-envs", type=int, default=4096, help="envs per process of the CPU arm")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-learner-envs", type=int, default=64, help="envs of the CPU iPPO iteration baseline")
+    ap.add_argument("--no-configs", action="store_true", help="skip the c1 / c2 / c4 / selection env-step sections")
     ap.add_argument("--no-learner", action="store_true", help="skip the learned-policy rollout / train SPS sections")
     ap.add_argument("--rollout-envs", type=int, default=65536, help="envs per GPU of the learned-policy rollout (c3)")
     ap.add_argument("--train-envs", type=int, default=4096, help="envs per GPU of the train-SPS sections")
@@ -234,8 +235,10 @@ def bench_learner(args, dev, world, rank, barrier, max_over_ranks):
     env = CombinatorialEnv(n_envs=B, device=dev, seed=7, env_offset=rank * B, **kw)
     agent = iPPO(env, hidden_size=64, gamma=0.4, policy_lr=3e-4, value_lr=1e-3, useRNN=True, combinatorial=True,
                  history_len=6, early_stopping=False, seed=1, scratch_bytes=6 << 30)
-    agent._run_episode(_lib.ACT_SAMPLE, per_step=None)          # warm-up episode (allocations, clocks)
-    dt, launches = timed(lambda: agent.create_rollouts(B))
+    agent.create_rollouts(B)                                    # warm-up rollout (scratch allocations, clocks)
+    n_roll = 3
+    dt, launches = timed(lambda: [agent.create_rollouts(B) for _ in range(n_roll)])
+    dt, launches = dt / n_roll, launches // n_roll
     flops = 2 * gru_flops_per_agent_step(30, 64, 6, 8) - (2 * 64 * 8 - 2 * 64)   # actor (O=8) + critic (O=1)
     steps = world * B * N_AGENTS * T
     hbm_peak, bf16_peak, peak_src = measured_peaks()
@@ -330,6 +333,79 @@ def bench_learner(args, dev, world, rank, barrier, max_over_ranks):
         lambda e: D2DPPO(e, hidden_size=64, gamma=0.6, policy_lr=3e-4, value_lr=1e-3, useRNN=True, combinatorial=False,
                          history_len=4, early_stopping=False, seed=4, scratch_bytes=6 << 30),
         4096, 4, "c2: D2DPPO GRU (H 64, L 4) on D2DEnv N=4, 4096 lockstep envs")
+    return out
+
+
+# ------------------------------------------------------------------------------------------------
+# the other BASELINE configs through the same step kernels (extra key `env_configs`)
+# ------------------------------------------------------------------------------------------------
+def env_alg_bytes(D, C, N, obs_floats_per_agent, per_env_bytes, action_bytes):
+    """(D + m + action + 8) read + (D + m + 8 + 4 obs + per_env / N) written per agent-step,
+    m = ceil(C / 8) channel-mask bytes; action_bytes = 0 when the policy is fused into the step kernel."""
+    m = (C + 7) // 8
+    return (D + m + action_bytes + 8) + (D + m + 8 + 4 * obs_floats_per_agent + per_env_bytes / N)
+
+
+def bench_env_configs(dev, hbm_peak, steps=200):
+    import numpy as np
+    import torch
+
+    from d2d_ppo_b200 import presets
+    from d2d_ppo_b200.envs import ChannelSelectionEnv, CombinatorialEnv, D2DEnv
+    out = []
+
+    def run(label, env, alg, tp=None, actions=None):
+        B, N, T = env.n_envs, env.n_agents, env.episode_length
+        obs = torch.empty((env.obs_layout[0], B), dtype=torch.float32, device=dev)
+        rew = torch.empty(B, dtype=torch.int32, device=dev)
+
+        def one():
+            if env.timestep >= T:
+                env._reset_device(True, False, out_obs=obs)
+            env._step_device(actions, True, False, obs, None, random_access_tp=tp, out_reward=rew)
+        env._reset_device(True, False, out_obs=obs)
+        for _ in range(5):
+            one()
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(steps + 1)]
+        ev[0].record()
+        for i in range(steps):
+            one()
+            ev[i + 1].record()
+        torch.cuda.synchronize()
+        ms = float(np.median([ev[i].elapsed_time(ev[i + 1]) for i in range(steps)]))
+        rate = B * N / (ms * 1e-3)
+        out.append({"config": label, "envs": B, "n_agents": N, "agent_steps_per_s": rate, "kernel_ms": ms,
+                    "alg_bytes_per_agent_step": alg, "achieved_gbs": rate * alg / 1e9,
+                    "frac_of_hbm_peak": rate * alg / 1e9 / hbm_peak,
+                    "working_set_mb": B * N * alg / 1e6})
+        del env, obs
+        torch.cuda.empty_cache()
+
+    # c1: run_ma_baselines.py default, 16 channels, ragged observations (deadlines[k] + 2C = 39 / 46 floats)
+    kw = presets.combinatorial_kwargs("setup", load=1 / 3, homogeneous_size=False)
+    run("c1 CombinatorialEnv setup.p (C=16, ragged obs), fused random access", CombinatorialEnv(
+        n_envs=1 << 19, device=dev, seed=1, **kw), env_alg_bytes(10.5, 16, 6, 42.5, 5 + 16, 0), tp=TP)
+    # c2: D2DEnv N=4 at the named 4096 envs (L2-resident, launch-latency bound) and at 4M envs (HBM roofline)
+    c2 = presets.d2d_c2_kwargs()
+    for B in (4096, 1 << 22):
+        run(f"c2 D2DEnv N=4 deadlines 7, {B} envs, fused random access", D2DEnv(n_envs=B, device=dev, seed=2, **c2),
+            env_alg_bytes(7, 1, 4, 9, 5, 0), tp=TP)
+    # c4: xp_n_agents sweep, C=4, deadlines 7, B x N = 4M
+    for N in (4, 16, 64):
+        kw = presets.n_agents_sweep_kwargs(N, load=1 / 3)
+        run(f"c4 CombinatorialEnv N={N} C=4 aperiodic load 1/3, fused random access", CombinatorialEnv(
+            n_envs=(1 << 22) // N, device=dev, seed=3, **kw), env_alg_bytes(7, 4, N, 15, 5 + 4, 0), tp=TP)
+    # ChannelSelectionEnv as in xp_gamma.py:43-54 (N=5, C=16): actions from a device tensor (no fused policy)
+    N, C = 5, 16
+    B = 1 << 20
+    sel = ChannelSelectionEnv(n_agents=N, n_channels=C, deadlines=np.array([7] * N), lbdas=np.array([1 / 3] * N),
+                              period=None, arrival_probs=None, offsets=None, episode_length=200,
+                              traffic_model="aperiodic", periodic_devices=[], channel_switch=np.array([0.2] * (C + 1)),
+                              n_envs=B, device=dev, seed=4)
+    acts = torch.randint(0, C + 1, (N, B), dtype=torch.uint8, device=dev)
+    # global channel state u32 per env (read + written), ack f32 [C+1] per env in the observation only
+    alg = (7 + 1 + 8) + (7 + 8 + 4 * (7 + C + 1)) + (8 + 5 + 4 * (C + 1)) / N
+    run("ChannelSelectionEnv xp_gamma.py (N=5, C=16), device actions u8 [N,B]", sel, alg, actions=acts)
     return out
 
 
@@ -484,6 +560,8 @@ def run_native(args):
     }
     del obs_buf, env, host_actions, host_masks
     torch.cuda.empty_cache()
+    if not args.no_configs:
+        line["env_configs"] = bench_env_configs(dev, peak)
     if not args.no_learner:
         line.update(bench_learner(args, dev, world, rank, barrier, max_over_ranks))
     if rank == 0 and world == 1 and not args.no_cpu_baseline:

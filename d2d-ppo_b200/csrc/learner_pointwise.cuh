@@ -401,44 +401,53 @@ __global__ void __launch_bounds__(128) returns_scan_kernel(const ScanArgs a) {
     if (do_ret) rm_ = a.ret_mean[g], rs_ = a.ret_std[g], rn = a.ret_norm[g] != 0;
   }
   const float rmf = (float)rm_, rsf = (float)rs_;
+  constexpr int U = 8;   // time steps loaded per batch: U independent row loads in flight ahead of the serial fp64 chain
+  const long long step = (long long)a.n_cols * a.B;
   for (int b = blockIdx.x * blockDim.x + threadIdx.x; b < a.B; b += gridDim.x * blockDim.x) {
     double gae = 0.0, run = 0.0, v_next = 0.0;
-    // the loads of the next row are issued before the dependent fp64 chain of this row
-    long long idx = ((long long)(a.T - 1) * a.n_cols + g) * a.B + b;
-    const long long step = (long long)a.n_cols * a.B;
-    double r_nx = a.reward_i ? (double)__ldg(a.reward_i + (long long)(a.T - 1) * a.B + b) : (double)__ldg(a.reward_f + idx);
-    float v_nx = do_adv ? __ldg(a.value + idx) : 0.f;
-    for (int t = a.T - 1; t >= 0; --t, idx -= step) {
-      const double r = r_nx;
-      const double v = (double)v_nx;
-      if (t > 0) {
-        r_nx = a.reward_i ? (double)__ldg(a.reward_i + (long long)(t - 1) * a.B + b) : (double)__ldg(a.reward_f + idx - step);
-        if (do_adv) v_nx = __ldg(a.value + idx - step);
-      }
-      if (do_adv) {
-        double out;
-        if (t == a.T - 1) {
-          // done: delta = r - v, gae = delta, out = gae + v = r;  the globally last row keeps r - v (:102)
-          const bool quirk = a.last_env_is_global_last && b == a.B - 1;
-          gae = quirk ? 0.0 : r - v;
-          out = quirk ? r - v : gae + v;
-        } else {
-          const double delta = r + a.gamma * v_next - v;
-          gae = delta + a.gamma * a.lam * gae;
-          out = gae + v;
+    for (int t_hi = a.T - 1; t_hi >= 0; t_hi -= U) {
+      float rr[U], vv[U];
+      const long long idx_hi = ((long long)t_hi * a.n_cols + g) * a.B + b;
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        if (t_hi - u >= 0) {
+          rr[u] = a.reward_i ? (float)__ldg(a.reward_i + (long long)(t_hi - u) * a.B + b)
+                             : __ldg(a.reward_f + idx_hi - u * step);
+          vv[u] = do_adv ? __ldg(a.value + idx_hi - u * step) : 0.f;
         }
-        v_next = v;
-        if (MODE == kScanRaw) a.adv_raw[idx] = out;
-        if (MODE == kScanEmit) a.adv_out[idx] = (float)(an ? (out - am) / as : out);
-        if (MODE != kScanEmit) s_adv += out, q_adv += out * out;
       }
-      if (do_ret) {
-        run = (t == a.T - 1) ? r : r + run * a.gamma;
-        if (MODE == kScanRaw) a.ret_raw[idx] = run;
-        const float xf = (float)run;               // the reference casts to fp32 before normalising (:119)
-        if (MODE == kScanEmit) a.ret_out[idx] = rn ? (xf - rmf) / rsf : xf;
-        const double rf = (double)xf;
-        if (MODE != kScanEmit) s_ret += rf, q_ret += rf * rf;
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int t = t_hi - u;
+        if (t < 0) break;
+        const long long idx = idx_hi - u * step;
+        const double r = (double)rr[u];
+        const double v = (double)vv[u];
+        if (do_adv) {
+          double out;
+          if (t == a.T - 1) {
+            // done: delta = r - v, gae = delta, out = gae + v = r;  the globally last row keeps r - v (:102)
+            const bool quirk = a.last_env_is_global_last && b == a.B - 1;
+            gae = quirk ? 0.0 : r - v;
+            out = quirk ? r - v : gae + v;
+          } else {
+            const double delta = r + a.gamma * v_next - v;
+            gae = delta + a.gamma * a.lam * gae;
+            out = gae + v;
+          }
+          v_next = v;
+          if (MODE == kScanRaw) a.adv_raw[idx] = out;
+          if (MODE == kScanEmit) __stcs(a.adv_out + idx, (float)(an ? (out - am) / as : out));
+          if (MODE != kScanEmit) s_adv += out, q_adv += out * out;
+        }
+        if (do_ret) {
+          run = (t == a.T - 1) ? r : r + run * a.gamma;
+          if (MODE == kScanRaw) a.ret_raw[idx] = run;
+          const float xf = (float)run;               // the reference casts to fp32 before normalising (:119)
+          if (MODE == kScanEmit) __stcs(a.ret_out + idx, rn ? (xf - rmf) / rsf : xf);
+          const double rf = (double)xf;
+          if (MODE != kScanEmit) s_ret += rf, q_ret += rf * rf;
+        }
       }
     }
   }

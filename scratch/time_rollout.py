@@ -22,3 +22,11 @@ env.reset_into(ag.obs_buf[ag.lead])
 timeit("env.step_into", lambda i: env.step_into(ag.act_buf[i], ag.obs_buf[ag.lead + i + 1], None, ag.reward_buf[i]))
 torch.cuda.synchronize(); t0 = time.perf_counter(); ag._run_episode(_lib.ACT_SAMPLE); torch.cuda.synchronize(); print("episode (policy only) s:", time.perf_counter() - t0)
 torch.cuda.synchronize(); t0 = time.perf_counter(); ag.create_rollouts(B); torch.cuda.synchronize(); print("create_rollouts s:", time.perf_counter() - t0)
+import subprocess, threading
+rows = []
+p = subprocess.Popen(["nvidia-smi", "--query-gpu=clocks.sm,power.draw,clocks_event_reasons.sw_power_cap", "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE, text=True)
+threading.Thread(target=lambda: [rows.append(l.strip()) for l in p.stdout], daemon=True).start()
+for _ in range(3):
+    torch.cuda.synchronize(); t0 = time.perf_counter(); ag.create_rollouts(B); torch.cuda.synchronize(); print("create_rollouts s:", time.perf_counter() - t0)
+p.terminate()
+print("clock samples:", rows[::3])
