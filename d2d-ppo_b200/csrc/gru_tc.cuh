@@ -42,6 +42,11 @@ struct GruTcArgs {
   int in_dim[D2D_MAX_AGENTS];
   int L, B, t0, t1;
   int padded;    // 1: steps before the episode start run on zero inputs; 0: they do not exist (rollout windows)
+  // training direction (store = 1, padded = 1): every step's gate activations and hidden state are kept for BPTT
+  int store;
+  View acts;     // [.. 4H ..] r, z, n, gh_n of step 0; step s is acts_step floats further
+  View hs;       // [.. H ..]  h after step 0; step s is hs_step floats further (h_out is not written when store = 1)
+  long long acts_step, hs_step;
 };
 
 namespace tc {
@@ -315,6 +320,12 @@ __global__ void __launch_bounds__(tc::kThreads, 1) gru_window_tc_kernel(const Gr
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         const uint32_t d = tmem + (uint32_t)slot * (4 * H) + lane_addr + (uint32_t)u0;
         const bool first = s == s0;
+        float* acts_row = nullptr;
+        float* hs_row = nullptr;
+        if (a.store && b < a.B) {
+          acts_row = view_ptr(a.acts, g, t, a.B, b) + (long long)s * a.acts_step;
+          hs_row = view_ptr(a.hs, g, t, a.B, b) + (long long)s * a.hs_step;
+        }
 #pragma unroll
         for (int c = 0; c < HH / 8; ++c) {
           float pr[8], pz[8], pin[8], phn[8];
@@ -344,6 +355,12 @@ __global__ void __launch_bounds__(tc::kThreads, 1) gru_window_tc_kernel(const Gr
             const float hv = fmaf(z, h[c * 8 + j] - nn, nn);   // (1 - z) n + z h
             h[c * 8 + j] = hv;
             split3_trunc(hv, q0[j], q1[j], q2[j]);
+            if (a.store && b < a.B) {   // rows of a warp are consecutive envs: every store below is one 128-byte line
+              const long long f = (long long)(u0 + c * 8 + j) * a.B;
+              const long long hb = (long long)H * a.B;
+              acts_row[f] = r, acts_row[f + hb] = z, acts_row[f + 2 * hb] = nn, acts_row[f + 3 * hb] = ghn;
+              hs_row[f] = hv;
+            }
           }
           if (has_next) {
             const int o = canon16(row, u0 + c * 8, H);
@@ -360,7 +377,7 @@ __global__ void __launch_bounds__(tc::kThreads, 1) gru_window_tc_kernel(const Gr
           publish();
         } else {
           // TMEM reads of this tile are complete before the next tile's first MMA: its publish() fences them
-          if (b < a.B) {
+          if (b < a.B && !a.store) {
             float* ho = view_ptr(a.h_out, g, t, a.B, b);
 #pragma unroll
             for (int u = 0; u < HH; ++u) ho[(long long)(u0 + u) * a.B] = h[u];

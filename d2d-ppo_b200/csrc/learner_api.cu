@@ -257,10 +257,12 @@ static int launch_gru_tc_h(const d2d_net* n, const GruTcArgs& a, cudaStream_t s)
 }
 
 static int launch_gru_tc(const d2d_net* n, const float* params, const View& x, const View& h_out, int t0, int t1,
-                         int padded, cudaStream_t s) {
+                         int padded, cudaStream_t s, const View* acts = nullptr, const View* hs = nullptr,
+                         long long acts_step = 0, long long hs_step = 0) {
   GruTcArgs a;
   memset(&a, 0, sizeof(a));
   a.x = x, a.h_out = h_out, a.w = params, a.w_agent_stride = n->stride;
+  if (acts) a.store = 1, a.acts = *acts, a.hs = *hs, a.acts_step = acts_step, a.hs_step = hs_step;
   for (int g = 0; g < n->N; ++g) {
     a.wih_off[g] = n->o_wih[g], a.whh_off[g] = n->o_whh[g], a.bih_off[g] = n->o_bih[g], a.bhh_off[g] = n->o_bhh[g];
     a.in_dim[g] = n->in_dim[g];
@@ -372,10 +374,19 @@ static int forward_chunk(d2d_net* n, const float* params, const float* x, int x_
     last = xin;
   } else {
     const int L = n->L, halo = c.halo;
-    const bool use_tc = !train && gru_tc_eligible(n);   // inference direction: tcgen05 fused window (gru_tc.cuh)
+    // tcgen05 fused window (gru_tc.cuh); training windows are always padded and keep every step's activations
+    const bool use_tc = gru_tc_eligible(n) && (!train || padded);
     if (use_tc) {
       const View hl = make_view(hs_ptr(n, c, train, L - 1), H * NB, -c0, N, H, B);
-      if ((rc = launch_gru_tc(n, params, xin, hl, c0, c1, padded, s))) return rc;
+      if (train) {
+        const View av = make_view(c.acts, 4 * H * NB, -c0, N, 4 * H, B);
+        const View hv = make_view(c.hs, H * NB, -c0, N, H, B);
+        rc = launch_gru_tc(n, params, xin, hl, c0, c1, padded, s, &av, &hv, (long long)c.Tc * 4 * H * NB,
+                           (long long)c.Tc * H * NB);
+      } else {
+        rc = launch_gru_tc(n, params, xin, hl, c0, c1, padded, s);
+      }
+      if (rc) return rc;
     }
     // input projections of every observation the chunk's windows touch: times [c0 - halo, c1)
     const View gi = make_view(c.gi, 3 * H * NB, -(c0 - halo), N, 3 * H, B);
