@@ -118,6 +118,36 @@ def test_cuda_philox_mode_matches_oracle(name, offset, cuda_device):
     _rollout_against_oracle(env, orc, kind, act, check_every=5)
 
 
+@pytest.mark.parametrize("n_agents,load", [(4, 1 / 14), (16, 1 / 3), (32, 0.8), (64, 1.0)])
+def test_n_agents_sweep_matches_oracle(n_agents, load, cuda_device):
+    """Config c4 (xp_n_agents.py:62-83 with xp_load.py traffic levels): N = 4..64 devices on 4 channels,
+    collision-heavy; device Philox streams against the numpy restatement, bit exact."""
+    from d2d_ppo_b200.presets import n_agents_sweep_kwargs
+    from oracle.envs_np import PhiloxSource
+    from oracle.gen_golden import draw_actions
+    kw = n_agents_sweep_kwargs(n_agents, load=load, episode_length=30)
+    B, T = 97, 30
+    act = draw_actions("combinatorial", kw, B, T, 0.4, np.random.default_rng(n_agents))
+    env = make_cuda_env("combinatorial", kw, B, rng="philox", seed=n_agents, env_offset=5, device=cuda_device)
+    orc = make_oracle("combinatorial", kw, B, PhiloxSource(B, n_agents, env_offset=5))
+    _rollout_against_oracle(env, orc, "combinatorial", act, check_every=3)
+
+
+def test_maximum_sizes_match_oracle(cuda_device):
+    """The build's limits in one env: 32 channels, deadlines up to 32, ragged observations, Poisson load 1."""
+    from oracle.envs_np import PhiloxSource
+    from oracle.gen_golden import draw_actions
+    N, C = 5, 32
+    kw = dict(n_agents=N, n_channels=C, deadlines=np.array([32, 1, 17, 32, 8]), lbdas=np.array([1.0] * N), period=None,
+              arrival_probs=None, offsets=None, episode_length=25, traffic_model="aperiodic", periodic_devices=[],
+              homogeneous_size=False, channel_switch=np.linspace(0.0, 1.0, N * C).reshape(N, C))
+    B, T = 70, 25
+    act = draw_actions("combinatorial", kw, B, T, 0.1, np.random.default_rng(9))
+    env = make_cuda_env("combinatorial", kw, B, rng="philox", seed=17, device=cuda_device)
+    orc = make_oracle("combinatorial", kw, B, PhiloxSource(B, 17))
+    _rollout_against_oracle(env, orc, "combinatorial", act, check_every=4)
+
+
 def test_fused_random_access_policy(cuda_device):
     """step_random_access == oracle step fed with the Philox policy-stream action bits."""
     from oracle import philox_np as px
