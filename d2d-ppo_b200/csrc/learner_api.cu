@@ -17,6 +17,7 @@
 #include <vector>
 
 #include "gru_tc.cuh"
+#include "gru_bwd_tc.cuh"
 #include "wgrad_tc.cuh"
 #include "dense_tc.cuh"
 #include "learner_pointwise.cuh"
@@ -276,6 +277,27 @@ static int launch_gru_tc(const d2d_net* n, const float* params, const View& x, c
   }
 }
 
+// tensor-core fused BPTT through the window (gru_bwd_tc.cuh)
+static bool gru_bwd_tc_eligible(const d2d_net* n) {
+  return tc_enabled() && n->arch == D2D_NET_GRU && (n->H == 32 || n->H == 64) && n->L >= 1;
+}
+
+template <int H>
+static int launch_gru_bwd_tc_h(const d2d_net* n, const GruBwdTcArgs& a, cudaStream_t s) {
+  static bool attr = false;
+  if (!attr) {
+    D2D_CUDA(cudaFuncSetAttribute(gru_bwd_tc_kernel<H>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  (int)tcb::Smem<H>::bytes));
+    attr = true;
+  }
+  const int tiles = (a.t1 - a.t0) * ((n->B + tc::kM - 1) / tc::kM);
+  if (tiles <= 0) return D2D_OK;
+  const int gx = std::max(1, std::min(tiles, 148 / n->N));
+  gru_bwd_tc_kernel<H><<<dim3(gx, n->N), tcb::kThreads, tcb::Smem<H>::bytes, s>>>(a);
+  D2D_LAUNCHED();
+  return D2D_OK;
+}
+
 static int launch_gate(const GateArgs& a, int N, bool bwd, cudaStream_t s) {
   const long long n = (long long)(a.t1 - a.t0) * a.H * a.B;
   if (n <= 0) return D2D_OK;
@@ -494,7 +516,29 @@ static int backward_chunk(d2d_net* n, const float* params, const float* x, int x
   const View dgi = make_view(c.dgi, 3 * H * NB, -(c0 - halo), N, 3 * H, B);
   const View dgh = make_view(c.gh, 3 * H * NB, -c0, N, 3 * H, B);
   Wt whh{&n->o_whh, &n->o_bhh, nullptr, H, 3 * H};
-  for (int st = L - 1; st >= 0; --st) {
+  const bool fused = gru_bwd_tc_eligible(n);
+  if (fused) {
+    // one kernel walks the whole window backwards (d(h) in registers, d(gh) W_hh on tcgen05); it leaves d(gh) of
+    // step s in the first 3H features of that step's activation block and d(gi) accumulated per observation
+    GruBwdTcArgs ba;
+    memset(&ba, 0, sizeof(ba));
+    ba.acts = make_view(c.acts, 4 * H * NB, -c0, N, 4 * H, B);
+    ba.hs = make_view(c.hs, H * NB, -c0, N, H, B);
+    ba.dh = make_view(dh_cur, H * NB, -c0, N, H, B);
+    ba.dgi = dgi;
+    ba.w = params, ba.w_agent_stride = n->stride;
+    for (int g = 0; g < N; ++g) ba.whh_off[g] = n->o_whh[g];
+    ba.acts_step = (long long)c.Tc * 4 * H * NB, ba.hs_step = (long long)c.Tc * H * NB;
+    ba.L = L, ba.B = B, ba.t0 = c0, ba.t1 = c1;
+    rc = n->H == 32 ? launch_gru_bwd_tc_h<32>(n, ba, s) : launch_gru_bwd_tc_h<64>(n, ba, s);
+    if (rc) return rc;
+    for (int st = L - 1; st >= 0; --st) {
+      const View hprev = make_view(hs_ptr(n, c, true, st - 1 < 0 ? 0 : st - 1), H * NB, -c0, N, H, B);
+      const View dgh_s = make_view(c.acts + (long long)st * c.Tc * 4 * H * NB, 4 * H * NB, -c0, N, 4 * H, B);
+      if ((rc = launch_wgrad(n, dgh_s, hprev, whh, st == 0, grads, c0, c1, s))) return rc;
+    }
+  }
+  for (int st = L - 1; st >= 0 && !fused; --st) {
     const View hprev = make_view(hs_ptr(n, c, true, st - 1 < 0 ? 0 : st - 1), H * NB, -c0, N, H, B);
     GateArgs ga;
     memset(&ga, 0, sizeof(ga));
