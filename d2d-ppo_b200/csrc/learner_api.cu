@@ -182,13 +182,13 @@ static int launch_wgrad(d2d_net* n, const View& dy, const View& x, const Wt& w, 
   }
   if (tc_enabled() && n->B % 8 == 0) {
     // tensor-core path (wgrad_tc.cuh): bf16 x 3 planes on tcgen05, accumulators in TMEM
-    strips = std::max(1, std::min(n->n_strips, 296 / n->N));   // two CTAs per SM
     const size_t smem = tcw::smem_bytes(maxK);
     static bool attr = false;
     if (!attr) {
       D2D_CUDA(cudaFuncSetAttribute(wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
       attr = true;
     }
+    strips = std::max(1, std::min(n->n_strips, 296 / n->N));   // two CTAs per SM
     wgrad_tc_kernel<<<dim3(strips, n->N), tcw::kThreads, smem, s>>>(a);
   } else {
     dim3 grid(strips, n->N);

@@ -37,7 +37,7 @@ __device__ __forceinline__ uint32_t idesc_bf16_m128(int n) {
 }  // namespace tcw
 
 // requires B % 8 == 0, out_dim <= 192, in_dim <= 128
-__global__ void __launch_bounds__(tcw::kThreads) wgrad_tc_kernel(const WgradArgs a) {
+__global__ void __launch_bounds__(tcw::kThreads, 2) wgrad_tc_kernel(const WgradArgs a) {
   using tc::canon16; using tc::desc16; using tc::mbar_arrive; using tc::mbar_init; using tc::mbar_wait;
   using tc::mma_bf16; using tc::pack_hi; using tc::smem_u32; using tc::split3_trunc; using tc::tmem_ld8;
   using namespace tcw;
@@ -124,40 +124,50 @@ __global__ void __launch_bounds__(tcw::kThreads) wgrad_tc_kernel(const WgradArgs
       const int b0 = (int)(c % chunks_per_t) * kRows;
       __nv_bfloat16* sa = stage_base + st * st_elems;
       __nv_bfloat16* sb = sa + 3 * kAPlane;
-      for (int it = tid; it < n_items; it += kProducers) {
-        const int f = it / (kRows / 8), r8 = (it % (kRows / 8)) * 8;
-        const bool ok = b0 + r8 < a.B;          // B % 8 == 0: a group of 8 rows is all valid or all past the end
-        float v[8];
-        __nv_bfloat16* dst;
-        int plane_stride;
-        if (f < O) {
-          dst = sa + canon16(f, r8, kRows), plane_stride = kAPlane;
-          if (ok) {
-            const float4* p = reinterpret_cast<const float4*>(view_ptr(a.dy, g, t, a.B, b0 + r8) + (long long)f * a.B);
-            const float4 v0 = p[0], v1 = p[1];
-            v[0] = v0.x, v[1] = v0.y, v[2] = v0.z, v[3] = v0.w, v[4] = v1.x, v[5] = v1.y, v[6] = v1.z, v[7] = v1.w;
-          }
-        } else {
-          const int k = f - O;
-          dst = sb + canon16(k, r8, kRows), plane_stride = NB * kRows;
-          if (ok && k < K) {
-            const float4* p = reinterpret_cast<const float4*>(view_ptr(a.x, g, t, a.B, b0 + r8) + (long long)k * a.B);
-            const float4 v0 = p[0], v1 = p[1];
-            v[0] = v0.x, v[1] = v0.y, v[2] = v0.z, v[3] = v0.w, v[4] = v1.x, v[5] = v1.y, v[6] = v1.z, v[7] = v1.w;
-          } else {
+      // every thread owns up to kItems (feature, 8-row group) items of the chunk; all of their loads are issued before
+      // the first use, so a producer keeps kItems x 32 bytes in flight instead of one item's
+      constexpr int kItems = 4;                // typical chunk: (192 + 64 + 1) features x 4 groups / 256 threads = 4.02
+      for (int base = 0; base < n_items; base += kItems * kProducers) {
+      float4 lo[kItems], hi[kItems];
 #pragma unroll
-            for (int j = 0; j < 8; ++j) v[j] = 1.0f;   // the ones row: db = sum of dy
+      for (int q = 0; q < kItems; ++q) {
+        const int it = base + tid + q * kProducers;
+        lo[q] = hi[q] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (it < n_items) {
+          const int f = it / (kRows / 8), r8 = (it % (kRows / 8)) * 8;
+          const bool ok = b0 + r8 < a.B;        // B % 8 == 0: a group of 8 rows is all valid or all past the end
+          const float* src = nullptr;
+          if (ok && f < O) src = view_ptr(a.dy, g, t, a.B, b0 + r8) + (long long)f * a.B;
+          else if (ok && f - O < K) src = view_ptr(a.x, g, t, a.B, b0 + r8) + (long long)(f - O) * a.B;
+          if (src) {
+            lo[q] = __ldg(reinterpret_cast<const float4*>(src));
+            hi[q] = __ldg(reinterpret_cast<const float4*>(src) + 1);
+          } else if (ok && f - O == K) {
+            lo[q] = hi[q] = make_float4(1.f, 1.f, 1.f, 1.f);   // the ones row: db = sum of dy
           }
         }
-        uint32_t q0[8], q1[8], q2[8];
+      }
 #pragma unroll
-        for (int j = 0; j < 8; ++j) split3_trunc(ok ? v[j] : 0.f, q0[j], q1[j], q2[j]);
-        *reinterpret_cast<uint4*>(dst) =
-            make_uint4(pack_hi(q0[0], q0[1]), pack_hi(q0[2], q0[3]), pack_hi(q0[4], q0[5]), pack_hi(q0[6], q0[7]));
-        *reinterpret_cast<uint4*>(dst + plane_stride) =
-            make_uint4(pack_hi(q1[0], q1[1]), pack_hi(q1[2], q1[3]), pack_hi(q1[4], q1[5]), pack_hi(q1[6], q1[7]));
-        *reinterpret_cast<uint4*>(dst + 2 * plane_stride) =
-            make_uint4(pack_hi(q2[0], q2[1]), pack_hi(q2[2], q2[3]), pack_hi(q2[4], q2[5]), pack_hi(q2[6], q2[7]));
+      for (int q = 0; q < kItems; ++q) {
+        const int it = base + tid + q * kProducers;
+        if (it < n_items) {
+          const int f = it / (kRows / 8), r8 = (it % (kRows / 8)) * 8;
+          __nv_bfloat16* dst;
+          int plane_stride;
+          if (f < O) dst = sa + canon16(f, r8, kRows), plane_stride = kAPlane;
+          else dst = sb + canon16(f - O, r8, kRows), plane_stride = NB * kRows;
+          const float v[8] = {lo[q].x, lo[q].y, lo[q].z, lo[q].w, hi[q].x, hi[q].y, hi[q].z, hi[q].w};
+          uint32_t q0[8], q1[8], q2[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) split3_trunc(v[j], q0[j], q1[j], q2[j]);
+          *reinterpret_cast<uint4*>(dst) =
+              make_uint4(pack_hi(q0[0], q0[1]), pack_hi(q0[2], q0[3]), pack_hi(q0[4], q0[5]), pack_hi(q0[6], q0[7]));
+          *reinterpret_cast<uint4*>(dst + plane_stride) =
+              make_uint4(pack_hi(q1[0], q1[1]), pack_hi(q1[2], q1[3]), pack_hi(q1[4], q1[5]), pack_hi(q1[6], q1[7]));
+          *reinterpret_cast<uint4*>(dst + 2 * plane_stride) =
+              make_uint4(pack_hi(q2[0], q2[1]), pack_hi(q2[2], q2[3]), pack_hi(q2[4], q2[5]), pack_hi(q2[6], q2[7]));
+        }
+      }
       }
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
       mbar_arrive(&full[st]);
