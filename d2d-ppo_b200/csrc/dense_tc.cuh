@@ -163,12 +163,43 @@ __global__ void __launch_bounds__(tcd::kThreads, 1) dense_tc_kernel(const DenseA
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         mbar_arrive(&a_ready[slot]);
       }
+      float* yp = view_ptr(a.y, g, t, a.B, ok ? b : 0);
+      const float* ap = a.epilogue == kEpiReluBwd ? view_ptr(a.aux, g, t, a.B, ok ? b : 0) : nullptr;
+      // the epilogue's second operand (ReLU mask / accumulation target) is requested before the wait for the MMAs
+      constexpr int kPre = 64;
+      const bool pre_ok = NP <= kPre && (a.epilogue == kEpiReluBwd || a.epilogue == kEpiAccum);
+      float pre[kPre];
+      if (pre_ok) {
+        const float* src = a.epilogue == kEpiReluBwd ? ap : yp;
+#pragma unroll
+        for (int o = 0; o < kPre; ++o) pre[o] = (ok && o < out_dim) ? src[(long long)o * a.B] : 0.f;
+      }
       mbar_wait(&d_ready[slot], ph);
       ph ^= 1u;
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       const uint32_t d = tmem + (uint32_t)(slot * NP) + lane_addr;
-      float* yp = view_ptr(a.y, g, t, a.B, ok ? b : 0);
-      const float* ap = a.epilogue == kEpiReluBwd ? view_ptr(a.aux, g, t, a.B, ok ? b : 0) : nullptr;
+      if (pre_ok) {
+#pragma unroll
+        for (int c0 = 0; c0 < kPre; c0 += 8) {
+          if (c0 < NP) {
+            float v[8];
+            tmem_ld8(d + c0, v);
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+            if (ok) {
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {
+                const int o = c0 + j;
+                if (o < out_dim) {
+                  float r = v[j] + bias[o];
+                  if (a.epilogue == kEpiAccum) r += pre[o];
+                  else r = pre[o] > 0.f ? r : 0.f;
+                  yp[(long long)o * a.B] = r;
+                }
+              }
+            }
+          }
+        }
+      } else
       for (int c0 = 0; c0 < NP; c0 += 8) {
         float v[8];
         tmem_ld8(d + c0, v);

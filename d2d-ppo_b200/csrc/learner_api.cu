@@ -283,7 +283,7 @@ static bool gru_bwd_tc_eligible(const d2d_net* n) {
 }
 
 template <int H>
-static int launch_gru_bwd_tc_h(const d2d_net* n, const GruBwdTcArgs& a, cudaStream_t s) {
+static int launch_gru_bwd_tc_h(const d2d_net* n, const GruBwdTcArgs& a, cudaStream_t s, int* strips) {
   static bool attr = false;
   if (!attr) {
     D2D_CUDA(cudaFuncSetAttribute(gru_bwd_tc_kernel<H>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -292,9 +292,10 @@ static int launch_gru_bwd_tc_h(const d2d_net* n, const GruBwdTcArgs& a, cudaStre
   }
   const int tiles = (a.t1 - a.t0) * ((n->B + tc::kM - 1) / tc::kM);
   if (tiles <= 0) return D2D_OK;
-  const int gx = std::max(1, std::min(tiles, 148 / n->N));
+  const int gx = std::max(1, std::min(std::min(tiles, 148 / n->N), n->n_strips));
   gru_bwd_tc_kernel<H><<<dim3(gx, n->N), tcb::kThreads, tcb::Smem<H>::bytes, s>>>(a);
   D2D_LAUNCHED();
+  *strips = gx;
   return D2D_OK;
 }
 
@@ -530,12 +531,19 @@ static int backward_chunk(d2d_net* n, const float* params, const float* x, int x
     for (int g = 0; g < N; ++g) ba.whh_off[g] = n->o_whh[g];
     ba.acts_step = (long long)c.Tc * 4 * H * NB, ba.hs_step = (long long)c.Tc * H * NB;
     ba.L = L, ba.B = B, ba.t0 = c0, ba.t1 = c1;
-    rc = n->H == 32 ? launch_gru_bwd_tc_h<32>(n, ba, s) : launch_gru_bwd_tc_h<64>(n, ba, s);
+    ba.partial = n->partial, ba.part_stride = n->part_stride;
+    int strips = 0;
+    rc = n->H == 32 ? launch_gru_bwd_tc_h<32>(n, ba, s, &strips) : launch_gru_bwd_tc_h<64>(n, ba, s, &strips);
     if (rc) return rc;
-    for (int st = L - 1; st >= 0; --st) {
-      const View hprev = make_view(hs_ptr(n, c, true, st - 1 < 0 ? 0 : st - 1), H * NB, -c0, N, H, B);
-      const View dgh_s = make_view(c.acts + (long long)st * c.Tc * 4 * H * NB, 4 * H * NB, -c0, N, 4 * H, B);
-      if ((rc = launch_wgrad(n, dgh_s, hprev, whh, st == 0, grads, c0, c1, s))) return rc;
+    if (strips > 0) {   // dW_hh / db_hh: fixed-order sum of the per-CTA partials
+      WreduceArgs r;
+      memset(&r, 0, sizeof(r));
+      r.partial = n->partial, r.part_stride = n->part_stride, r.n_strips = strips, r.grads = grads;
+      r.g_agent_stride = n->stride, r.out_dim = 3 * H, r.with_bias = 1;
+      for (int g = 0; g < N; ++g) r.w_off[g] = n->o_whh[g], r.b_off[g] = n->o_bhh[g], r.in_dim[g] = H;
+      const int total = 3 * H * H + 3 * H;
+      wreduce_kernel<<<dim3((total + 255) / 256, N), 256, 0, s>>>(r);
+      D2D_LAUNCHED();
     }
   }
   for (int st = L - 1; st >= 0 && !fused; --st) {

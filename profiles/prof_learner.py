@@ -24,7 +24,9 @@ e0, e1, e2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
 e0.record()
 agent.create_rollouts(B)
 e1.record()
+torch.cuda.profiler.start()       # ncu --profile-from-start off: capture the update epoch only
 agent.update_epoch()
+torch.cuda.profiler.stop()
 e2.record()
 torch.cuda.synchronize()
 print(f"B={B} T={T} rollout {e0.elapsed_time(e1):.2f} ms  epoch {e1.elapsed_time(e2):.2f} ms")
