@@ -13,14 +13,16 @@
 // on a K = 64 GEMM incl. the tensor core's own accumulation).  Observations are small integers (exact in bf16), so
 // the input projection needs only x(1 plane) x W_ih(3 planes).
 //
-// CTA = 17 warps.  Two 128-row tiles ("slots") are in flight per CTA so that the tensor pipe works on one slot while
-// the other slot's gates are evaluated:
+// CTA = 16 warps (512 threads: 128 registers each; a 17th warp would be charged as four and leave 96, which spills
+// the prefetched observations in store mode).  Two 128-row tiles ("slots") are in flight per CTA so that the tensor
+// pipe works on one slot while the other slot's gates are evaluated:
 //   warps 0-7  : slot 0; warp w serves TMEM lane quadrant w % 4 (rows 32 (w % 4) + lane) and the hidden units of
 //                half (w / 4) % 2: stage x, read gate pre-activations with tcgen05.ld, gate maths, write h
 //                (3 bf16 planes) + next x into the canonical K-major smem layout
 //   warps 8-15 : the same for slot 1
-//   warp  16   : one elected lane issues tcgen05.mma (x W_ih^T into TMEM columns [0, 3H), h W_hh^T accumulated
-//                into [0, 2H) for r, z and into [3H, 4H) for the n gate, which needs gi_n and gh_n separately)
+//   the first thread of each slot also issues that slot's tcgen05.mma batch once the slot's operands are in place
+//                (x W_ih^T into TMEM columns [0, 3H), h W_hh^T accumulated into [0, 2H) for r, z and into
+//                [3H, 4H) for the n gate, which needs gi_n and gh_n separately)
 // Hand-offs are mbarriers: a_ready[slot] (256 arrivals: operands staged) and d_ready[slot] (tcgen05.commit).
 // The kernel is bound by the gate maths (6 MUFU per (row, unit, step)), not by the tensor pipe: sigmoid / tanh use
 // ex2.approx + rcp.approx (rel. error ~2^-21), the bf16 planes are cut by integer masking instead of F2F.
@@ -53,7 +55,7 @@ namespace tc {
 
 constexpr int kM = 128;       // rows per slot
 constexpr int kKx = 32;       // padded input size (I <= 32)
-constexpr int kThreads = 544;
+constexpr int kThreads = 512;
 constexpr int kGateThreads = 256;   // per slot
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -198,7 +200,7 @@ __global__ void __launch_bounds__(tc::kThreads, 1) gru_window_tc_kernel(const Gr
     mbar_init(&d_ready[0], 1), mbar_init(&d_ready[1], 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == 16) {
+  if (warp == 0) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(tmem_slot)));
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
   }
@@ -212,57 +214,7 @@ __global__ void __launch_bounds__(tc::kThreads, 1) gru_window_tc_kernel(const Gr
   const int pairs_per_t = (a.B + 2 * kM - 1) / (2 * kM);
   const int n_pairs = (a.t1 - a.t0) * pairs_per_t;
 
-  if (warp == 16) {
-    // =================== MMA issuer ===================
-    if (lane == 0) {
-      uint32_t ph[2] = {0, 0};
-      const uint32_t id3 = idesc_bf16(3 * H), id2 = idesc_bf16(2 * H), id1 = idesc_bf16(H);
-      const uint32_t sbo_h = (H >> 3) * 128;   // bytes between 8-row groups of a [.][H] tile
-      for (int p = blockIdx.x; p < n_pairs; p += gridDim.x) {
-        const int t = a.t0 + p / pairs_per_t;
-        const int s0 = a.padded ? 0 : max(0, L - 1 - t);
-        for (int s = s0; s < L; ++s) {
-          for (int slot = 0; slot < 2; ++slot) {
-            mbar_wait(&a_ready[slot], ph[slot]);
-            ph[slot] ^= 1u;
-            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            const uint32_t d = tmem + (uint32_t)slot * (4 * H);
-            const uint32_t ax_addr = smem_u32(ax + slot * S::kAx);
-            // input projection: x (exact in bf16) against the three planes of W_ih -> columns [0, 3H)
-#pragma unroll
-            for (int j = 0; j < 3; ++j)
-#pragma unroll
-              for (int k16 = 0; k16 < kKx / 16; ++k16)
-                mma_bf16(d, desc16(ax_addr + k16 * 256, kKx), desc16(smem_u32(wih + j * S::kWih) + k16 * 256, kKx), id3,
-                         !(j == 0 && k16 == 0));
-            if (s > s0) {
-              // hidden projection, plane pairs (i, j) with i + j <= 2: r, z accumulate onto the input projection,
-              // the n gate gets its own columns [3H, 4H)
-              bool first = true;
-#pragma unroll
-              for (int i = 0; i < 3; ++i)
-#pragma unroll
-                for (int j = 0; j < 3; ++j) {
-                  if (i + j > 2) continue;
-                  const uint32_t ah_addr = smem_u32(ah + (slot * 3 + i) * S::kAh);
-                  const uint32_t wb = smem_u32(whh + j * S::kWhh);
-#pragma unroll
-                  for (int k16 = 0; k16 < H / 16; ++k16) {
-                    const uint64_t ad = desc16(ah_addr + k16 * 256, H);
-                    mma_bf16(d, ad, desc16(wb + k16 * 256, H), id2, true);
-                    mma_bf16(d + 3 * H, ad, desc16(wb + (2 * H / 8) * sbo_h + k16 * 256, H), id1, !first);
-                    first = false;
-                  }
-                }
-            }
-            asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];"
-                         ::"r"(smem_u32(&d_ready[slot]))
-                         : "memory");
-          }
-        }
-      }
-    }
-  } else {
+  {
     // =================== gate warps: slot = warp / 8, lane quadrant = warp % 4, unit half = (warp / 4) % 2 ====
     constexpr int HH = H / 2;          // hidden units per thread
     constexpr int KH = kKx / 2;        // input features staged per thread
@@ -273,8 +225,49 @@ __global__ void __launch_bounds__(tc::kThreads, 1) gru_window_tc_kernel(const Gr
     __nv_bfloat16* my_ax = ax + slot * S::kAx;
     __nv_bfloat16* my_ah = ah + slot * 3 * S::kAh;
     const int u0 = half * HH;
-    uint32_t ph = 0;
+    uint32_t ph = 0, ph_a = 0;
     float h[HH];
+    const bool issuer = (tid & (kGateThreads - 1)) == 0;
+    const uint32_t id3 = idesc_bf16(3 * H), id2 = idesc_bf16(2 * H), id1 = idesc_bf16(H);
+    const uint32_t sbo_h = (H >> 3) * 128;   // bytes between 8-row groups of a [.][H] tile
+    // the slot's MMA batch for the step whose operands were just published (first_step: h = 0, input projection only)
+    auto issue = [&](bool first_step) {
+      mbar_wait(&a_ready[slot], ph_a);
+      ph_a ^= 1u;
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      const uint32_t d = tmem + (uint32_t)slot * (4 * H);
+      const uint32_t ax_addr = smem_u32(ax + slot * S::kAx);
+      // input projection: x (exact in bf16) against the three planes of W_ih -> columns [0, 3H)
+#pragma unroll
+      for (int j = 0; j < 3; ++j)
+#pragma unroll
+        for (int k16 = 0; k16 < kKx / 16; ++k16)
+          mma_bf16(d, desc16(ax_addr + k16 * 256, kKx), desc16(smem_u32(wih + j * S::kWih) + k16 * 256, kKx), id3,
+                   !(j == 0 && k16 == 0));
+      if (!first_step) {
+        // hidden projection, plane pairs (i, j) with i + j <= 2: r, z accumulate onto the input projection,
+        // the n gate gets its own columns [3H, 4H)
+        bool first = true;
+#pragma unroll
+        for (int i = 0; i < 3; ++i)
+#pragma unroll
+          for (int j = 0; j < 3; ++j) {
+            if (i + j > 2) continue;
+            const uint32_t ah_addr = smem_u32(ah + (slot * 3 + i) * S::kAh);
+            const uint32_t wb = smem_u32(whh + j * S::kWhh);
+#pragma unroll
+            for (int k16 = 0; k16 < H / 16; ++k16) {
+              const uint64_t ad = desc16(ah_addr + k16 * 256, H);
+              mma_bf16(d, ad, desc16(wb + k16 * 256, H), id2, true);
+              mma_bf16(d + 3 * H, ad, desc16(wb + (2 * H / 8) * sbo_h + k16 * 256, H), id1, !first);
+              first = false;
+            }
+          }
+      }
+      asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];"
+                   ::"r"(smem_u32(&d_ready[slot]))
+                   : "memory");
+    };
 
     auto load_x = [&](int t_obs, int b, float* xr) {   // this thread's half of the row's observation -> registers
       const bool ok = b < a.B;
@@ -310,6 +303,8 @@ __global__ void __launch_bounds__(tc::kThreads, 1) gru_window_tc_kernel(const Gr
       load_x(t - (L - 1 - s0), b, xr);
       stage_x(xr);
       publish();
+      if (issuer) issue(true);
+      __syncwarp();
 #pragma unroll
       for (int u = 0; u < HH; ++u) h[u] = 0.f;
       for (int s = s0; s < L; ++s) {
@@ -375,6 +370,8 @@ __global__ void __launch_bounds__(tc::kThreads, 1) gru_window_tc_kernel(const Gr
         if (has_next) {
           stage_x(xr);
           publish();
+          if (issuer) issue(false);
+          __syncwarp();
         } else {
           // TMEM reads of this tile are complete before the next tile's first MMA: its publish() fences them
           if (b < a.B && !a.store) {
@@ -388,7 +385,7 @@ __global__ void __launch_bounds__(tc::kThreads, 1) gru_window_tc_kernel(const Gr
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
-  if (warp == 16) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem));
+  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem));
 }
 
 }  // namespace d2d
