@@ -15,7 +15,10 @@
 // written until the CTA stores its partial dW_hh / db_hh at the end (summed over CTAs by wreduce_kernel).
 //
 // CTA = 16 warps on ONE 128-row tile (512 threads leave 128 registers each): warp w serves TMEM lane quadrant w % 4
-// (row = 32 (w % 4) + lane) and the hidden units of quarter w / 4; thread 0 also issues the MMAs.
+// (row = 32 (w % 4) + lane) and the hidden units of quarter w / 4.  Lane 0 of EVERY warp issues a share of the step's
+// 140 MMAs: a single issuing thread needs ~18 instructions per tcgen05.mma and was the critical path (5 of 11 us per
+// tile-step).  Concurrent issue needs order-free accumulation: D is pre-loaded with the direct path dh z through
+// tcgen05.st and the dW accumulators are zeroed once, so every MMA accumulates.
 // Per step the threads write two operand tiles in the canonical no-swizzle layout (16-byte vectors, thread = row):
 //   G = d(gh)   [128 rows][3H]   2 bf16 planes (hi + lo, round to nearest: 16 significant bits, unbiased)
 //   P = h_prev  [128 rows][H]    3 bf16 planes (+ a constant ones column in plane 0 for the bias gradient)
@@ -64,6 +67,13 @@ __device__ __forceinline__ uint64_t desc_mn(uint32_t saddr, uint32_t k_stride, u
   return start | (lbo << 16) | (sbo << 32) | (1ull << 46);
 }
 // D = F32, A = B = BF16, M = 128; bit 15 / 16: A / B are MN-major
+__device__ __forceinline__ void tmem_st8(uint32_t taddr, const float* v) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
+               ::"r"(taddr), "r"(__float_as_uint(v[0])), "r"(__float_as_uint(v[1])), "r"(__float_as_uint(v[2])),
+                 "r"(__float_as_uint(v[3])), "r"(__float_as_uint(v[4])), "r"(__float_as_uint(v[5])),
+                 "r"(__float_as_uint(v[6])), "r"(__float_as_uint(v[7]))
+               : "memory");
+}
 __device__ __forceinline__ uint32_t idesc_bf16_mn(int n) {
   return (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(n >> 3) << 17) |
          ((uint32_t)(tc::kM >> 4) << 24);
@@ -105,7 +115,7 @@ __global__ void __launch_bounds__(tcb::kThreads, 1) gru_bwd_tc_kernel(const GruB
     sp0[canon16(r, H + c, NP0)] = __float2bfloat16_rn(c == 0 ? 1.0f : 0.0f);
   }
   if (tid == 0) {
-    mbar_init(a_ready, tcb::kThreads), mbar_init(d_ready, 1), mbar_init(w_done, 1);
+    mbar_init(a_ready, tcb::kThreads), mbar_init(d_ready, tcb::kThreads / 32), mbar_init(w_done, tcb::kThreads / 32);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   constexpr uint32_t kColsUsed = H + NBLK * NP0;
@@ -121,6 +131,14 @@ __global__ void __launch_bounds__(tcb::kThreads, 1) gru_bwd_tc_kernel(const GruB
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem = *tmem_slot;
   const uint32_t tmem_dw = tmem + H;     // weight-gradient accumulators: block blk at columns blk * NP0
+  if (warp < 4) {                        // zero the weight-gradient accumulators once: every MMA accumulates
+    const float zero[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    for (int c0 = 0; c0 < NBLK * NP0; c0 += 8) tcb::tmem_st8(tmem_dw + ((uint32_t)(warp * 32) << 16) + (uint32_t)c0, zero);
+    asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 
   const int L = a.L;
   const int n_t = a.t1 - a.t0;
@@ -134,7 +152,6 @@ __global__ void __launch_bounds__(tcb::kThreads, 1) gru_bwd_tc_kernel(const GruB
   const long long HB = (long long)H * a.B;
   uint32_t ph_d = 0, ph_a = 0, ph_w = 0;
   bool staged_before = false;           // a weight-gradient batch is (or was) in flight on the operand tiles
-  bool dw_started = false;              // thread 0: the accumulators hold data (the very first MMA must not accumulate)
   const uint32_t id_d = idesc_bf16(H);
   const uint32_t id_w0 = tcb::idesc_bf16_mn(NP0), id_w = tcb::idesc_bf16_mn(H);
 
@@ -186,12 +203,13 @@ __global__ void __launch_bounds__(tcb::kThreads, 1) gru_bwd_tc_kernel(const GruB
           const float dz = d * (hp[u] - nn[u]) * z[u] * (1.0f - z[u]);
           const float dr = dn * ghn[u] * r[u] * (1.0f - r[u]);
           dg[0][j] = dr, dg[1][j] = dz, dg[2][j] = dn * r[u];
-          dh[u] = d * z[u];                  // direct path; d(gh) W_hh is added once the MMA is done
+          dh[u] = d * z[u];                  // direct path: pre-loaded into D, d(gh) W_hh accumulates on top
           if (ok) {
             const long long f = (long long)u * a.B;
             atomicAdd(gp + f, dr), atomicAdd(gp + f + HB, dz), atomicAdd(gp + f + 2 * HB, dn);
           }
         }
+        if (s > 0) tcb::tmem_st8(tmem + lane_addr + (uint32_t)(u0 + c * 8), &dh[c * 8]);
 #pragma unroll
         for (int gate = 0; gate < 3; ++gate) {
           uint32_t w0[4], w1[4];
@@ -219,26 +237,25 @@ __global__ void __launch_bounds__(tcb::kThreads, 1) gru_bwd_tc_kernel(const GruB
               make_uint4(pack_hi(q2[0], q2[1]), pack_hi(q2[2], q2[3]), pack_hi(q2[4], q2[5]), pack_hi(q2[6], q2[7]));
         }
       }
+      if (s > 0) asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
       mbar_arrive(a_ready);
-      if (tid == 0) {
+      if (lane == 0) {
         mbar_wait(a_ready, ph_a);
         ph_a ^= 1u;
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        constexpr int kWarps = tcb::kThreads / 32;
         const uint32_t g_addr[2] = {smem_u32(sg), smem_u32(sg + S::kG)};
         if (s > 0) {
-          // D = d(gh) W_hh : G K-major x W_hh^T K-major, five plane products, 3H / 16 reduction steps each
-          bool first = true;
-#pragma unroll
-          for (int pr = 0; pr < 5; ++pr) {
+          // D += d(gh) W_hh : G K-major x W_hh^T K-major, five plane products x 3H / 16 reduction steps, dealt round
+          // robin to the warps' issuing lanes
+          constexpr int kPer = K3 / 16;
+          for (int m = warp; m < 5 * kPer; m += kWarps) {
+            const int pr = m / kPer, k16 = m % kPer;
             const int gi_ = pr < 3 ? 0 : 1, wi = pr < 3 ? pr : pr - 3;
-            const uint32_t wb = smem_u32(sw + wi * S::kW);
-#pragma unroll
-            for (int k16 = 0; k16 < K3 / 16; ++k16) {
-              mma_bf16(tmem, desc16(g_addr[gi_] + k16 * 256, K3), desc16(wb + k16 * 256, K3), id_d, !first);
-              first = false;
-            }
+            mma_bf16(tmem, desc16(g_addr[gi_] + k16 * 256, K3), desc16(smem_u32(sw + wi * S::kW) + k16 * 256, K3),
+                     id_d, true);
           }
           asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];"
                        ::"r"(smem_u32(d_ready))
@@ -246,24 +263,17 @@ __global__ void __launch_bounds__(tcb::kThreads, 1) gru_bwd_tc_kernel(const GruB
         }
         // dW += G^T P : both tiles read along their contiguous dimension, reduction over the 128 rows
         constexpr uint32_t ks_g = (K3 / 8) * 128, ks_p0 = (NP0 / 8) * 128, ks_p = (H / 8) * 128;   // K (row group) strides
-#pragma unroll
-        for (int pr = 0; pr < 5; ++pr) {
+        constexpr int kPerW = (kM / 16) * NBLK;
+        for (int m = warp; m < 5 * kPerW; m += kWarps) {
+          const int pr = m / kPerW, k16 = (m % kPerW) / NBLK, blk = m % NBLK;
           const int gi_ = (pr == 1 || pr == 4) ? 1 : 0;          // (g0 p0) (g1 p0) (g0 p1) (g0 p2) (g1 p1)
           const int pi = pr < 2 ? 0 : (pr == 3 ? 2 : 1);
           const uint32_t pb = pi == 0 ? smem_u32(sp0) : smem_u32(sp1 + (pi - 1) * S::kP);
           const uint32_t ks_b = pi == 0 ? ks_p0 : ks_p;
-          const uint32_t idw = pi == 0 ? id_w0 : id_w;
-#pragma unroll
-          for (int k16 = 0; k16 < kM / 16; ++k16) {
-            const uint64_t bd = tcb::desc_mn(pb + k16 * 2 * ks_b, ks_b, 128);
-#pragma unroll
-            for (int blk = 0; blk < NBLK; ++blk)
-              mma_bf16(tmem_dw + (uint32_t)(blk * NP0),
-                       tcb::desc_mn(g_addr[gi_] + blk * 16 * 128 + k16 * 2 * ks_g, ks_g, 128), bd, idw,
-                       dw_started || pr > 0 || k16 > 0);
-          }
+          mma_bf16(tmem_dw + (uint32_t)(blk * NP0),
+                   tcb::desc_mn(g_addr[gi_] + blk * 16 * 128 + k16 * 2 * ks_g, ks_g, 128),
+                   tcb::desc_mn(pb + k16 * 2 * ks_b, ks_b, 128), pi == 0 ? id_w0 : id_w, true);
         }
-        dw_started = true;
         asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];"
                      ::"r"(smem_u32(w_done))
                      : "memory");
@@ -280,7 +290,7 @@ __global__ void __launch_bounds__(tcb::kThreads, 1) gru_bwd_tc_kernel(const GruB
         tmem_ld8(tmem + lane_addr + (uint32_t)(u0 + c * 8), v);
         asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
-        for (int j = 0; j < 8; ++j) dh[c * 8 + j] += v[j];
+        for (int j = 0; j < 8; ++j) dh[c * 8 + j] = v[j];      // dh z + d(gh) W_hh
       }
     }
   }
