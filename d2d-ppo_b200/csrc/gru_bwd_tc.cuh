@@ -154,6 +154,11 @@ __global__ void __launch_bounds__(tcb::kThreads, 1) gru_bwd_tc_kernel(const GruB
   bool staged_before = false;           // a weight-gradient batch is (or was) in flight on the operand tiles
   const uint32_t id_d = idesc_bf16(H);
   const uint32_t id_w0 = tcb::idesc_bf16_mn(NP0), id_w = tcb::idesc_bf16_mn(H);
+  // base descriptors, built once (desc_adv moves the start address only)
+  constexpr uint32_t ks_g = (K3 / 8) * 128, ks_p0 = (NP0 / 8) * 128, ks_p = (H / 8) * 128;   // K (row group) strides
+  const uint64_t dg_k = desc16(smem_u32(sg), K3), dw_k = desc16(smem_u32(sw), K3);
+  const uint64_t dg_mn = tcb::desc_mn(smem_u32(sg), ks_g, 128);
+  const uint64_t dp0_mn = tcb::desc_mn(smem_u32(sp0), ks_p0, 128), dp1_mn = tcb::desc_mn(smem_u32(sp1), ks_p, 128);
 
   for (int p = blockIdx.x; p < n_tiles; p += gridDim.x) {
     const int t = a.t0 + p % n_t;
@@ -246,7 +251,6 @@ __global__ void __launch_bounds__(tcb::kThreads, 1) gru_bwd_tc_kernel(const GruB
         ph_a ^= 1u;
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         constexpr int kWarps = tcb::kThreads / 32;
-        const uint32_t g_addr[2] = {smem_u32(sg), smem_u32(sg + S::kG)};
         if (s > 0) {
           // D += d(gh) W_hh : G K-major x W_hh^T K-major, five plane products x 3H / 16 reduction steps, dealt round
           // robin to the warps' issuing lanes
@@ -254,25 +258,23 @@ __global__ void __launch_bounds__(tcb::kThreads, 1) gru_bwd_tc_kernel(const GruB
           for (int m = warp; m < 5 * kPer; m += kWarps) {
             const int pr = m / kPer, k16 = m % kPer;
             const int gi_ = pr < 3 ? 0 : 1, wi = pr < 3 ? pr : pr - 3;
-            mma_bf16(tmem, desc16(g_addr[gi_] + k16 * 256, K3), desc16(smem_u32(sw + wi * S::kW) + k16 * 256, K3),
-                     id_d, true);
+            mma_bf16(tmem, desc_adv(dg_k, gi_ * S::kG * 2 + k16 * 256), desc_adv(dw_k, wi * S::kW * 2 + k16 * 256), id_d,
+                     true);
           }
           asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];"
                        ::"r"(smem_u32(d_ready))
                        : "memory");
         }
         // dW += G^T P : both tiles read along their contiguous dimension, reduction over the 128 rows
-        constexpr uint32_t ks_g = (K3 / 8) * 128, ks_p0 = (NP0 / 8) * 128, ks_p = (H / 8) * 128;   // K (row group) strides
         constexpr int kPerW = (kM / 16) * NBLK;
         for (int m = warp; m < 5 * kPerW; m += kWarps) {
           const int pr = m / kPerW, k16 = (m % kPerW) / NBLK, blk = m % NBLK;
           const int gi_ = (pr == 1 || pr == 4) ? 1 : 0;          // (g0 p0) (g1 p0) (g0 p1) (g0 p2) (g1 p1)
           const int pi = pr < 2 ? 0 : (pr == 3 ? 2 : 1);
-          const uint32_t pb = pi == 0 ? smem_u32(sp0) : smem_u32(sp1 + (pi - 1) * S::kP);
-          const uint32_t ks_b = pi == 0 ? ks_p0 : ks_p;
-          mma_bf16(tmem_dw + (uint32_t)(blk * NP0),
-                   tcb::desc_mn(g_addr[gi_] + blk * 16 * 128 + k16 * 2 * ks_g, ks_g, 128),
-                   tcb::desc_mn(pb + k16 * 2 * ks_b, ks_b, 128), pi == 0 ? id_w0 : id_w, true);
+          const uint64_t pd = pi == 0 ? desc_adv(dp0_mn, k16 * 2 * ks_p0)
+                                      : desc_adv(dp1_mn, (pi - 1) * S::kP * 2 + k16 * 2 * ks_p);
+          mma_bf16(tmem_dw + (uint32_t)(blk * NP0), desc_adv(dg_mn, gi_ * S::kG * 2 + blk * 16 * 128 + k16 * 2 * ks_g),
+                   pd, pi == 0 ? id_w0 : id_w, true);
         }
         asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];"
                      ::"r"(smem_u32(w_done))

@@ -70,6 +70,11 @@ __device__ __forceinline__ uint64_t desc16(uint32_t saddr, int kc) {
   const uint64_t lbo = 128 >> 4, sbo = (uint64_t)((kc >> 3) * 128) >> 4;
   return start | (lbo << 16) | (sbo << 32) | (1ull << 46);   // version 1 (Blackwell), no swizzle, base offset 0
 }
+// descriptor of the tile `byte_off` bytes further (same strides): one 32-bit add on the start-address field instead of
+// rebuilding the descriptor; the single issuing thread is latency bound on exactly this arithmetic
+__device__ __forceinline__ uint64_t desc_adv(uint64_t base, uint32_t byte_off) {
+  return (base & 0xFFFFFFFF00000000ull) | (uint64_t)((uint32_t)base + (byte_off >> 4));
+}
 // instruction descriptor: D = F32, A = B = BF16, both K-major, M = 128
 __device__ __forceinline__ uint32_t idesc_bf16(int n) {
   return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(kM >> 4) << 24);
@@ -230,19 +235,21 @@ __global__ void __launch_bounds__(tc::kThreads, 1) gru_window_tc_kernel(const Gr
     const bool issuer = (tid & (kGateThreads - 1)) == 0;
     const uint32_t id3 = idesc_bf16(3 * H), id2 = idesc_bf16(2 * H), id1 = idesc_bf16(H);
     const uint32_t sbo_h = (H >> 3) * 128;   // bytes between 8-row groups of a [.][H] tile
+    // base descriptors of the slot's operand tiles, built once
+    const uint32_t d_slot = tmem + (uint32_t)slot * (4 * H);
+    const uint64_t dx = desc16(smem_u32(ax + slot * S::kAx), kKx), dwih = desc16(smem_u32(wih), kKx);
+    const uint64_t dah = desc16(smem_u32(ah + slot * 3 * S::kAh), H), dwhh = desc16(smem_u32(whh), H);
     // the slot's MMA batch for the step whose operands were just published (first_step: h = 0, input projection only)
     auto issue = [&](bool first_step) {
       mbar_wait(&a_ready[slot], ph_a);
       ph_a ^= 1u;
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      const uint32_t d = tmem + (uint32_t)slot * (4 * H);
-      const uint32_t ax_addr = smem_u32(ax + slot * S::kAx);
       // input projection: x (exact in bf16) against the three planes of W_ih -> columns [0, 3H)
 #pragma unroll
       for (int j = 0; j < 3; ++j)
 #pragma unroll
         for (int k16 = 0; k16 < kKx / 16; ++k16)
-          mma_bf16(d, desc16(ax_addr + k16 * 256, kKx), desc16(smem_u32(wih + j * S::kWih) + k16 * 256, kKx), id3,
+          mma_bf16(d_slot, desc_adv(dx, k16 * 256), desc_adv(dwih, (j * S::kWih) * 2 + k16 * 256), id3,
                    !(j == 0 && k16 == 0));
       if (!first_step) {
         // hidden projection, plane pairs (i, j) with i + j <= 2: r, z accumulate onto the input projection,
@@ -253,13 +260,12 @@ __global__ void __launch_bounds__(tc::kThreads, 1) gru_window_tc_kernel(const Gr
 #pragma unroll
           for (int j = 0; j < 3; ++j) {
             if (i + j > 2) continue;
-            const uint32_t ah_addr = smem_u32(ah + (slot * 3 + i) * S::kAh);
-            const uint32_t wb = smem_u32(whh + j * S::kWhh);
 #pragma unroll
             for (int k16 = 0; k16 < H / 16; ++k16) {
-              const uint64_t ad = desc16(ah_addr + k16 * 256, H);
-              mma_bf16(d, ad, desc16(wb + k16 * 256, H), id2, true);
-              mma_bf16(d + 3 * H, ad, desc16(wb + (2 * H / 8) * sbo_h + k16 * 256, H), id1, !first);
+              const uint64_t ad = desc_adv(dah, (i * S::kAh) * 2 + k16 * 256);
+              mma_bf16(d_slot, ad, desc_adv(dwhh, (j * S::kWhh) * 2 + k16 * 256), id2, true);
+              mma_bf16(d_slot + 3 * H, ad, desc_adv(dwhh, (j * S::kWhh) * 2 + (2 * H / 8) * sbo_h + k16 * 256), id1,
+                       !first);
               first = false;
             }
           }
