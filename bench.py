@@ -538,6 +538,24 @@ def run_native(args):
     if os.path.exists(tpath):
         traffic = json.load(open(tpath)).get("dram_bytes_per_launch")
 
+    # context for the write-heavy mix (83 % of the step kernel's DRAM traffic is stores): what plain fill / copy
+    # kernels reach on this GPU right now (torch, 2 GiB buffers, best of 5)
+    def _bw(fn, nbytes):
+        best = 0.0
+        for _ in range(5):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            fn()
+            e1.record()
+            torch.cuda.synchronize()
+            best = max(best, nbytes / (e0.elapsed_time(e1) * 1e-3) / 1e9)
+        return best
+    scratch_a = torch.empty(1 << 30, dtype=torch.uint8, device=dev)
+    scratch_b = torch.empty(1 << 30, dtype=torch.uint8, device=dev)
+    fill_gbs = _bw(lambda: scratch_a.fill_(7), 1 << 30)
+    copy_gbs = _bw(lambda: scratch_b.copy_(scratch_a), 2 << 30)
+    del scratch_a, scratch_b
+
     line = {
         "metric": "agent-steps/sec (env step + random-access policy)", "value": value, "unit": "agent-steps/s",
         "n_gpus": world, "steps": K, "warmup": max(W, 3), "ms_per_step": total_ms / K, "higher_is_better": True,
@@ -546,7 +564,10 @@ def run_native(args):
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "traffic": traffic, "kernel": "comb_step_kernel<4,uint8_t,6>", "kernel_ms": kernel_ms,
                      "alg_bytes_per_agent_step": ALG_BYTES, "agent_steps_per_launch": B * N_AGENTS,
-                     "peak_source": peak_src},
+                     "peak_source": peak_src,
+                     "context": {"torch_fill_gbs": fill_gbs, "torch_copy_gbs": copy_gbs,
+                                 "note": "write-only and copy bandwidth measured in this run (1 GiB torch fill_ / "
+                                         "copy_); the step kernel's traffic is 83 % stores"}},
         "e2e": {"value": e2e_value, "unit": "agent-steps/s",
                 "h2d_bytes_per_step": B * N_AGENTS * N_CHANNELS, "d2h_bytes_per_step": B * 4, "steps": Ke,
                 "api": "CombinatorialEnv.step_host (C ABI d2d_env_step_host): actions u8 [B,N,C] 0/1, the reference's "

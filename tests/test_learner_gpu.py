@@ -299,3 +299,55 @@ def test_d2dppo_chain_gradients(tag, cuda_device):
         opt.step(clipped)
         for k in pol.keys:
             assert torch.allclose(pol.tensor_view(pol.params, i, k).cpu(), opt.p[k], rtol=1e-5, atol=1e-7), (i, k)
+
+
+@pytest.mark.parametrize("H,Lh,E,T,I,C", [(32, 4, 136, 9, 11, 4), (64, 1, 40, 6, 30, 8), (64, 6, 300, 5, 30, 8),
+                                          (48, 3, 64, 7, 20, 8)])
+def test_tensor_core_training_path_vs_autograd(H, Lh, E, T, I, C, cuda_device):
+    """Shapes the fixtures do not reach on the tcgen05 training path (hidden 32 / 48, history 1, several 128-row
+    tiles, ragged last tile): surrogate + MSE gradients against torch autograd on the oracle with random weights."""
+    from d2d_ppo_b200 import _lib as L
+    from d2d_ppo_b200.algorithms._nets import action_dtype, policy_head
+    N = 3
+    gen = torch.Generator().manual_seed(H * 1000 + Lh)
+    obs = torch.randint(-1, 4, (E * T, N, I), generator=gen).float()              # integer observations (exact in bf16)
+    acts = torch.randint(0, 2, (E * T, N, C), generator=gen).float()
+    adv = torch.randn(E * T, N, generator=gen)
+    ret = torch.randn(E * T, N, generator=gen)
+    lead = Lh - 1
+    x = _env_minor(obs.reshape(E * T, N * I).numpy(), E, T, lead, cuda_device)
+    in_dim, in_off = [I] * N, [k * I for k in range(N)]
+    pol = _netset(cuda_device, "gru", "sigmoid", N, E, in_dim, in_off, N * I, H, C, Lh, exact=True)
+    val = _netset(cuda_device, "gru", "identity", N, E, in_dim, in_off, N * I, H, 1, Lh, exact=True)
+    packed = (acts.long() * (1 << torch.arange(C))).sum(-1)
+    actions = packed.reshape(E, T, N).permute(1, 2, 0).contiguous().to(action_dtype(0, C)).to(cuda_device)
+
+    def em(a):
+        return a.reshape(E, T, N).permute(1, 2, 0).contiguous().to(cuda_device)
+    # old log-probs from the padded windows themselves, shifted a little so that ratios differ from 1
+    logits = pol.forward(x, lead, 0, T, padded=1)
+    logp = torch.empty((T, N, E), device=cuda_device)
+    policy_head(logits, N, E, C, L.OUT_SIGMOID, L.DIST_BERNOULLI, L.ACT_GIVEN, actions, logp)
+    logp_old = logp + 0.05 * em(torch.randn(E * T, N, generator=gen))
+    R = E * T
+    sums = torch.zeros((N, 2), dtype=torch.float64, device=cuda_device)
+    pol.zero_grad()
+    pol.policy_grad(x, lead, 0, T, L.DIST_BERNOULLI, actions, logp_old, em(adv), 1, None, 1.0 / R, 0.1, 0.01, sums)
+    vsum = torch.zeros(N, dtype=torch.float64, device=cuda_device)
+    val.zero_grad()
+    val.value_grad(x, lead, 0, T, 1, em(ret), 1, 1.0 / R, vsum)
+    lp_rows = torch.tensor(_rows(logp_old))
+    for i in range(N):
+        pp = {k: v.clone().requires_grad_(True) for k, v in pol.state_dict(i).items()}
+        xi, valid = P.windows(obs[:, i], T, Lh, True)
+        probs = P.net_forward(pp, xi, "sigmoid", valid)
+        loss, _ = P.surrogate(probs, acts[:, i], lp_rows[:, i], adv[:, i], True, 0.1, 0.01)
+        for (name, _), gr in zip(pp.items(), torch.autograd.grad(loss, list(pp.values()))):
+            assert rel_err(pol.tensor_view(pol.grads, i, name), gr) < 2e-5, ("policy", i, name)
+        mine_loss = -(sums[i, 0].item() / R) - 0.01 * sums[i, 1].item() / R
+        assert abs(mine_loss - float(loss.detach())) <= 1e-5 * max(1.0, abs(float(loss.detach())))
+        vp = {k: v.clone().requires_grad_(True) for k, v in val.state_dict(i).items()}
+        vloss = ((P.net_forward(vp, xi, "identity", valid).squeeze(-1) - ret[:, i]) ** 2).mean()
+        for (name, _), gr in zip(vp.items(), torch.autograd.grad(vloss, list(vp.values()))):
+            assert rel_err(val.tensor_view(val.grads, i, name), gr) < 2e-5, ("value", i, name)
+        assert abs(vsum[i].item() / R - float(vloss.detach())) <= 1e-5 * max(1.0, float(vloss.detach()))
