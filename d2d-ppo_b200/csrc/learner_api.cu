@@ -20,6 +20,7 @@
 #include "gru_bwd_tc.cuh"
 #include "wgrad_tc.cuh"
 #include "dense_tc.cuh"
+#include "head_fused.cuh"
 #include "learner_pointwise.cuh"
 
 using namespace d2d;
@@ -277,6 +278,41 @@ static int launch_gru_tc(const d2d_net* n, const float* params, const View& x, c
   }
 }
 
+// fused network head (head_fused.cuh): out = W2 relu(W1 h + b1) + b2; y1 == nullptr: first-layer outputs not kept
+template <int H, int OMAX>
+static void launch_head_fused_t(const HeadFusedArgs& a, int N, int tiles, cudaStream_t s) {
+  const int gx = std::max(1, std::min(tiles, (148 * 2) / N));
+  head_fused_kernel<H, OMAX><<<dim3(gx, N), kHeadThreads, 0, s>>>(a);
+}
+
+static bool head_fused_eligible(const d2d_net* n) {
+  static int disabled = -1;
+  if (disabled < 0) {
+    const char* e = getenv("D2D_DISABLE_FUSED_HEAD");
+    disabled = (e && e[0] == '1') ? 1 : 0;
+  }
+  return !disabled && n->arch == D2D_NET_GRU && (n->H == 32 || n->H == 64) && n->O <= 16;
+}
+
+static int launch_head_fused(const d2d_net* n, const float* params, const View& h, float* y1, const View& out, int t0,
+                             int t1, cudaStream_t s) {
+  HeadFusedArgs a;
+  memset(&a, 0, sizeof(a));
+  const long long NB = (long long)n->N * n->B;
+  a.h = h, a.out = out, a.w = params, a.w_agent_stride = n->stride, a.O = n->O, a.B = n->B, a.t0 = t0, a.t1 = t1;
+  if (y1) a.y1 = make_view(y1, n->H * NB, -t0, n->N, n->H, n->B);
+  for (int g = 0; g < n->N; ++g)
+    a.w1_off[g] = n->o_w1[g], a.b1_off[g] = n->o_b1[g], a.w2_off[g] = n->o_w2[g], a.b2_off[g] = n->o_b2[g];
+  const int tiles = (t1 - t0) * ((n->B + 2 * kHeadThreads - 1) / (2 * kHeadThreads));
+  if (tiles <= 0) return D2D_OK;
+  const int om = n->O <= 1 ? 1 : (n->O <= 8 ? 8 : 16);
+#define HF(H_, O_) if (n->H == H_ && om == O_) launch_head_fused_t<H_, O_>(a, n->N, tiles, s)
+  HF(32, 1); HF(32, 8); HF(32, 16); HF(64, 1); HF(64, 8); HF(64, 16);
+#undef HF
+  D2D_LAUNCHED();
+  return D2D_OK;
+}
+
 // tensor-core fused BPTT through the window (gru_bwd_tc.cuh)
 static bool gru_bwd_tc_eligible(const d2d_net* n) {
   return tc_enabled() && n->arch == D2D_NET_GRU && (n->H == 32 || n->H == 64) && n->L >= 1;
@@ -454,6 +490,7 @@ static int forward_chunk(d2d_net* n, const float* params, const float* x, int x_
     }
     last = make_view(hs_ptr(n, c, train, L - 1), H * NB, -c0, N, H, B);
   }
+  if (head_fused_eligible(n)) return launch_head_fused(n, params, last, train ? c.y1 : nullptr, lg, c0, c1, s);
   {
     DenseArgs a;
     memset(&a, 0, sizeof(a));
@@ -734,6 +771,9 @@ extern "C" int d2d_net_rollout_step(d2d_net* n, const float* params, const float
   }
   const View y1 = make_view(c.y1, H * NB, -t, N, H, B);
   const View lg = make_view(out, O * NB, -t, N, O, B);
+  if (head_fused_eligible(n))
+    return launch_head_fused(n, params, make_view(hs_ptr(n, c, false, L - 1), H * NB, -t, N, H, B), nullptr, lg, t,
+                             t + 1, s);
   Wt w1{&n->o_w1, &n->o_b1, nullptr, H, H};
   Wt w2{&n->o_w2, &n->o_b2, nullptr, H, O};
   {
