@@ -1,0 +1,13 @@
+import sys
+sys.path.insert(0, "/root/repo"); sys.path.insert(0, "/root/repo/tests")
+import torch
+import test_learner_gpu as T
+dev = torch.device("cuda", 0)
+bad = 0
+for rep in range(int(sys.argv[1])):
+    for cfg in [(32, 4, 136, 9, 11, 4), (64, 1, 40, 6, 30, 8), (64, 6, 300, 5, 30, 8), (48, 3, 64, 7, 20, 8)]:
+        try:
+            T.test_tensor_core_training_path_vs_autograd(*cfg, dev)
+        except AssertionError as e:
+            bad += 1; print(rep, cfg, str(e)[:200])
+print("bad", bad)

@@ -309,6 +309,7 @@ def test_tensor_core_training_path_vs_autograd(H, Lh, E, T, I, C, cuda_device):
     from d2d_ppo_b200 import _lib as L
     from d2d_ppo_b200.algorithms._nets import action_dtype, policy_head
     N = 3
+    torch.manual_seed(H * 1000 + Lh + 7)            # NetSet draws its initial weights from the global generator
     gen = torch.Generator().manual_seed(H * 1000 + Lh)
     obs = torch.randint(-1, 4, (E * T, N, I), generator=gen).float()              # integer observations (exact in bf16)
     acts = torch.randint(0, 2, (E * T, N, C), generator=gen).float()
@@ -329,6 +330,11 @@ def test_tensor_core_training_path_vs_autograd(H, Lh, E, T, I, C, cuda_device):
     logp = torch.empty((T, N, E), device=cuda_device)
     policy_head(logits, N, E, C, L.OUT_SIGMOID, L.DIST_BERNOULLI, L.ACT_GIVEN, actions, logp)
     logp_old = logp + 0.05 * em(torch.randn(E * T, N, generator=gen))
+    # the clipped surrogate is not differentiable where the ratio crosses 1 -+ cliprange: a row within rounding noise
+    # of the kink flips its whole gradient contribution between two fp32 implementations, so keep rows away from it
+    ratio = torch.exp(logp - logp_old)
+    near = ((ratio - 0.9).abs() < 2e-3) | ((ratio - 1.1).abs() < 2e-3)
+    logp_old = torch.where(near, logp_old + 0.01, logp_old)
     R = E * T
     sums = torch.zeros((N, 2), dtype=torch.float64, device=cuda_device)
     pol.zero_grad()
