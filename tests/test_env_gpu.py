@@ -212,6 +212,37 @@ def test_host_buffer_step_matches_oracle(layout, cuda_device):
         env.step_host(host_a[0][:1], host_r[0])
 
 
+def test_host_buffer_step_single_channel_env(cuda_device):
+    """step_host on D2DEnv (device action layout u8 [N, B]) against step() on an identically seeded env."""
+    import torch
+    g = load_env_case("d2d_c2")
+    kw = g["config"]
+    B, T = 333, 25
+    a_env = make_cuda_env("d2d", kw, B, rng="philox", seed=9, device=cuda_device)
+    b_env = make_cuda_env("d2d", kw, B, rng="philox", seed=9, device=cuda_device)
+    a_env.reset(), b_env.reset()
+    rng = np.random.default_rng(1)
+    host_r = [torch.empty(B, dtype=torch.int32).pin_memory() for _ in range(2)]
+    pending = None
+    want = []
+    for t in range(T):
+        act = rng.binomial(1, 0.3, (B, kw["n_agents"])).astype(np.uint8)
+        host_a = torch.from_numpy(np.ascontiguousarray(act.T)).pin_memory()
+        tk = a_env.step_host(host_a, host_r[t % 2], layout="device", with_state=True)
+        obs, state, rew, done, _ = b_env.step(act)
+        want.append(to_np(rew)[:, 0].astype(np.int32))
+        assert np.array_equal(to_np(a_env.obs_rows_tensor.t()), cat_obs(obs)) and np.array_equal(
+            to_np(a_env.state_rows_tensor.t()), to_np(state))
+        if pending is not None:
+            a_env.host_wait(pending)
+            assert np.array_equal(host_r[(t - 1) % 2].numpy(), want[t - 1])
+        pending = tk
+    a_env.host_wait(pending)
+    assert np.array_equal(host_r[(T - 1) % 2].numpy(), want[T - 1])
+    with pytest.raises(Exception):
+        a_env.step_host(torch.zeros((B, kw["n_agents"], 1), dtype=torch.uint8).pin_memory(), host_r[0], layout="reference")
+
+
 def test_reference_compatible_single_env_mode(cuda_device):
     """n_envs=None: host numpy outputs with the reference's shapes and dtypes."""
     g = load_env_case("comb_c3_load1_ragged_obs")
