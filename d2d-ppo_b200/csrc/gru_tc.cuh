@@ -20,13 +20,14 @@
 //                half (w / 4) % 2: stage x, read gate pre-activations with tcgen05.ld, gate maths, write h
 //                (3 bf16 planes) + next x into the canonical K-major smem layout
 //   warps 8-15 : the same for slot 1
-//   the first thread of each slot also issues that slot's tcgen05.mma batch once the slot's operands are in place
-//                (x W_ih^T into TMEM columns [0, 3H), h W_hh^T accumulated into [0, 2H) for r, z and into
-//                [3H, 4H) for the n gate, which needs gi_n and gh_n separately)
+//   the first thread of each slot also issues that slot's tcgen05.mma batch once the slot's operands are in place:
+//                TMEM columns [0, H) r, [H, 2H) z, [2H, 3H) gh_n, [3H, 4H) gi_n (the n gate needs gi_n and gh_n
+//                separately); h W_hh^T is ONE N = 3H MMA per (plane pair, k-step) over W_hh's natural [r; z; n] rows,
+//                x W_ih^T is split instead (r, z onto [0, 2H), n into [3H, 4H)): 36 MMAs per step, A tiles fetched once
 // Hand-offs are mbarriers: a_ready[slot] (256 arrivals: operands staged) and d_ready[slot] (tcgen05.commit).
 // The kernel is bound by the gate maths (6 MUFU per (row, unit, step)), not by the tensor pipe: sigmoid / tanh use
 // ex2.approx + rcp.approx (rel. error ~2^-21), the bf16 planes are cut by integer masking instead of F2F.
-// Shared memory (H = 64, I <= 32): W_ih planes 36 KB + W_hh planes 72 KB + h planes 2 x 48 KB + x 2 x 8 KB = 221 KB;
+// Shared memory (H = 64, I <= 32): W_ih planes 40 KB + W_hh planes 72 KB + h planes 2 x 48 KB + x 2 x 8 KB = 225 KB;
 // TMEM: 2 slots x 4H = 512 columns.
 #pragma once
 #include <cuda_bf16.h>
@@ -144,11 +145,12 @@ __device__ __forceinline__ uint32_t pack2(__nv_bfloat16 a, __nv_bfloat16 b) {
 
 template <int H>
 struct Smem {
-  static constexpr int kWih = 3 * H * kKx;        // bf16 elements per plane
+  static constexpr int kWih = 3 * H * kKx;        // bf16 elements of W_ih planes 1, 2: rows [r; z; n]
+  static constexpr int kWih0 = 4 * H * kKx;       // plane 0: rows [r; z; 0; n] (the zero block initialises the gh_n columns)
   static constexpr int kWhh = 3 * H * H;
   static constexpr int kAh = kM * H;
   static constexpr int kAx = kM * kKx;
-  static constexpr size_t bytes = (size_t)(3 * kWih + 3 * kWhh + 2 * 3 * kAh + 2 * kAx) * 2 + 4 * H * 4 + 64;
+  static constexpr size_t bytes = (size_t)(kWih0 + 2 * kWih + 3 * kWhh + 2 * 3 * kAh + 2 * kAx) * 2 + 4 * H * 4 + 64;
 };
 
 }  // namespace tc
@@ -159,8 +161,8 @@ __global__ void __launch_bounds__(tc::kThreads, 1) gru_window_tc_kernel(const Gr
   using S = Smem<H>;
   static_assert(H % 16 == 0 && H >= 16 && H <= 64, "H in {16, 32, 48, 64}");
   extern __shared__ __align__(1024) uint8_t smem_raw[];
-  __nv_bfloat16* wih = reinterpret_cast<__nv_bfloat16*>(smem_raw);      // [3 planes][3H][kKx]
-  __nv_bfloat16* whh = wih + 3 * S::kWih;                               // [3 planes][3H][H]
+  __nv_bfloat16* wih = reinterpret_cast<__nv_bfloat16*>(smem_raw);      // plane 0 [4H][kKx], planes 1, 2 [3H][kKx]
+  __nv_bfloat16* whh = wih + S::kWih0 + 2 * S::kWih;                    // [3 planes][3H][H]
   __nv_bfloat16* ah = whh + 3 * S::kWhh;                                // [2 slots][3 planes][128][H]
   __nv_bfloat16* ax = ah + 2 * 3 * S::kAh;                              // [2 slots][128][kKx]
   float* bias = reinterpret_cast<float*>(ax + 2 * S::kAx);              // [2H] b_ih + b_hh (r, z), [H] b_in, [H] b_hn
@@ -183,8 +185,10 @@ __global__ void __launch_bounds__(tc::kThreads, 1) gru_window_tc_kernel(const Gr
     __nv_bfloat16 p0, p1, p2;
     split3(k < I ? Wih[(long long)n * I + k] : 0.f, p0, p1, p2);
     const int o = canon16(n, k, kKx);
-    wih[o] = p0, wih[S::kWih + o] = p1, wih[2 * S::kWih + o] = p2;
+    wih[canon16(n < 2 * H ? n : n + H, k, kKx)] = p0;
+    wih[S::kWih0 + o] = p1, wih[S::kWih0 + S::kWih + o] = p2;
   }
+  for (int i = tid; i < H * kKx; i += kThreads) wih[canon16(2 * H + i / kKx, i % kKx, kKx)] = __float2bfloat16_rn(0.f);
   for (int i = tid; i < 3 * H * H; i += kThreads) {
     const int n = i / H, k = i % H;
     __nv_bfloat16 p0, p1, p2;
@@ -244,30 +248,38 @@ __global__ void __launch_bounds__(tc::kThreads, 1) gru_window_tc_kernel(const Gr
       mbar_wait(&a_ready[slot], ph_a);
       ph_a ^= 1u;
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      // input projection: x (exact in bf16) against the three planes of W_ih -> columns [0, 3H)
+      // Accumulator columns of the slot: [0, H) r, [H, 2H) z, [2H, 3H) gh_n, [3H, 4H) gi_n (the n gate needs both
+      // separately).  The hidden projection is ONE N = 3H MMA per (plane pair, k-step) over W_hh's natural [r; z; n]
+      // rows: the A tile is fetched once instead of twice (N = 2H + N = H), which is what limits this kernel.
+      // input projection, x exact in bf16: plane 0 [r; z; 0] initialises [0, 3H) (zeros into the gh_n columns),
+      // planes 1, 2 accumulate onto r, z; the n rows of all planes go to [3H, 4H)
+      constexpr uint32_t sbo_x = (kKx >> 3) * 128;
+#pragma unroll
+      for (int k16 = 0; k16 < kKx / 16; ++k16) mma_bf16(d_slot, desc_adv(dx, k16 * 256), desc_adv(dwih, k16 * 256), id3, k16 > 0);
+#pragma unroll
+      for (int j = 1; j < 3; ++j)
+#pragma unroll
+        for (int k16 = 0; k16 < kKx / 16; ++k16)
+          mma_bf16(d_slot, desc_adv(dx, k16 * 256), desc_adv(dwih, (S::kWih0 + (j - 1) * S::kWih) * 2 + k16 * 256), id2,
+                   true);
 #pragma unroll
       for (int j = 0; j < 3; ++j)
 #pragma unroll
-        for (int k16 = 0; k16 < kKx / 16; ++k16)
-          mma_bf16(d_slot, desc_adv(dx, k16 * 256), desc_adv(dwih, (j * S::kWih) * 2 + k16 * 256), id3,
-                   !(j == 0 && k16 == 0));
+        for (int k16 = 0; k16 < kKx / 16; ++k16) {
+          const uint32_t off = j == 0 ? (3 * H / 8) * sbo_x : (S::kWih0 + (j - 1) * S::kWih) * 2 + (2 * H / 8) * sbo_x;
+          mma_bf16(d_slot + 3 * H, desc_adv(dx, k16 * 256), desc_adv(dwih, off + k16 * 256), id1, !(j == 0 && k16 == 0));
+        }
       if (!first_step) {
-        // hidden projection, plane pairs (i, j) with i + j <= 2: r, z accumulate onto the input projection,
-        // the n gate gets its own columns [3H, 4H)
-        bool first = true;
+        // hidden projection, plane pairs (i, j) with i + j <= 2
 #pragma unroll
         for (int i = 0; i < 3; ++i)
 #pragma unroll
           for (int j = 0; j < 3; ++j) {
             if (i + j > 2) continue;
 #pragma unroll
-            for (int k16 = 0; k16 < H / 16; ++k16) {
-              const uint64_t ad = desc_adv(dah, (i * S::kAh) * 2 + k16 * 256);
-              mma_bf16(d_slot, ad, desc_adv(dwhh, (j * S::kWhh) * 2 + k16 * 256), id2, true);
-              mma_bf16(d_slot + 3 * H, ad, desc_adv(dwhh, (j * S::kWhh) * 2 + (2 * H / 8) * sbo_h + k16 * 256), id1,
-                       !first);
-              first = false;
-            }
+            for (int k16 = 0; k16 < H / 16; ++k16)
+              mma_bf16(d_slot, desc_adv(dah, (i * S::kAh) * 2 + k16 * 256), desc_adv(dwhh, (j * S::kWhh) * 2 + k16 * 256),
+                       id3, true);
           }
       }
       asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];"
@@ -332,8 +344,8 @@ __global__ void __launch_bounds__(tc::kThreads, 1) gru_window_tc_kernel(const Gr
           float pr[8], pz[8], pin[8], phn[8];
           tmem_ld8(d + c * 8, pr);
           tmem_ld8(d + H + c * 8, pz);
-          tmem_ld8(d + 2 * H + c * 8, pin);
-          if (!first) tmem_ld8(d + 3 * H + c * 8, phn);
+          tmem_ld8(d + 3 * H + c * 8, pin);
+          tmem_ld8(d + 2 * H + c * 8, phn);      // zero at the window's first step (written by the zero block)
           asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
           uint32_t q0[8], q1[8], q2[8];
           const float4* bz = reinterpret_cast<const float4*>(bias + u0 + c * 8);   // 16-byte aligned: u0 + 8c
@@ -349,7 +361,7 @@ __global__ void __launch_bounds__(tc::kThreads, 1) gru_window_tc_kernel(const Gr
           for (int j = 0; j < 8; ++j) {
             const float r = rcp_approx(1.0f + ex2_approx(fmaf(pr[j], -1.4426950408889634f, b_r[j])));
             const float z = rcp_approx(1.0f + ex2_approx(fmaf(pz[j], -1.4426950408889634f, b_z[j])));
-            const float ghn = (first ? 0.f : phn[j]) + b_h[j];
+            const float ghn = phn[j] + b_h[j];
             const float pre = fmaf(r, ghn, pin[j] + b_i[j]);
             // tanh(v) = 1 - 2 / (1 + 2^(2 v log2 e))
             const float nn = fmaf(-2.0f, rcp_approx(1.0f + ex2_approx(2.8853900817779268f * pre)), 1.0f);
