@@ -389,7 +389,7 @@ struct ScanArgs {
 enum { kScanRaw = 0, kScanStats = 1, kScanEmit = 2 };
 
 template <int MODE>
-__global__ void __launch_bounds__(128) returns_scan_kernel(const ScanArgs a) {
+__global__ void __launch_bounds__(128, 12) returns_scan_kernel(const ScanArgs a) {
   const int g = blockIdx.y;
   const bool do_adv = MODE == kScanRaw ? a.adv_raw != nullptr : (MODE == kScanStats ? a.want_adv : a.adv_out != nullptr);
   const bool do_ret = MODE == kScanRaw ? a.ret_raw != nullptr : (MODE == kScanStats ? a.want_ret : a.ret_out != nullptr);
@@ -401,7 +401,7 @@ __global__ void __launch_bounds__(128) returns_scan_kernel(const ScanArgs a) {
     if (do_ret) rm_ = a.ret_mean[g], rs_ = a.ret_std[g], rn = a.ret_norm[g] != 0;
   }
   const float rmf = (float)rm_, rsf = (float)rs_;
-  constexpr int U = 8;   // time steps loaded per batch: U independent row loads in flight ahead of the serial fp64 chain
+  constexpr int U = 4;   // time steps loaded per batch: U independent row loads in flight ahead of the serial fp64 chain
   const long long step = (long long)a.n_cols * a.B;
   for (int b = blockIdx.x * blockDim.x + threadIdx.x; b < a.B; b += gridDim.x * blockDim.x) {
     double gae = 0.0, run = 0.0, v_next = 0.0;
