@@ -75,6 +75,8 @@ __global__ void __launch_bounds__(256, 4) comb_step_kernel(const StepArgs a) {
 
     // ---- pass 2: serve, age, switch, arrive, observe; device k+1's state is fetched while k is processed ----
     int n_success = 0;
+    uint4 arr4 = make_uint4(0u, 0u, 0u, 0u);
+    int arr_group = -1;
     Rec<W> r_nx = rec_load<W>(a.buf, (size_t)b);   // second touch of the record: L1 hit
     uint32_t ch_nx = chan[b];
     uint32_t disc_nx = (slot0 & 1ull) ? a.disc[b] : 0u;
@@ -114,18 +116,11 @@ __global__ void __launch_bounds__(256, 4) comb_step_kernel(const StepArgs a) {
         if constexpr (REPLAY) {
           arrived = a.rp_arr[idx];
         } else {
-          const uint32_t u = philox_rk(a, env, a.t, (uint32_t)k | (kPurposeArrival << 16), 0u).x;
-          if (P->arrival_kind[k] == D2D_ARRIVAL_BERNOULLI) {
-            arrived = (uint64_t)u < P->bern_thr[k] ? 1u : 0u;
-          } else {
-            const uint32_t* c = cdf + k * D2D_POISSON_KMAX;
-            arrived = 0;
-#pragma unroll 1
-            for (int m = 0; m < D2D_POISSON_KMAX; ++m) {
-              if (u < c[m]) break;
-              ++arrived;
-            }
+          if ((k >> 2) != arr_group) {          // one Philox call per four devices (env_common.cuh: ArrivalWords)
+            arr_group = k >> 2;
+            arr4 = philox_rk(a, env, a.t, (uint32_t)arr_group | (kPurposeArrival << 16), 0u);
           }
+          arrived = arrival_from_u(P, cdf, k, pick_word(arr4, k & 3));
         }
         rec_set_byte<W>(r, dl - 1, arrived);
         if (arrived) a.recv[idx] = recv_v + arrived;

@@ -159,12 +159,13 @@ __device__ __forceinline__ void rec_emit(const Rec<W>& r, int n, float* p, size_
   }
 }
 
-// arrival of device k at timestep a.t (only called when the device is active)
-__device__ __forceinline__ uint32_t draw_arrival(const StepArgs& a, const EnvParamsHdr* P, const uint32_t* cdf, int k,
-                                                 int b) {
-  if (a.rng_mode == D2D_RNG_REPLAY) return a.rp_arr[(size_t)k * a.B + b];
-  const uint32_t u =
-      philox4x32_10(a.env_offset + (uint32_t)b, a.t, (uint32_t)k | (kPurposeArrival << 16), 0u, a.k0, a.k1).x;
+// Arrival uniforms: one Philox call serves FOUR devices (counter device field = k / 4, device k takes word k % 4), so a
+// step draws ceil(N / 4) arrival calls per env instead of N.
+__device__ __forceinline__ uint32_t pick_word(const uint4& r, int i) {
+  return i == 0 ? r.x : (i == 1 ? r.y : (i == 2 ? r.z : r.w));
+}
+
+__device__ __forceinline__ uint32_t arrival_from_u(const EnvParamsHdr* P, const uint32_t* cdf, int k, uint32_t u) {
   if (P->arrival_kind[k] == D2D_ARRIVAL_BERNOULLI) return (uint64_t)u < P->bern_thr[k] ? 1u : 0u;
   const uint32_t* c = cdf + k * D2D_POISSON_KMAX;
   uint32_t n = 0;
@@ -175,6 +176,41 @@ __device__ __forceinline__ uint32_t draw_arrival(const StepArgs& a, const EnvPar
   }
   return n;
 }
+
+// the four arrival words of device group k / 4, fetched once and reused while the device loop stays in the group
+struct ArrivalWords {
+  uint4 r;
+  int group = -1;
+  __device__ __forceinline__ uint32_t get(const StepArgs& a, uint32_t env, int k) {
+    if ((k >> 2) != group) {
+      group = k >> 2;
+      r = philox4x32_10(env, a.t, (uint32_t)group | (kPurposeArrival << 16), 0u, a.k0, a.k1);
+    }
+    return pick_word(r, k & 3);
+  }
+};
+
+// arrival of device k at timestep a.t (only called when the device is active)
+__device__ __forceinline__ uint32_t draw_arrival(const StepArgs& a, const EnvParamsHdr* P, const uint32_t* cdf, int k,
+                                                 int b, ArrivalWords& words) {
+  if (a.rng_mode == D2D_RNG_REPLAY) return a.rp_arr[(size_t)k * a.B + b];
+  return arrival_from_u(P, cdf, k, words.get(a, a.env_offset + (uint32_t)b, k));
+}
+
+// 16-bit lanes shared by EIGHT devices (single-channel env: one switch / policy bit per device): counter device field
+// = k / 8, device k takes lane k % 8
+struct LaneWords {
+  uint4 r;
+  int group = -1;
+  __device__ __forceinline__ uint32_t get(const StepArgs& a, uint32_t env, int k, uint32_t purpose) {
+    if ((k >> 3) != group) {
+      group = k >> 3;
+      r = philox4x32_10(env, a.t, (uint32_t)group | (purpose << 16), 0u, a.k0, a.k1);
+    }
+    const uint32_t w = pick_word(r, (k & 7) >> 1);
+    return (k & 1) ? (w >> 16) : (w & 0xFFFFu);
+  }
+};
 
 // Philox with the host-precomputed round keys of StepArgs (one constant-bank operand per XOR).
 __device__ __forceinline__ uint4 philox_rk(const StepArgs& a, uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3) {

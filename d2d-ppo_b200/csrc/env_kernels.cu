@@ -43,6 +43,7 @@ __global__ void __launch_bounds__(256) comb_reset_kernel(const StepArgs a) {
   MaskT* chan = reinterpret_cast<MaskT*>(a.chan);
   const uint32_t cmask = C >= 32 ? 0xFFFFFFFFu : ((1u << C) - 1u);
   for (int b = blockIdx.x * blockDim.x + threadIdx.x; b < a.B; b += gridDim.x * blockDim.x) {
+    ArrivalWords arr_words;
     for (int k = 0; k < N; ++k) {
       const size_t idx = (size_t)k * B + b;
       Rec<W> r;
@@ -51,7 +52,7 @@ __global__ void __launch_bounds__(256) comb_reset_kernel(const StepArgs a) {
       uint32_t arrived = 0;
       const int dl = P->deadline[k];
       if ((a.active >> k) & 1ull) {
-        arrived = draw_arrival(a, P, cdf, k, b);
+        arrived = draw_arrival(a, P, cdf, k, b, arr_words);
         rec_set_byte<W>(r, dl - 1, arrived);
       }
       rec_store<W>(a.buf, idx, r);
@@ -93,7 +94,9 @@ __global__ void __launch_bounds__(256) sc_step_kernel(const StepArgs a) {
   const uint8_t* rp_sw = reinterpret_cast<const uint8_t*>(a.rp_sw);
 
   for (int b = blockIdx.x * blockDim.x + threadIdx.x; b < a.B; b += gridDim.x * blockDim.x) {
+    ArrivalWords arr_words;
     const uint32_t env = a.env_offset + (uint32_t)b;
+    LaneWords pol_lanes, sw_lanes;   // one Philox call per eight devices for the 1-bit policy / switch draws
     // ---- pass 1 (env.py:125-127): attempts and the lone transmitter's channel ----
     uint64_t att = 0, good = 0;
     for (int k = 0; k < N; ++k) {
@@ -103,9 +106,7 @@ __global__ void __launch_bounds__(256) sc_step_kernel(const StepArgs a) {
       if (a.act_mode == 0) {
         want = act[idx] != 0;
       } else {
-        const uint32_t thr = a.tp_thr;
-        want = philox_lane_mask(env, a.t, (uint32_t)k | (kPurposePolicy << 16), 1, a.k0, a.k1,
-                                [thr](int) { return thr; });
+        want = pol_lanes.get(a, env, k, kPurposePolicy) < a.tp_thr;
         if (act_out) act_out[idx] = (uint8_t)want;
       }
       const uint64_t at = (want && rec_any<W>(r)) ? 1ull : 0ull;
@@ -131,13 +132,11 @@ __global__ void __launch_bounds__(256) sc_step_kernel(const StepArgs a) {
       if (a.rng_mode == D2D_RNG_REPLAY) {
         sw = rp_sw[idx] & 1u;
       } else {
-        const uint32_t thr = swthr[k];
-        sw = philox_lane_mask(env, a.t, (uint32_t)k | (kPurposeSwitch << 16), 1, a.k0, a.k1,
-                              [thr](int) { return thr; });
+        sw = sw_lanes.get(a, env, k, kPurposeSwitch) < swthr[k];
       }
       chan[idx] = (uint8_t)((chan[idx] ^ sw) & 1u);
       if ((a.active >> k) & 1ull) {                             // :162-180
-        const uint32_t arrived = draw_arrival(a, P, cdf, k, b);
+        const uint32_t arrived = draw_arrival(a, P, cdf, k, b, arr_words);
         rec_set_byte<W>(r, P->deadline[k] - 1, arrived);
         if (arrived) a.recv[idx] += arrived;
       }
@@ -178,6 +177,7 @@ __global__ void __launch_bounds__(256) sc_reset_kernel(const StepArgs a) {
   const size_t B = (size_t)a.B;
   uint8_t* chan = reinterpret_cast<uint8_t*>(a.chan);
   for (int b = blockIdx.x * blockDim.x + threadIdx.x; b < a.B; b += gridDim.x * blockDim.x) {
+    ArrivalWords arr_words;
     for (int k = 0; k < N; ++k) {
       const size_t idx = (size_t)k * B + b;
       Rec<W> r;
@@ -185,7 +185,7 @@ __global__ void __launch_bounds__(256) sc_reset_kernel(const StepArgs a) {
       for (int j = 0; j < W; ++j) r.w[j] = 0;
       uint32_t arrived = 0;
       if ((a.active >> k) & 1ull) {
-        arrived = draw_arrival(a, P, cdf, k, b);
+        arrived = draw_arrival(a, P, cdf, k, b, arr_words);
         rec_set_byte<W>(r, P->deadline[k] - 1, arrived);
       }
       rec_store<W>(a.buf, idx, r);
@@ -235,6 +235,7 @@ __global__ void __launch_bounds__(256) sel_step_kernel(const StepArgs a) {
   const uint32_t cmask = C1 >= 32 ? 0xFFFFFFFFu : ((1u << C1) - 1u);
 
   for (int b = blockIdx.x * blockDim.x + threadIdx.x; b < a.B; b += gridDim.x * blockDim.x) {
+    ArrivalWords arr_words;
     const uint32_t env = a.env_offset + (uint32_t)b;
     const uint32_t ch = chan[b];
     // ---- pass 1 (channel_selection_env.py:124-128): per-channel attempt counts, bit-sliced ----
@@ -275,7 +276,7 @@ __global__ void __launch_bounds__(256) sel_step_kernel(const StepArgs a) {
       const uint32_t expired = rec_age<W>(r);
       if (expired) a.disc[idx] += expired;
       if ((a.active >> k) & 1ull) {
-        const uint32_t arrived = draw_arrival(a, P, cdf, k, b);
+        const uint32_t arrived = draw_arrival(a, P, cdf, k, b, arr_words);
         rec_set_byte<W>(r, P->deadline[k] - 1, arrived);
         if (arrived) a.recv[idx] += arrived;
       }
@@ -318,6 +319,7 @@ __global__ void __launch_bounds__(256) sel_reset_kernel(const StepArgs a) {
   uint32_t* chan = reinterpret_cast<uint32_t*>(a.chan);
   const uint32_t cmask = C1 >= 32 ? 0xFFFFFFFFu : ((1u << C1) - 1u);
   for (int b = blockIdx.x * blockDim.x + threadIdx.x; b < a.B; b += gridDim.x * blockDim.x) {
+    ArrivalWords arr_words;
     for (int k = 0; k < N; ++k) {
       const size_t idx = (size_t)k * B + b;
       Rec<W> r;
@@ -325,7 +327,7 @@ __global__ void __launch_bounds__(256) sel_reset_kernel(const StepArgs a) {
       for (int j = 0; j < W; ++j) r.w[j] = 0;
       uint32_t arrived = 0;
       if ((a.active >> k) & 1ull) {
-        arrived = draw_arrival(a, P, cdf, k, b);
+        arrived = draw_arrival(a, P, cdf, k, b, arr_words);
         rec_set_byte<W>(r, P->deadline[k] - 1, arrived);
       }
       rec_store<W>(a.buf, idx, r);

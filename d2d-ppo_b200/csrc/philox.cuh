@@ -1,5 +1,7 @@
 // Philox4x32-10 (Salmon et al., SC'11) and the 16-bit-lane draw helpers of the "philox" RNG mode.
 // Counter layout: (env_global_index, timestep, device | purpose << 16, block); key = 64-bit seed.
+// Arrival uniforms share a call between four devices, the single-channel env's 1-bit draws between eight
+// (env_common.cuh: ArrivalWords, LaneWords).
 // The numpy restatement used by the parity tests is oracle/philox_np.py.
 #pragma once
 #include <stdint.h>

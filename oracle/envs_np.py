@@ -129,8 +129,7 @@ class PhiloxSource:
         if p.ndim == 1:  # D2DEnv [N]
             out = np.empty((self.env.shape[0], p.shape[0]), dtype=np.int64)
             for k in range(p.shape[0]):
-                lanes = px.lanes16(self.seed, self.env, t, k, px.PURPOSE_SWITCH, 1)
-                out[:, k] = lanes[:, 0] < px.thr16(p[k])
+                out[:, k] = px.lane16_shared(self.seed, self.env, t, k, px.PURPOSE_SWITCH) < px.thr16(p[k])
             return out
         out = np.empty((self.env.shape[0],) + p.shape, dtype=np.int64)  # Combinatorial [N, C]
         for k in range(p.shape[0]):

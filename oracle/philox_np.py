@@ -19,6 +19,10 @@ Counter layout (mirrors ``d2d-ppo_b200/csrc/philox.cuh``):
     key = (seed & 0xffffffff, seed >> 32)
 purpose: 0 = channel switch, 1 = arrival, 2 = policy (random-access action bits).
 A 16-bit lane ``c`` lives in block ``c // 8``, word ``(c % 8) // 2``, half ``c % 2``.
+Calls are shared between devices where a device needs less than a call yields (``env_common.cuh``):
+* arrivals: the counter's device field is ``k // 4`` and device k takes word ``k % 4`` (``word32``);
+* single-channel env switch / policy bits: device field ``k // 8``, device k takes 16-bit lane ``k % 8``
+  (``lane16_shared``).
 """
 from __future__ import annotations
 
@@ -72,10 +76,16 @@ def lanes16(seed, env, t, device, purpose, n_lanes):
 
 
 def word32(seed, env, t, device, purpose):
-    """Word 0 of block 0: the 32-bit uniform used for arrivals."""
+    """The 32-bit uniform of ``device``: word ``device % 4`` of the call whose device field is ``device // 4``."""
     k0, k1 = _key(seed)
-    c2 = (int(device) & 0xFFFF) | (int(purpose) << 16)
-    return philox4x32_10(np.asarray(env, dtype=np.uint64), t, c2, 0, k0, k1)[0]
+    c2 = ((int(device) // 4) & 0xFFFF) | (int(purpose) << 16)
+    return philox4x32_10(np.asarray(env, dtype=np.uint64), t, c2, 0, k0, k1)[int(device) % 4]
+
+
+def lane16_shared(seed, env, t, device, purpose):
+    """One 16-bit lane per device, eight devices per call (single-channel env): lane ``device % 8`` of the call whose
+    device field is ``device // 8``."""
+    return lanes16(seed, env, t, int(device) // 8, purpose, 8)[:, int(device) % 8]
 
 
 # ---- integer thresholds (computed on the host in float64, identically in product and oracle) ----

@@ -243,6 +243,30 @@ def test_host_buffer_step_single_channel_env(cuda_device):
         a_env.step_host(torch.zeros((B, kw["n_agents"], 1), dtype=torch.uint8).pin_memory(), host_r[0], layout="reference")
 
 
+def test_fused_random_access_policy_single_channel(cuda_device):
+    """D2DEnv.step_random_access == oracle step fed with the shared-lane Philox policy bits (one call per eight
+    devices), with neighbourhood observations."""
+    from oracle import philox_np as px
+    from oracle.envs_np import PhiloxSource
+    g = load_env_case("d2d_neighbourhoods")
+    kw = dict(g["config"])
+    B, T, seed, tp = 301, 30, 13, 0.35
+    kw["episode_length"] = T
+    N = kw["n_agents"]
+    env = make_cuda_env("d2d", kw, B, rng="philox", seed=seed, env_offset=17, device=cuda_device)
+    orc = make_oracle("d2d", kw, B, PhiloxSource(B, seed, env_offset=17))
+    env.reset(), orc.reset()
+    envs = np.arange(B) + 17
+    for t in range(1, T + 1):
+        obs, state, rew, done, _ = env.step_random_access(tp)
+        a = np.stack([px.lane16_shared(seed, envs, t, k, px.PURPOSE_POLICY) < px.thr16(tp) for k in range(N)], axis=1)
+        o_obs, o_state, o_rew, o_done, _ = orc.step(a.astype(np.int64))
+        assert np.array_equal(cat_obs(obs), cat_obs(o_obs)) and np.array_equal(to_np(state), o_state), t
+        assert np.array_equal(to_np(rew).astype(np.float64), o_rew.astype(np.float64))
+    assert np.array_equal(to_np(env.received_packets), orc.received)
+    assert np.array_equal(to_np(env.discarded_packets), orc.discarded)
+
+
 def test_reference_compatible_single_env_mode(cuda_device):
     """n_envs=None: host numpy outputs with the reference's shapes and dtypes."""
     g = load_env_case("comb_c3_load1_ragged_obs")
