@@ -1,0 +1,32 @@
+"""bench.py contract checks that run without a GPU: the reference arm (CPU port of the path) prints one JSON line with
+the keys the driver reads, and under a multi-rank launch only rank 0 prints."""
+import json
+import os
+import subprocess
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _run(env_extra=None):
+    env = dict(os.environ, **(env_extra or {}))
+    return subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "1", "--steps", "3",
+                           "--warmup", "1", "--cpu-envs", "64"], capture_output=True, text=True, env=env, timeout=300)
+
+
+def test_reference_arm_json_line():
+    r = _run()
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [l for l in r.stdout.splitlines() if l.startswith("{")]
+    assert len(lines) == 1
+    j = json.loads(lines[0])
+    assert j["impl"] == "reference" and j["unit"] == "agent-steps/s" and j["higher_is_better"] is True
+    assert j["metric"].startswith("agent-steps/sec") and j["value"] > 0 and j["steps"] == 3
+    assert j["cpu_baseline"]["kind"] == "port" and j["cpu_baseline"]["cores"] >= 1 and j["cpu_baseline"]["value"] == j["value"]
+    assert j["e2e"] == {"value": j["value"], "unit": j["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    assert "workload" in j["config"] and j["scaling"] == "weak" and j["vs_baseline"] is None and j["dtype"] == "u8"
+
+
+def test_reference_arm_other_ranks_are_silent():
+    r = _run({"RANK": "1", "WORLD_SIZE": "2", "LOCAL_RANK": "1"})
+    assert r.returncode == 0 and r.stdout.strip() == ""
