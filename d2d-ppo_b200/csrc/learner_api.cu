@@ -56,10 +56,16 @@ static View make_view(float* p, long long t_stride, int t_off, int N, int feat_p
 
 // D2D_DISABLE_TCGEN05=1 keeps every GEMM on the FP32 CUDA-core kernels (A/B comparison, debugging)
 // per-kernel A/B switches: D2D_NO_GRUTC / D2D_NO_BWDTC / D2D_NO_DENSETC / D2D_NO_WGRADTC = 1 route that GEMM family to
-// its FP32 CUDA-core kernel
-static bool dbg_off(const char* name) {
-  const char* e = getenv(name);
-  return e && e[0] == '1';
+// its FP32 CUDA-core kernel (read once per process)
+enum { kSwGruTc = 0, kSwBwdTc, kSwDenseTc, kSwWgradTc, kSwCount };
+static bool switched_off(int which) {
+  static int cache[kSwCount] = {-1, -1, -1, -1};
+  static const char* names[kSwCount] = {"D2D_NO_GRUTC", "D2D_NO_BWDTC", "D2D_NO_DENSETC", "D2D_NO_WGRADTC"};
+  if (cache[which] < 0) {
+    const char* e = getenv(names[which]);
+    cache[which] = (e && e[0] == '1') ? 1 : 0;
+  }
+  return cache[which] != 0;
 }
 static bool tc_enabled() {
   static int disabled = -1;
@@ -96,7 +102,7 @@ static int launch_dense(const d2d_net* n, DenseArgs& a, int max_in, cudaStream_t
   a.B = n->B;
   // tensor-core path (dense_tc.cuh) for single-chunk reductions (K <= 64); with K = 3H the three stage -> MMA round
   // trips per tile serialise inside a slot and the register-tiled FP32 kernel is faster (measured 212 vs 480 us)
-  if (tc_enabled() && !dbg_off("D2D_NO_DENSETC") && n->B >= 256 && a.out_dim <= 192 && max_in <= tcd::kKc &&
+  if (tc_enabled() && !switched_off(kSwDenseTc) && n->B >= 256 && a.out_dim <= 192 && max_in <= tcd::kKc &&
       tcd::smem_bytes(max_in, a.out_dim) <= 225 * 1024) {
     static bool attr = false;
     if (!attr) {
@@ -187,7 +193,7 @@ static int launch_wgrad(d2d_net* n, const View& dy, const View& x, const Wt& w, 
     set_error("learner: weight-gradient tile %d x %d exceeds the supported 192 x 128", O, maxK);
     return D2D_ERR_INVALID;
   }
-  if (tc_enabled() && !dbg_off("D2D_NO_WGRADTC") && n->B % 8 == 0) {
+  if (tc_enabled() && !switched_off(kSwWgradTc) && n->B % 8 == 0) {
     // tensor-core path (wgrad_tc.cuh): bf16 x 3 planes on tcgen05, accumulators in TMEM
     const size_t smem = tcw::smem_bytes(maxK);
     static bool attr = false;
@@ -244,7 +250,7 @@ static int launch_gru_step(const d2d_net* n, GruStepArgs& a, const float* params
 
 // tensor-core fused GRU window (gru_tc.cuh): x windows -> last hidden state, no intermediate in HBM
 static bool gru_tc_eligible(const d2d_net* n) {
-  return tc_enabled() && !dbg_off("D2D_NO_GRUTC") && n->arch == D2D_NET_GRU && n->x_exact && n->max_in <= tc::kKx &&
+  return tc_enabled() && !switched_off(kSwGruTc) && n->arch == D2D_NET_GRU && n->x_exact && n->max_in <= tc::kKx &&
          (n->H == 16 || n->H == 32 || n->H == 48 || n->H == 64);
 }
 
@@ -321,7 +327,7 @@ static int launch_head_fused(const d2d_net* n, const float* params, const View& 
 
 // tensor-core fused BPTT through the window (gru_bwd_tc.cuh)
 static bool gru_bwd_tc_eligible(const d2d_net* n) {
-  return tc_enabled() && !dbg_off("D2D_NO_BWDTC") && n->arch == D2D_NET_GRU && (n->H == 32 || n->H == 64) && n->L >= 1;
+  return tc_enabled() && !switched_off(kSwBwdTc) && n->arch == D2D_NET_GRU && (n->H == 32 || n->H == 64) && n->L >= 1;
 }
 
 template <int H>
