@@ -155,7 +155,8 @@ struct Smem {
 
 }  // namespace tc
 
-template <int H>
+// STORE: the training direction (a.store); compile time so that the rollout kernel carries none of the store code
+template <int H, bool STORE>
 __global__ void __launch_bounds__(tc::kThreads, 1) gru_window_tc_kernel(const GruTcArgs a) {
   using namespace tc;
   using S = Smem<H>;
@@ -335,7 +336,7 @@ __global__ void __launch_bounds__(tc::kThreads, 1) gru_window_tc_kernel(const Gr
         const bool first = s == s0;
         float* acts_row = nullptr;
         float* hs_row = nullptr;
-        if (a.store && b < a.B) {
+        if (STORE && b < a.B) {
           acts_row = view_ptr(a.acts, g, t, a.B, b) + (long long)s * a.acts_step;
           hs_row = view_ptr(a.hs, g, t, a.B, b) + (long long)s * a.hs_step;
         }
@@ -368,7 +369,7 @@ __global__ void __launch_bounds__(tc::kThreads, 1) gru_window_tc_kernel(const Gr
             const float hv = fmaf(z, h[c * 8 + j] - nn, nn);   // (1 - z) n + z h
             h[c * 8 + j] = hv;
             split3_trunc(hv, q0[j], q1[j], q2[j]);
-            if (a.store && b < a.B) {   // rows of a warp are consecutive envs: every store below is one 128-byte line
+            if (STORE && b < a.B) {   // rows of a warp are consecutive envs: every store below is one 128-byte line
               const long long f = (long long)(u0 + c * 8 + j) * a.B;
               const long long hb = (long long)H * a.B;
               acts_row[f] = r, acts_row[f + hb] = z, acts_row[f + 2 * hb] = nn, acts_row[f + 3 * hb] = ghn;
@@ -392,7 +393,7 @@ __global__ void __launch_bounds__(tc::kThreads, 1) gru_window_tc_kernel(const Gr
           __syncwarp();
         } else {
           // TMEM reads of this tile are complete before the next tile's first MMA: its publish() fences them
-          if (b < a.B && !a.store) {
+          if (b < a.B && !STORE) {
             float* ho = view_ptr(a.h_out, g, t, a.B, b);
 #pragma unroll
             for (int u = 0; u < HH; ++u) ho[(long long)(u0 + u) * a.B] = h[u];

@@ -254,20 +254,25 @@ static bool gru_tc_eligible(const d2d_net* n) {
          (n->H == 16 || n->H == 32 || n->H == 48 || n->H == 64);
 }
 
-template <int H>
-static int launch_gru_tc_h(const d2d_net* n, const GruTcArgs& a, cudaStream_t s) {
+template <int H, bool STORE>
+static int launch_gru_tc_hs(const d2d_net* n, const GruTcArgs& a, cudaStream_t s) {
   static bool attr = false;
   if (!attr) {
-    D2D_CUDA(cudaFuncSetAttribute(gru_window_tc_kernel<H>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    D2D_CUDA(cudaFuncSetAttribute(gru_window_tc_kernel<H, STORE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   (int)tc::Smem<H>::bytes));
     attr = true;
   }
   const int pairs = (a.t1 - a.t0) * ((n->B + 2 * tc::kM - 1) / (2 * tc::kM));
   if (pairs <= 0) return D2D_OK;
   const int gx = std::max(1, std::min(pairs, 148 / n->N));   // one CTA per SM (all of its shared memory and TMEM)
-  gru_window_tc_kernel<H><<<dim3(gx, n->N), tc::kThreads, tc::Smem<H>::bytes, s>>>(a);
+  gru_window_tc_kernel<H, STORE><<<dim3(gx, n->N), tc::kThreads, tc::Smem<H>::bytes, s>>>(a);
   D2D_LAUNCHED();
   return D2D_OK;
+}
+
+template <int H>
+static int launch_gru_tc_h(const d2d_net* n, const GruTcArgs& a, cudaStream_t s) {
+  return a.store ? launch_gru_tc_hs<H, true>(n, a, s) : launch_gru_tc_hs<H, false>(n, a, s);
 }
 
 static int launch_gru_tc(const d2d_net* n, const float* params, const View& x, const View& h_out, int t0, int t1,
