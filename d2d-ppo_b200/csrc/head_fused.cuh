@@ -24,7 +24,7 @@ struct HeadFusedArgs {
 
 constexpr int kHeadThreads = 128;
 
-template <int H, int OMAX>
+template <int H, int OMAX, bool KEEP_Y1>   // KEEP_Y1: the backward pass needs relu(W1 h + b1) (training direction)
 __global__ void __launch_bounds__(kHeadThreads) head_fused_kernel(const HeadFusedArgs a) {
   static_assert(H % 8 == 0 && H <= 64, "hidden size");
   __shared__ __align__(16) float w1s[H * H];        // [k][j] = W1[j][k]
@@ -60,8 +60,8 @@ __global__ void __launch_bounds__(kHeadThreads) head_fused_kernel(const HeadFuse
     float o0[OMAX], o1[OMAX];
 #pragma unroll
     for (int o = 0; o < OMAX; ++o) o0[o] = o1[o] = b2s[o];
-    float* yp0 = a.y1.p ? view_ptr(a.y1, g, t, a.B, ok0 ? b0 : 0) : nullptr;
-    float* yp1 = a.y1.p ? view_ptr(a.y1, g, t, a.B, ok1 ? b1 : 0) : nullptr;
+    float* yp0 = KEEP_Y1 ? view_ptr(a.y1, g, t, a.B, ok0 ? b0 : 0) : nullptr;
+    float* yp1 = KEEP_Y1 ? view_ptr(a.y1, g, t, a.B, ok1 ? b1 : 0) : nullptr;
 #pragma unroll 1
     for (int jc = 0; jc < H / 8; ++jc) {
       float a0[8], a1[8];
@@ -83,8 +83,8 @@ __global__ void __launch_bounds__(kHeadThreads) head_fused_kernel(const HeadFuse
       for (int i = 0; i < 8; ++i) {
         const int j = jc * 8 + i;
         a0[i] = fmaxf(a0[i], 0.f), a1[i] = fmaxf(a1[i], 0.f);
-        if (yp0 && ok0) yp0[j * Bl] = a0[i];
-        if (yp1 && ok1) yp1[j * Bl] = a1[i];
+        if (KEEP_Y1 && ok0) yp0[j * Bl] = a0[i];
+        if (KEEP_Y1 && ok1) yp1[j * Bl] = a1[i];
 #pragma unroll
         for (int o = 0; o < OMAX; ++o) {
           const float w2 = w2s[j * OMAX + o];

@@ -299,7 +299,8 @@ static int launch_gru_tc(const d2d_net* n, const float* params, const View& x, c
 template <int H, int OMAX>
 static void launch_head_fused_t(const HeadFusedArgs& a, int N, int tiles, cudaStream_t s) {
   const int gx = std::max(1, std::min(tiles, (148 * 2) / N));
-  head_fused_kernel<H, OMAX><<<dim3(gx, N), kHeadThreads, 0, s>>>(a);
+  if (a.y1.p) head_fused_kernel<H, OMAX, true><<<dim3(gx, N), kHeadThreads, 0, s>>>(a);
+  else head_fused_kernel<H, OMAX, false><<<dim3(gx, N), kHeadThreads, 0, s>>>(a);
 }
 
 static bool head_fused_eligible(const d2d_net* n) {
