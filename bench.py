@@ -196,9 +196,10 @@ def measured_peaks():
 
 def gru_tc_issued_flops(I_pad, H, L):
     """bf16 tensor-pipe flops the fused GRU-window kernel ISSUES per row (csrc/gru_tc.cuh): every fp32 operand is
-    three bf16 planes; x (exact in one plane) x W_ih (3 planes) = 3 MMAs of K = I_pad, h (3) x W_hh (3) keeps the 6
-    plane pairs with i + j <= 2, K = H; both produce 3H columns per step."""
-    return 2 * L * 3 * H * (3 * I_pad + 6 * H)
+    three bf16 planes.  Per step: h (3 planes) x W_hh (3 planes) keeps the 6 plane pairs with i + j <= 2 as N = 3H
+    MMAs of K = H; x (exact in one plane) x W_ih: plane 0 as N = 3H ([r; z; 0]), planes 1, 2 as N = 2H, and the n rows of
+    the three planes as N = H, all of K = I_pad."""
+    return 2 * L * (6 * H * 3 * H + I_pad * (3 * H + 2 * 2 * H + 3 * H))
 
 
 def gru_flops_per_agent_step(I, H, L, O):
@@ -250,8 +251,8 @@ def bench_learner(args, dev, world, rank, barrier, max_over_ranks):
         "seconds_per_episode": dt, "gpu_launches": int(launches),
         "roofline": {"bound": "tensor",
                      "note": "GRU windows on tcgen05 with fp32 operands split into 3 bf16 planes (fp32 parity at 1e-5): "
-                             "`achieved` counts the bf16 MMA flops the kernels issue (6 plane pairs for h W_hh, 3 for "
-                             "x W_ih, K padded 30 -> 32) over the WHOLE rollout time (env step, heads, sampling and "
+                             "`achieved` counts the bf16 MMA flops the kernels issue (6 plane pairs for h W_hh, 3 planes "
+                             "of W_ih, K padded 30 -> 32) over the WHOLE rollout time (env step, heads, sampling and "
                              "returns included); fp32_equivalent_tflops counts the algorithmic flops once",
                      "achieved": steps / world * issued / dt / 1e12, "peak": bf16_peak, "unit": "TFLOP/s",
                      "frac": steps / world * issued / dt / 1e12 / bf16_peak, "traffic": None,
