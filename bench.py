@@ -319,20 +319,20 @@ def bench_learner(args, dev, world, rank, barrier, max_over_ranks):
     out["train_ippo_c3"] = train_sps(
         lambda B: CombinatorialEnv(n_envs=B, device=dev, seed=8, env_offset=rank * B, **kw),
         lambda e: iPPO(e, hidden_size=64, gamma=0.4, policy_lr=3e-4, value_lr=1e-3, useRNN=True, combinatorial=True,
-                       history_len=6, early_stopping=False, seed=2, scratch_bytes=6 << 30),
+                       history_len=6, early_stopping=False, seed=2, scratch_bytes=24 << 30),
         Bt, N_AGENTS, "c3 shape: iPPO GRU (H 64, L 6) on CombinatorialEnv setup_8_channels.p")
     torch.cuda.empty_cache()
     out["train_d2dppo_c3"] = train_sps(
         lambda B: CombinatorialEnv(n_envs=B, device=dev, seed=9, env_offset=rank * B, **kw),
         lambda e: D2DPPO(e, hidden_size=64, gamma=0.6, policy_lr=3e-4, value_lr=1e-3, useRNN=True, combinatorial=True,
-                         history_len=6, early_stopping=False, seed=3, scratch_bytes=6 << 30),
+                         history_len=6, early_stopping=False, seed=3, scratch_bytes=24 << 30),
         Bt, N_AGENTS, "xp_load.py:78-106: D2DPPO GRU (H 64, L 6, gamma .6) on CombinatorialEnv setup_8_channels.p")
     torch.cuda.empty_cache()
     c2 = presets.d2d_c2_kwargs()
     out["train_d2dppo_c2"] = train_sps(
         lambda B: D2DEnv(n_envs=B, device=dev, seed=10, env_offset=rank * B, **c2),
         lambda e: D2DPPO(e, hidden_size=64, gamma=0.6, policy_lr=3e-4, value_lr=1e-3, useRNN=True, combinatorial=False,
-                         history_len=4, early_stopping=False, seed=4, scratch_bytes=6 << 30),
+                         history_len=4, early_stopping=False, seed=4, scratch_bytes=24 << 30),
         4096, 4, "c2: D2DPPO GRU (H 64, L 4) on D2DEnv N=4, 4096 lockstep envs")
     return out
 

@@ -16,7 +16,7 @@ dev = torch.device("cuda", 0)
 kw = presets.combinatorial_kwargs("setup_8_channels", load=1 / 3, episode_length=T)
 env = CombinatorialEnv(n_envs=B, device=dev, seed=7, **kw)
 agent = iPPO(env, hidden_size=64, gamma=0.4, policy_lr=3e-4, value_lr=1e-3, useRNN=True, combinatorial=True,
-             history_len=6, early_stopping=False, seed=1, scratch_bytes=6 << 30)
+             history_len=6, early_stopping=False, seed=1, scratch_bytes=int(__import__("os").environ.get("SCRATCH_GB", "6")) << 30)
 agent.create_rollouts(B)
 agent.update_epoch()          # warm-up: scratch allocation happens here
 torch.cuda.synchronize()
