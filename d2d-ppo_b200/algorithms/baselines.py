@@ -1,6 +1,12 @@
-"""Baseline policies on the device.  Only CombinatorialRandomAccess is in scope: it is
-the policy of run_ma_baselines.py:71-74 and xp_n_agents.py:137-140; the other baselines of the reference are stale
-against its current env return types.  Drop-in for algorithms/baselines.py:171-222.
+"""Baseline policies on the device.
+
+* ``CombinatorialRandomAccess`` (algorithms/baselines.py:171-222): the policy of run_ma_baselines.py:71-74 and
+  xp_n_agents.py:137-140, fused into the combinatorial env's step kernel.
+* ``RandomAccess`` (algorithms/baselines.py:5-45): uniform channel pick on ``ChannelSelectionEnv``; the one other
+  baseline of the reference that still runs against its envs.
+``EarliestDeadlineFirstScheduler`` and ``GFAccess`` (baselines.py:48-168) are not carried over: in the reference
+snapshot they unpack ``env.reset()``'s state as a (buffers, channel) pair, which ``D2DEnv`` no longer returns (flat
+array, env.py:189-190), and ``GFAccess.run`` reads ``buffer_state`` before assigning it (:150-154).
 """
 from __future__ import annotations
 
@@ -53,6 +59,63 @@ class CombinatorialRandomAccess:
             jains = torch.as_tensor(env.compute_jains(), device=env.device, dtype=torch.float64).sum()
             chsc = torch.as_tensor(env.compute_channel_score(), device=env.device, dtype=torch.float64).sum()
             tot += torch.stack([disc, recv, jains, chsc, rew.sum() * env.n_agents,
+                                torch.tensor(float(B), dtype=torch.float64, device=env.device)])
+        _dist.all_reduce_sum_(tot)
+        n = tot[5].item()
+        if self.verbose:
+            print(f"Number of received packets: {tot[1].item()}")
+            print(f"Channel score: {tot[3].item() / n}")
+        return 1 - tot[0].item() / tot[1].item(), tot[2].item() / n, tot[3].item() / n, tot[4].item() / n
+
+
+class RandomAccess:
+    """Uniform random channel pick for every device that has a packet (baselines.py:5-45), on ``ChannelSelectionEnv``.
+    ``act`` takes the flattened buffers [..., N * Dmax] the reference passes (``state[0]``); in batched mode the draws
+    come from torch's CUDA generator (seed with ``torch.manual_seed``), in single-env mode from ``np.random`` as in the
+    reference."""
+
+    def __init__(self, env, verbose=False):
+        self.env = env
+        self.verbose = verbose
+
+    def act(self, buffers):
+        env = self.env
+        N, C = env.n_agents, env.n_channels
+        if env.compat:
+            n_packets = np.asarray(buffers).reshape((N, int(env.deadlines.max()))).sum(1)
+            actions = np.random.choice(np.arange(0, C + 1), size=N)
+            actions[n_packets == 0] = 0
+            return actions
+        b = torch.as_tensor(buffers, device=env.device)
+        n_packets = b.reshape(env.n_envs, N, int(env.deadlines.max())).sum(2)
+        actions = torch.randint(0, C + 1, (env.n_envs, N), device=env.device)
+        return torch.where(n_packets == 0, torch.zeros_like(actions), actions)
+
+    def run(self, n_episodes):
+        """ceil(n_episodes / B) lockstep batches.  Returns (1 - sum discarded / sum received, mean Jain, mean channel
+        score, mean per-episode reward sum over agents and steps), as the reference's ``run``."""
+        env = self.env
+        if len(set(int(d) for d in env.deadlines)) != 1:
+            raise ValueError("RandomAccess reshapes the buffers to (n_agents, deadlines.max()): equal deadlines only")
+        B = env.n_envs
+        sd = int(env.deadlines.sum())
+        batches = max(1, -(-int(n_episodes) // B))
+        tot = torch.zeros(6, dtype=torch.float64, device=env.device)
+        for _ in range(batches):
+            _, state = env.reset()
+            buffers = state[0] if env.compat else state[:, :sd]
+            rew = torch.zeros(B, dtype=torch.float64, device=env.device)
+            done = False
+            while not done:
+                _, state, r, done, _ = env.step(self.act(buffers))
+                buffers = state[0] if env.compat else state[:, :sd]
+                r = torch.as_tensor(np.asarray(r) if env.compat else r, device=env.device).to(torch.float64)
+                rew += r.reshape(B, -1).sum(1)                 # np.sum(rewards_episode): every agent's copy counts
+            disc = torch.as_tensor(env.discarded_packets, device=env.device).to(torch.float64).sum()
+            recv = torch.as_tensor(env.received_packets, device=env.device).to(torch.float64).sum()
+            jains = torch.as_tensor(env.compute_jains(), device=env.device, dtype=torch.float64).sum()
+            chsc = torch.as_tensor(env.compute_channel_score(), device=env.device, dtype=torch.float64).sum()
+            tot += torch.stack([disc, recv, jains, chsc, rew.sum(),
                                 torch.tensor(float(B), dtype=torch.float64, device=env.device)])
         _dist.all_reduce_sum_(tot)
         n = tot[5].item()

@@ -166,3 +166,34 @@ def test_random_access_baseline(cuda_device):
         _, _, _, done, _ = orc.step(rng.binomial(1, gf.transmission_prob, (512, 6, 16)))
     ref = 1 - orc.discarded.sum() / orc.received.sum()
     assert abs(score - ref) < 0.02, (score, ref)
+
+
+def test_random_access_channel_selection_baseline(cuda_device):
+    """RandomAccess (baselines.py:5-45) on ChannelSelectionEnv: idle devices never pick a channel, metrics in range,
+    reproducible under torch.manual_seed, and more channels help (fewer collisions)."""
+    import torch
+    from d2d_ppo_b200.algorithms.baselines import RandomAccess
+    from d2d_ppo_b200.envs import ChannelSelectionEnv
+
+    def make(C, seed=3):
+        N = 5
+        return ChannelSelectionEnv(n_agents=N, n_channels=C, deadlines=np.array([7] * N), lbdas=np.array([0.3] * N),
+                                   period=None, arrival_probs=None, offsets=None, episode_length=60,
+                                   traffic_model="aperiodic", periodic_devices=[],
+                                   channel_switch=np.array([0.1] * (C + 1)), n_envs=256, device=cuda_device, seed=seed)
+    env = make(8)
+    ra = RandomAccess(env)
+    _, state = env.reset()
+    a = ra.act(state[:, :35])
+    empty = state[:, :35].reshape(256, 5, 7).sum(2) == 0
+    assert a.shape == (256, 5) and int(a.max()) <= 8 and bool((a[empty] == 0).all()) and bool((a[~empty] >= 0).all())
+    torch.manual_seed(11)
+    r1 = ra.run(256)
+    torch.manual_seed(11)
+    r2 = ra.run(256)
+    assert r1 == r2
+    score, jain, chsc, rew = r1
+    assert 0.0 <= score <= 1.0 and 0.0 < jain <= 1.0 + 1e-12 and rew > 0
+    torch.manual_seed(11)
+    few = RandomAccess(make(2)).run(256)
+    assert score > few[0]
