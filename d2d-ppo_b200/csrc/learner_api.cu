@@ -116,7 +116,9 @@ static int launch_dense(const d2d_net* n, DenseArgs& a, int max_in, cudaStream_t
     D2D_LAUNCHED();
     return D2D_OK;
   }
-  if (n->B % 4 == 0 && a.out_dim <= 192) {   // register-tiled path (rows are moved as float4)
+  const int tile_opt = a.out_dim > 64 ? 24 : (a.out_dim > 32 ? 8 : 4), tile_rows = a.out_dim > 64 ? 128 : 256;
+  const size_t tile_smem = ((size_t)std::max(max_in, 1) * 8 * tile_opt + 8 * tile_opt + 2 * kDenseKC * tile_rows) * 4;
+  if (n->B % 4 == 0 && a.out_dim <= 192 && tile_smem <= 200 * 1024) {   // register-tiled path (rows moved as float4)
     if (a.out_dim > 64) return launch_dense_tile<4, 24>(n, a, max_in, s);
     if (a.out_dim > 32) return launch_dense_tile<8, 8>(n, a, max_in, s);
     return launch_dense_tile<8, 4>(n, a, max_in, s);
@@ -189,9 +191,28 @@ static int launch_wgrad(d2d_net* n, const View& dy, const View& x, const Wt& w, 
   }
   int strips = n->n_strips;
   const int O = w.out_dim;
-  if (O > 192 || maxK > 128) {
-    set_error("learner: weight-gradient tile %d x %d exceeds the supported 192 x 128", O, maxK);
+  if (maxK > 128) {
+    set_error("learner: weight-gradient reduction width %d exceeds the supported 128", maxK);
     return D2D_ERR_INVALID;
+  }
+  if (O > 192) {   // hidden sizes above 64: 3H output rows are handled as blocks of <= 192 rows
+    for (int o0 = 0; o0 < O; o0 += 192) {
+      Wt wb = w;
+      wb.out_dim = std::min(192, O - o0);
+      std::vector<int> woff(n->N), boff(n->N);
+      View dyb = dy;
+      for (int g = 0; g < n->N; ++g) {
+        const int K = w.in_dim ? (*w.in_dim)[g] : w.in_const;   // row length of the stored matrix
+        woff[g] = (*w.w_off)[g] + o0 * K;
+        boff[g] = w.b_off ? (*w.b_off)[g] + o0 : 0;
+        dyb.f_off[g] += o0;
+      }
+      wb.w_off = &woff;
+      wb.b_off = w.b_off ? &boff : nullptr;
+      const int rc = launch_wgrad(n, dyb, x, wb, zero_in, grads, t0, t1, s);
+      if (rc) return rc;
+    }
+    return D2D_OK;
   }
   if (tc_enabled() && !switched_off(kSwWgradTc) && n->B % 8 == 0) {
     // tensor-core path (wgrad_tc.cuh): bf16 x 3 planes on tcgen05, accumulators in TMEM
@@ -479,7 +500,7 @@ static int forward_chunk(d2d_net* n, const float* params, const float* x, int x_
     for (int st = 0; st < L && !use_tc; ++st) {
       const View hprev = make_view(hs_ptr(n, c, train, st - 1 < 0 ? 0 : st - 1), H * NB, -c0, N, H, B);
       const View hout = make_view(hs_ptr(n, c, train, st), H * NB, -c0, N, H, B);
-      if (B % 4 == 0) {
+      if (B % 4 == 0 && H <= 64) {   // fused hidden projection + gates (its register tile covers 3H <= 192 outputs)
         GruStepArgs fa;
         memset(&fa, 0, sizeof(fa));
         fa.h_prev = hprev, fa.h_out = hout, fa.gi = gi, fa.gi.t_off = gi.t_off - (L - 1 - st);
@@ -639,7 +660,7 @@ extern "C" int d2d_net_create(const d2d_net_config* cfg, d2d_net** out) {
   D2D_REQUIRE(cfg->out_kind >= 0 && cfg->out_kind <= 2, "d2d_net_create: unknown out_kind");
   D2D_REQUIRE(cfg->n_agents >= 1 && cfg->n_agents <= D2D_MAX_AGENTS, "d2d_net_create: n_agents out of range");
   D2D_REQUIRE(cfg->n_envs >= 1, "d2d_net_create: n_envs must be positive");
-  D2D_REQUIRE(cfg->hidden >= 1 && cfg->hidden <= 64, "d2d_net_create: hidden size %d not in 1..64 (this build)",
+  D2D_REQUIRE(cfg->hidden >= 1 && cfg->hidden <= 128, "d2d_net_create: hidden size %d not in 1..128 (this build)",
               cfg->hidden);
   D2D_REQUIRE(cfg->n_out >= 1 && cfg->n_out <= kMaxOut, "d2d_net_create: n_out not in 1..%d", kMaxOut);
   D2D_REQUIRE(cfg->arch == D2D_NET_MLP || (cfg->history_len >= 1 && cfg->history_len <= 64),
@@ -747,7 +768,8 @@ extern "C" int d2d_net_forward(d2d_net* n, const float* params, const float* x, 
 extern "C" int d2d_net_rollout_step(d2d_net* n, const float* params, const float* x, int x_lead, int t, float* out,
                                     void* stream) {
   D2D_REQUIRE(n && params && x && out, "d2d_net_rollout_step: null argument");
-  if (n->arch == D2D_NET_MLP || n->B % 4 != 0) return d2d_net_forward(n, params, x, x_lead, t, t + 1, 0, out, stream);
+  if (n->arch == D2D_NET_MLP || n->B % 4 != 0 || n->H > 64)
+    return d2d_net_forward(n, params, x, x_lead, t, t + 1, 0, out, stream);
   int rc = check_range(n, x_lead, t, t + 1, "d2d_net_rollout_step");
   if (rc) return rc;
   cudaStream_t s = as_stream(stream);

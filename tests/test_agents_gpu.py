@@ -197,3 +197,39 @@ def test_random_access_channel_selection_baseline(cuda_device):
     torch.manual_seed(11)
     few = RandomAccess(make(2)).run(256)
     assert score > few[0]
+
+
+def test_reference_default_hidden_size(cuda_device):
+    """The reference constructors default to hidden_size=128 (ippo.py:223, d2d_ppo.py:220): MLP and GRU learners run
+    a training iteration with it, the rollout log-probs match the oracle, and checkpoints round-trip."""
+    import torch
+    from d2d_ppo_b200 import presets
+    from d2d_ppo_b200.algorithms.d2d_ppo import D2DPPO
+    from d2d_ppo_b200.algorithms.ippo import iPPO
+    from d2d_ppo_b200.envs import CombinatorialEnv
+    from oracle import ppo_torch as P
+    kw = presets.combinatorial_kwargs("setup_8_channels", load=0.5, episode_length=12)
+    B, T, N, C = 24, 12, 6, 8
+    for cls, rnn in ((iPPO, False), (D2DPPO, True)):
+        env = CombinatorialEnv(n_envs=B, device=cuda_device, seed=3, **kw)
+        ag = cls(env, combinatorial=True, useRNN=rnn, history_len=4, early_stopping=False, seed=1)   # hidden_size=128
+        assert ag.hidden_size == 128
+        out = ag.create_rollouts(B)
+        obs, actions, logp = out[0], out[2] if cls is D2DPPO else out[1], out[3] if cls is D2DPPO else out[2]
+        I = 14 + 2 * C
+        rows = obs[:T].reshape(T, N, I, B).permute(3, 0, 1, 2).reshape(B * T, N, I).cpu()
+        acts = ((actions.long().unsqueeze(-1) >> torch.arange(C, device=cuda_device)) & 1).permute(2, 0, 1, 3)
+        acts = acts.reshape(B * T, N, C).float().cpu()
+        for i in (0, N - 1):
+            sd = ag.policies.state_dict(i)
+            if rnn:
+                x, valid = P.windows(rows[:, i], T, 4, pad=False)
+                probs = P.net_forward(sd, x, "sigmoid", valid)
+            else:
+                probs = P.net_forward(sd, rows[:, i], "softmax")
+            ref, _ = P.logp_entropy(probs, acts[:, i], True)
+            assert torch.allclose(logp[:, i].t().reshape(-1).cpu(), ref, rtol=1e-5, atol=2e-6)
+        before = ag.policies.params.clone()
+        res = ag.train(num_iter=1, n_epoch=2, num_episodes=B, test_freq=10 ** 9)
+        losses = np.concatenate([np.ravel(np.asarray(v, dtype=np.float64)) for v in list(res[2]) + list(res[3])])
+        assert np.isfinite(losses).all() and not torch.equal(before, ag.policies.params)

@@ -305,11 +305,13 @@ def test_d2dppo_chain_gradients(tag, cuda_device):
                                                 (64, 6, 300, 5, 30, 8, True), (48, 3, 64, 7, 20, 8, True),
                                                 (64, 5, 260, 4, 40, 8, False), (32, 3, 77, 6, 9, 4, False),
                                                 (64, 6, 256, 5, 30, 8, True), (32, 4, 128, 7, 11, 4, True),
-                                                (64, 3, 384, 3, 30, 1, True)])
+                                                (64, 3, 384, 3, 30, 1, True), (128, 3, 36, 5, 30, 8, True),
+                                                (96, 2, 21, 4, 12, 4, False)])
 def test_tensor_core_training_path_vs_autograd(H, Lh, E, T, I, C, exact, cuda_device):
     """Shapes the fixtures do not reach on the tcgen05 training path (hidden 32 / 48, history 1, several 128-row
     tiles, ragged last tile; exact=False: inputs not flagged bf16-exact, i.e. FP32 forward kernels feeding the tcgen05
-    BPTT kernel, as for the selection env's fractional acks; E a multiple of 128: full tiles only): surrogate + MSE gradients against torch autograd on the
+    BPTT kernel, as for the selection env's fractional acks; E a multiple of 128: full tiles only; hidden 96 / 128, the
+    reference constructors' default, on the FP32 kernels): surrogate + MSE gradients against torch autograd on the
     oracle with random weights."""
     from d2d_ppo_b200 import _lib as L
     from d2d_ppo_b200.algorithms._nets import action_dtype, policy_head
