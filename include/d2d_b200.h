@@ -198,7 +198,7 @@ typedef struct d2d_net_config {
   int32_t out_kind;        /* D2D_OUT_*                                                         */
   int32_t n_agents;        /* N networks                                                        */
   int32_t n_envs;          /* B                                                                 */
-  int32_t hidden;          /* H                                                                 */
+  int32_t hidden;          /* H, 1..128 (16 / 32 / 48 / 64: tcgen05 kernels; others: FP32 kernels)      */
   int32_t n_out;           /* O: action_space[k].n for policies, 1 for critics (<= 32)          */
   int32_t history_len;     /* L: GRU window (d2d_ppo.py:302); ignored for MLP                   */
   int32_t in_rows;         /* feature rows per time block of the input matrix                   */
