@@ -139,8 +139,8 @@ class PPOBase:
         mean = stats[:, cols[0]] / n
         var = (stats[:, cols[1]] - n * mean * mean) / (n - ddof)
         std = var.clamp(min=0).sqrt()
-        ok = bool((std > 0).all().item())
-        flags = torch.full((stats.shape[0],), int(ok), dtype=torch.int32, device=self.device)
+        # stays on the device (no host round trip between the statistics pass and the emit pass)
+        flags = (std > 0).all().to(torch.int32).expand(stats.shape[0]).contiguous()
         return mean.contiguous(), std.contiguous(), flags
 
     def _check_episodes(self, num_episodes):
