@@ -30,3 +30,14 @@ def test_reference_arm_json_line():
 def test_reference_arm_other_ranks_are_silent():
     r = _run({"RANK": "1", "WORLD_SIZE": "2", "LOCAL_RANK": "1"})
     assert r.returncode == 0 and r.stdout.strip() == ""
+
+
+def test_cpu_learner_baseline_runs():
+    """oracle/ippo_cpu.py (the CPU baseline of bench.py's rollout / train figures) completes a tiny iteration."""
+    import sys
+    sys.path.insert(0, ROOT)
+    from d2d_ppo_b200 import presets
+    from oracle.ippo_cpu import ippo_iteration_cpu
+    kw = presets.combinatorial_kwargs("setup_8_channels", load=0.5, episode_length=8)
+    r = ippo_iteration_cpu(3, kw, n_epoch=1, hidden=16, history_len=3)
+    assert r["agent_steps"] == 3 * 8 * 6 and r["rollout_s"] > 0 and r["update_s"] > 0
