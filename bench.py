@@ -51,7 +51,9 @@ def parse():
     ap.add_argument("--no-configs", action="store_true", help="skip the c1 / c2 / c4 / selection env-step sections")
     ap.add_argument("--no-learner", action="store_true", help="skip the learned-policy rollout / train SPS sections")
     ap.add_argument("--rollout-envs", type=int, default=65536, help="envs per GPU of the learned-policy rollout (c3)")
-    ap.add_argument("--train-envs", type=int, default=4096, help="envs per GPU of the train-SPS sections")
+    ap.add_argument("--train-envs", type=int, default=65536,
+                    help="envs per GPU of the c3 train-SPS sections (BASELINE config 3 names 65,536)")
+    ap.add_argument("--train-envs-small", type=int, default=4096, help="extra c3 train-SPS point (round-1 shape)")
     return ap.parse_args()
 
 
@@ -147,6 +149,21 @@ def cpu_throughput(n_envs, steps, warmup, procs):
     return procs * n_envs * N_AGENTS * steps / dt, dt
 
 
+def reference_value(cores, episodes):
+    """(value, dt, kind, sample) of the reference arm: the UNMODIFIED reference staged in oracle/_ref (one single-env
+    instance per host core, CombinatorialRandomAccess.run) when present, else the vectorised oracle port."""
+    from d2d_ppo_b200 import presets
+    from oracle import make_ref, ref_timing
+    if make_ref.verify():
+        kw = presets.combinatorial_kwargs("setup_8_channels", load=LOAD)
+        v, dt = ref_timing.random_access_throughput(kw, TP, episodes, cores)
+        return v, dt, "reference", (
+            f"UNMODIFIED reference (oracle/_ref, hashes verified): {cores} processes x 1 env x {episodes} episodes x 200 "
+            f"steps of algorithms/baselines.py CombinatorialRandomAccess.run on envs/combinatorial_env.py "
+            f"(run_ma_baselines.py:71-74 loop), global np.random, {dt:.1f} s")
+    return None
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -155,15 +172,26 @@ def run_reference(args):
     steps, warmup = args.steps, args.warmup
     # bound the sample: one step of 4096 envs costs ~5 ms per process; keep the whole run to ~a minute
     steps_eff = min(steps, 2000)
-    value, dt = cpu_throughput(args.cpu_envs, steps_eff, min(warmup, 50), cores)
-    sample = (f"{cores} processes x {args.cpu_envs} envs x {steps_eff} steps of oracle/envs_np.CombinatorialOracle "
-              f"(numpy restatement, vectorised over envs) + numpy random-access policy")
+    port_value, port_dt = cpu_throughput(args.cpu_envs, steps_eff, min(warmup, 50), cores)
+    port_sample = (f"{cores} processes x {args.cpu_envs} envs x {steps_eff} steps of oracle/envs_np.CombinatorialOracle "
+                   f"(numpy restatement, vectorised over envs) + numpy random-access policy")
+    # one reference episode (200 env steps) costs ~25 ms per core: ~20 s per process
+    ref = reference_value(cores, episodes=max(4, min(800, 4 * steps_eff // 10)))
+    if ref is not None:
+        value, dt, kind, sample = ref
+    else:
+        value, dt, kind, sample = port_value, port_dt, "port", port_sample
     line = {
         "impl": "reference", "metric": "agent-steps/sec (env step + random-access policy)", "value": value,
         "unit": "agent-steps/s", "n_gpus": args.gpus, "steps": steps_eff, "warmup": min(warmup, 50),
-        "ms_per_step": dt / steps_eff * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "u8", "data": "synthetic", "config": workload_config(args.cpu_envs * cores, cpu=True),
-        "cpu_baseline": {"value": value, "unit": "agent-steps/s", "cores": cores, "kind": "port", "sample": sample},
+        "ms_per_step": port_dt / steps_eff * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "u8", "data": "synthetic",
+        "config": workload_config(cores if kind == "reference" else args.cpu_envs * cores, cpu=True),
+        "cpu_baseline": {"value": value, "unit": "agent-steps/s", "cores": cores, "kind": kind, "sample": sample,
+                         "port_value": port_value, "port_sample": port_sample,
+                         "note": "value = the reference's own single-env Python loop on every host core; port_value = "
+                                 "the numpy restatement vectorised over 4096 envs per process (a far faster CPU "
+                                 "program than the reference, kept as the conservative comparison)"},
         "e2e": {"value": value, "unit": "agent-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -190,8 +218,13 @@ def measured_peaks():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(path):
         j = json.load(open(path))
+        global BF16_SUSTAINED
+        BF16_SUSTAINED = float(j.get("bf16_tflops_sustained", j["bf16_tflops"]))
         return float(j["hbm_gbs"]), float(j["bf16_tflops"]), "of measured (MEASURED_PEAKS.json)"
     return FALLBACK_HBM, FALLBACK_BF16, "of fallback (B200_PROFILING.md)"
+
+
+BF16_SUSTAINED = FALLBACK_BF16
 
 
 def gru_tc_issued_flops(I_pad, H, L):
@@ -250,15 +283,20 @@ def bench_learner(args, dev, world, rank, barrier, max_over_ranks):
         "config": "c3: iPPO useRNN=True hidden 64 history_len 6 on CombinatorialEnv setup_8_channels.p",
         "seconds_per_episode": dt, "gpu_launches": int(launches),
         "roofline": {"bound": "tensor",
-                     "note": "GRU windows on tcgen05 with fp32 operands split into 3 bf16 planes (fp32 parity at 1e-5): "
-                             "`achieved` counts the bf16 MMA flops the kernels issue (6 plane pairs for h W_hh, 3 planes "
-                             "of W_ih, K padded 30 -> 32) over the WHOLE rollout time (env step, heads, sampling and "
-                             "returns included); fp32_equivalent_tflops counts the algorithmic flops once",
-                     "achieved": steps / world * issued / dt / 1e12, "peak": bf16_peak, "unit": "TFLOP/s",
-                     "frac": steps / world * issued / dt / 1e12 / bf16_peak, "traffic": None,
-                     "issued_bf16_flops_per_agent_step": issued, "flops_per_agent_step": flops,
-                     "fp32_equivalent_tflops": steps / world * flops / dt / 1e12,
-                     "fp32_ffma_peak_tflops": FFMA_PEAK_TFLOPS, "peak_source": peak_src + " bf16_tflops (burst)"}}
+                     "note": "primary figure: ALGORITHMIC forward flops (SURVEY.md 8d: 2 L 3H (I + H) + 2 H^2 + 2 H O per "
+                             "net, counted once) over the WHOLE rollout time (env step, heads, sampling, returns "
+                             "included) against the SUSTAINED bf16 peak (a kernel inside a 0.2 s step).  The GRU windows "
+                             "run on tcgen05 with fp32 operands split into 3 bf16 planes (fp32 parity at 1e-5), i.e. "
+                             "the tensor pipe ISSUES issued_bf16_flops_per_agent_step (6 plane pairs for h W_hh, 3 "
+                             "planes of W_ih, K padded 30 -> 32): issued_frac_of_sustained is that rate",
+                     "achieved": steps / world * flops / dt / 1e12, "peak": BF16_SUSTAINED, "unit": "TFLOP/s",
+                     "frac": steps / world * flops / dt / 1e12 / BF16_SUSTAINED, "traffic": None,
+                     "flops_per_agent_step": flops, "issued_bf16_flops_per_agent_step": issued,
+                     "issued_tflops": steps / world * issued / dt / 1e12,
+                     "issued_frac_of_sustained": steps / world * issued / dt / 1e12 / BF16_SUSTAINED,
+                     "issued_frac_of_burst": steps / world * issued / dt / 1e12 / bf16_peak,
+                     "fp32_ffma_peak_tflops": FFMA_PEAK_TFLOPS,
+                     "peak_source": peak_src + " bf16_tflops_sustained"}}
 
     # GAE / returns scans of that rollout: lambda-returns + discounted returns for T x N x B elements, two passes
     # (statistics; normalised fp32 emit), HBM-bound.  Algorithmic bytes per element: SURVEY.md section 8d
@@ -303,7 +341,18 @@ def bench_learner(args, dev, world, rank, barrier, max_over_ranks):
     torch.cuda.empty_cache()
 
     # (iii) PPO train SPS = agent-steps consumed per second of train() (rollout + n_epoch = 5 full-batch updates)
-    def train_sps(make_env, make_agent, B, n_agents, label, n_epoch=5, iters=2):
+    def train_flops(n_nets_gru, I_pad, H, L, O_list):
+        """Per agent-step of ONE update epoch, summed over the GRU nets an agent trains (policy / + critic):
+        (algorithmic fp32-equivalent flops, bf16 MMA flops the GRU window + BPTT kernels issue)."""
+        alg = issued = 0.0
+        for O in O_list:
+            fwd = gru_flops_per_agent_step(30, H, L, O)
+            alg += 3 * fwd                                               # backward = data + weight gradients = 2 x forward
+            issued += gru_tc_issued_flops(I_pad, H, L)                   # forward window (training direction)
+            issued += 2 * L * (5 * 3 * H * H + 5 * 3 * H * (H + 16))     # BPTT: D = G W_hh and dW += G^T P, 5 plane pairs
+        return alg, issued
+
+    def train_sps(make_env, make_agent, B, n_agents, label, n_epoch=5, iters=2, nets=None):
         env = make_env(B)
         ag = make_agent(env)
         kwargs = dict(num_iter=1, n_epoch=n_epoch, num_episodes=B, test_freq=10 ** 9)
@@ -311,29 +360,68 @@ def bench_learner(args, dev, world, rank, barrier, max_over_ranks):
         ag.train(**kwargs)                                       # warm-up iteration
         kwargs["num_iter"] = iters
         dt, launches = timed(lambda: ag.train(**kwargs))
-        return {"metric": "PPO train SPS (agent-steps consumed per second of train(): rollout + 5 epochs)",
-                "value": world * iters * B * n_agents * env.episode_length / dt, "unit": "agent-steps/s",
-                "envs_per_gpu": B, "config": label, "seconds_per_iteration": dt / iters, "gpu_launches": int(launches)}
+        # the update alone: one epoch on the rollout in place (device events), for the roofline of the update kernels
+        ep_dt, _ = timed(lambda: ag.update_epoch())
+        res = {"metric": "PPO train SPS (agent-steps consumed per second of train(): rollout + 5 epochs)",
+               "value": world * iters * B * n_agents * env.episode_length / dt, "unit": "agent-steps/s",
+               "envs_per_gpu": B, "config": label, "seconds_per_iteration": dt / iters, "gpu_launches": int(launches),
+               "seconds_per_epoch": ep_dt}
+        if nets is not None:
+            alg, issued = train_flops(*nets)
+            rows = B * n_agents * env.episode_length
+            traffic = None
+            tpath = os.path.join(ROOT, "profiles", "train_epoch_traffic.json")
+            if os.path.exists(tpath):
+                traffic = json.load(open(tpath))
+            res["roofline"] = {
+                "bound": "tensor", "kernel": "gru_bwd_tc_kernel<64> (+ gru_window_tc_kernel<64,1>): ~75 % of an epoch",
+                "achieved": rows * alg / ep_dt / 1e12, "peak": BF16_SUSTAINED, "unit": "TFLOP/s",
+                "frac": rows * alg / ep_dt / 1e12 / BF16_SUSTAINED,
+                "flops_per_agent_step_epoch": alg, "issued_bf16_flops_per_agent_step_epoch": issued,
+                "issued_tflops": rows * issued / ep_dt / 1e12,
+                "issued_frac_of_sustained": rows * issued / ep_dt / 1e12 / BF16_SUSTAINED,
+                "traffic": traffic,
+                "note": "one update epoch timed alone with CUDA events; `achieved` = algorithmic fp32-equivalent flops "
+                        "of forward + backward of every GRU net (3 x forward), `issued` = bf16 MMA flops of the GRU "
+                        "window and BPTT kernels (3-plane operands); `traffic` = DRAM bytes per 4,096-env epoch of the "
+                        "two dominant kernels from the ncu launch list in profiles/ (null if absent)",
+                "peak_source": peak_src + " bf16_tflops_sustained"}
+        del ag, env
+        torch.cuda.empty_cache()
+        return res
 
-    Bt = args.train_envs
-    out["train_ippo_c3"] = train_sps(
-        lambda B: CombinatorialEnv(n_envs=B, device=dev, seed=8, env_offset=rank * B, **kw),
-        lambda e: iPPO(e, hidden_size=64, gamma=0.4, policy_lr=3e-4, value_lr=1e-3, useRNN=True, combinatorial=True,
-                       history_len=6, early_stopping=False, seed=2, scratch_bytes=24 << 30),
-        Bt, N_AGENTS, "c3 shape: iPPO GRU (H 64, L 6) on CombinatorialEnv setup_8_channels.p")
-    torch.cuda.empty_cache()
-    out["train_d2dppo_c3"] = train_sps(
-        lambda B: CombinatorialEnv(n_envs=B, device=dev, seed=9, env_offset=rank * B, **kw),
-        lambda e: D2DPPO(e, hidden_size=64, gamma=0.6, policy_lr=3e-4, value_lr=1e-3, useRNN=True, combinatorial=True,
-                         history_len=6, early_stopping=False, seed=3, scratch_bytes=24 << 30),
-        Bt, N_AGENTS, "xp_load.py:78-106: D2DPPO GRU (H 64, L 6, gamma .6) on CombinatorialEnv setup_8_channels.p")
-    torch.cuda.empty_cache()
+    def c3_env(seed):
+        return lambda B: CombinatorialEnv(n_envs=B, device=dev, seed=seed, env_offset=rank * B, **kw)
+
+    def c3_ippo(e):
+        return iPPO(e, hidden_size=64, gamma=0.4, policy_lr=3e-4, value_lr=1e-3, useRNN=True, combinatorial=True,
+                    history_len=6, early_stopping=False, seed=2, scratch_bytes=24 << 30)
+
+    def c3_d2dppo(e):
+        return D2DPPO(e, hidden_size=64, gamma=0.6, policy_lr=3e-4, value_lr=1e-3, useRNN=True, combinatorial=True,
+                      history_len=6, early_stopping=False, seed=3, scratch_bytes=24 << 30)
+
+    # BASELINE config 3 names 65,536 envs: that is the headline train figure; the 4,096-env point is kept beside it
+    Bt, Bs = args.train_envs, args.train_envs_small
+    out["train_ippo_c3"] = train_sps(c3_env(8), c3_ippo, Bt, N_AGENTS,
+                                     f"c3: iPPO GRU (H 64, L 6) on CombinatorialEnv setup_8_channels.p, {Bt} envs/GPU",
+                                     iters=1 if Bt > 16384 else 2, nets=(2, 32, 64, 6, [8, 1]))
+    out["train_d2dppo_c3"] = train_sps(c3_env(9), c3_d2dppo, Bt, N_AGENTS,
+                                       f"xp_load.py:78-106: D2DPPO GRU (H 64, L 6, gamma .6) on CombinatorialEnv "
+                                       f"setup_8_channels.p, {Bt} envs/GPU", iters=1 if Bt > 16384 else 2,
+                                       nets=(1, 32, 64, 6, [8]))
+    if Bs and Bs != Bt:
+        out["train_ippo_c3_small"] = train_sps(c3_env(8), c3_ippo, Bs, N_AGENTS,
+                                               f"c3 shape at {Bs} envs/GPU (round-1 bench shape)", nets=(2, 32, 64, 6, [8, 1]))
+        out["train_d2dppo_c3_small"] = train_sps(c3_env(9), c3_d2dppo, Bs, N_AGENTS,
+                                                 f"xp_load.py shape at {Bs} envs/GPU (round-1 bench shape)",
+                                                 nets=(1, 32, 64, 6, [8]))
     c2 = presets.d2d_c2_kwargs()
     out["train_d2dppo_c2"] = train_sps(
         lambda B: D2DEnv(n_envs=B, device=dev, seed=10, env_offset=rank * B, **c2),
         lambda e: D2DPPO(e, hidden_size=64, gamma=0.6, policy_lr=3e-4, value_lr=1e-3, useRNN=True, combinatorial=False,
                          history_len=4, early_stopping=False, seed=4, scratch_bytes=24 << 30),
-        4096, 4, "c2: D2DPPO GRU (H 64, L 4) on D2DEnv N=4, 4096 lockstep envs")
+        4096, 4, "c2: D2DPPO GRU (H 64, L 4) on D2DEnv N=4, 4096 lockstep envs (the named size)")
     return out
 
 
@@ -462,31 +550,44 @@ def run_native(args):
         step()
 
     # ---- device-resident throughput: K steps, CUDA events on the launching stream --------------
+    # The K steps (and the resets that fall inside them) are enqueued by ONE call of the C ABI's multi-step entry
+    # d2d_env_run_random_access (the library loops over the launches): with a Python -> ctypes call per step, short
+    # windows at 8 ranks were bounded by host launch jitter, not by the GPUs (round 1: 0.77 at N = 8, --steps 20).
+    rew_buf = torch.zeros(B, dtype=torch.int32, device=dev)
+
+    def run(n):
+        done = env.run_random_access(TP, n, auto_reset=True, out_obs=obs_buf, out_reward=rew_buf)
+        assert done == n
+
     sampler = ClockSampler(local)
-    ev = [torch.cuda.Event(enable_timing=True) for _ in range(K + 1)]
-    launches0 = _lib.launch_count()
     sampler.start()
     t_spin = time.perf_counter()
     while time.perf_counter() - t_spin < 1.2:      # untimed spin-up under the same load (see ClockSampler)
-        for _ in range(50):
-            step()
+        run(50)
         torch.cuda.synchronize()
-    barrier()
-    t_begin = time.perf_counter()
+    # per-launch duration of the step kernel: events between consecutive single-step calls (untimed for the headline)
+    n_probe = max(20, min(K, 200))
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(n_probe + 1)]
     ev[0].record()
-    n_resets = 0
-    for i in range(K):
-        if env.timestep >= T:
-            n_resets += 1
+    for i in range(n_probe):
         step()
         ev[i + 1].record()
+    torch.cuda.synchronize()
+    per = np.array([ev[i].elapsed_time(ev[i + 1]) for i in range(n_probe)])
+    kernel_ms = float(np.median(per))             # gaps that contain a reset launch do not move the median
+    launches0 = _lib.launch_count()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t_begin = time.perf_counter()
+    e0.record()
+    run(K)
+    e1.record()
     barrier()
     clocks = sampler.stop(t_begin, time.perf_counter())
     launches = _lib.launch_count() - launches0
-    total_ms = max_over_ranks(ev[0].elapsed_time(ev[K]))
-    per = np.array([ev[i].elapsed_time(ev[i + 1]) for i in range(K)])
-    # per-launch duration of the step kernel: gaps that contain a reset launch are excluded from the average
-    kernel_ms = float(np.median(per))
+    n_resets = launches - K
+    total_ms = max_over_ranks(e0.elapsed_time(e1))
+    launch_ms = total_ms / max(launches, 1)       # average launch duration inside the timed region (resets included)
     value = world * B * N_AGENTS * K / (total_ms * 1e-3)
 
     # ---- end to end through the public API with HOST buffers ------------------------------------
@@ -516,16 +617,20 @@ def run_native(args):
         env.host_wait(pending[0])
         return checksum + int(pending[1][0])
 
+    e2e_secs = {}
+
     def e2e_time(acts, layout):
         e2e_run(acts, layout, 4)
         barrier()
         t0 = time.perf_counter()
         e2e_run(acts, layout, Ke)
         barrier()
-        return world * B * N_AGENTS * Ke / max_over_ranks(time.perf_counter() - t0)
+        e2e_secs[layout] = max_over_ranks(time.perf_counter() - t0)
+        return world * B * N_AGENTS * Ke / e2e_secs[layout]
 
     e2e_value = e2e_time(host_actions, "reference")
     e2e_masks = e2e_time(host_masks, "device")
+    h2d_gbs_rank = B * N_AGENTS * N_CHANNELS * Ke / e2e_secs["reference"] / 1e9
 
     # ---- roofline of the dominant kernel ---------------------------------------------------------
     peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
@@ -533,7 +638,10 @@ def run_native(args):
         peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "of measured (MEASURED_PEAKS.json hbm_gbs)"
     else:
         peak, peak_src = FALLBACK_HBM, "of fallback (B200_PROFILING.md 6.65 TB/s)"
-    achieved = B * N_AGENTS * ALG_BYTES / (kernel_ms * 1e-3) / 1e9
+    # `achieved`: algorithmic bytes of one launch / the AVERAGE launch duration over the timed region (total time /
+    # launches: launch gaps and the cheaper reset launches included, so it can only understate the kernel);
+    # kernel_ms = median gap between consecutive single-step launches, reported beside it
+    achieved = B * N_AGENTS * ALG_BYTES / (launch_ms * 1e-3) / 1e9
     traffic = None
     tpath = os.path.join(ROOT, "profiles", "env_step_traffic.json")
     if os.path.exists(tpath):
@@ -563,7 +671,9 @@ def run_native(args):
         "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
         "config": workload_config(world * B),
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "traffic": traffic, "kernel": "comb_step_kernel<4,uint8_t,6>", "kernel_ms": kernel_ms,
+                     "traffic": traffic, "kernel": "comb_step_kernel<4,uint8_t,8,1,2>", "kernel_ms": kernel_ms,
+                     "avg_launch_ms_timed_region": launch_ms,
+                     "achieved_at_median_kernel_ms": B * N_AGENTS * ALG_BYTES / (kernel_ms * 1e-3) / 1e9,
                      "alg_bytes_per_agent_step": ALG_BYTES, "agent_steps_per_launch": B * N_AGENTS,
                      "peak_source": peak_src,
                      "context": {"torch_fill_gbs": fill_gbs, "torch_copy_gbs": copy_gbs,
@@ -575,6 +685,11 @@ def run_native(args):
                        "(N,C) array per env, in pinned host memory -> i32 [B] rewards in pinned host memory, read by "
                        "the host every step; two calls in flight",
                 "bound": "PCIe: 48 B of actions per env-step",
+                "h2d_gbs_per_rank": h2d_gbs_rank, "h2d_gbs_all_ranks": h2d_gbs_rank * world,
+                "limiter": "host -> device copy of the u8 [B,N,C] actions (50.3 MB per step and rank) over each GPU's "
+                           "PCIe link; with N ranks the N concurrent pinned-memory copies share the host's memory / "
+                           "root-complex bandwidth, so the per-rank rate drops as N grows (no collective is involved); "
+                           "packed_actions moves 8x fewer bytes through the same call",
                 "packed_actions": {"value": e2e_masks, "unit": "agent-steps/s", "h2d_bytes_per_step": B * N_AGENTS,
                                    "d2h_bytes_per_step": B * 4,
                                    "api": "same call with the device action layout (u8 channel bitmask [N,B])"}},
@@ -590,17 +705,34 @@ def run_native(args):
         steps_cpu = 600
         v, dt = cpu_throughput(args.cpu_envs, steps_cpu, 20, 1)
         v1, dt1 = cpu_throughput(1, 3000, 50, 1)
-        line["cpu_baseline"] = {
-            "value": v, "unit": "agent-steps/s", "cores": 1, "kind": "port",
-            "sample": f"{args.cpu_envs} envs x {steps_cpu} steps of oracle/envs_np.CombinatorialOracle (numpy, "
-                      f"vectorised over envs) + numpy random-access policy, {dt:.1f} s",
-            "single_env_value": v1,
-            "single_env_sample": f"1 env x 3000 steps (the reference's own shape: one instance per process), {dt1:.1f} s"}
+        port = {"value": v, "unit": "agent-steps/s", "cores": 1, "kind": "port",
+                "sample": f"{args.cpu_envs} envs x {steps_cpu} steps of oracle/envs_np.CombinatorialOracle (numpy, "
+                          f"vectorised over envs) + numpy random-access policy, {dt:.1f} s",
+                "single_env_value": v1,
+                "single_env_sample": f"1 env x 3000 steps (the reference's own shape: one instance per process), "
+                                     f"{dt1:.1f} s"}
+        ref = reference_value(1, episodes=400)              # ~10 s of the unmodified reference on one core
+        if ref is not None:
+            line["cpu_baseline"] = {"value": ref[0], "unit": "agent-steps/s", "cores": 1, "kind": "reference",
+                                    "sample": ref[3], "port": port}
+        else:
+            line["cpu_baseline"] = port
         if not args.no_learner:
             from oracle.ippo_cpu import ippo_iteration_cpu
             threads = torch.get_num_threads()
             r = ippo_iteration_cpu(args.cpu_learner_envs, presets.combinatorial_kwargs("setup_8_channels", load=LOAD),
                                    n_epoch=5)
+            from oracle import make_ref, ref_timing
+            if make_ref.verify():
+                rr = ref_timing.ippo_iteration(presets.combinatorial_kwargs("setup_8_channels", load=LOAD),
+                                               num_episodes=2, n_epoch=5, threads=threads)
+                line["cpu_baseline_learner_reference"] = {
+                    "rollout_value": rr["agent_steps"] / rr["rollout_s"], "train_value": rr["agent_steps"] / rr["total_s"],
+                    "unit": "agent-steps/s", "cores": rr["threads"], "kind": "reference",
+                    "sample": f"UNMODIFIED reference (oracle/_ref): iPPO.create_rollouts(2) then iPPO.train(num_iter=1, "
+                              f"n_epoch=5, num_episodes=2) of algorithms/ippo.py, GRU actor + critic per agent (H 64, "
+                              f"L 6) on envs/combinatorial_env.py setup_8_channels.p, torch CPU with {rr['threads']} "
+                              f"threads: rollout {rr['rollout_s']:.1f} s, train {rr['total_s']:.1f} s"}
             line["cpu_baseline_learner"] = {
                 "rollout_value": r["agent_steps"] / r["rollout_s"],
                 "train_value": r["agent_steps"] / (r["rollout_s"] + r["update_s"]), "unit": "agent-steps/s",

@@ -49,6 +49,7 @@ OUT_SOFTMAX, OUT_SIGMOID, OUT_IDENTITY = 0, 1, 2
 DIST_BERNOULLI, DIST_CATEGORICAL = 0, 1
 ACT_SAMPLE, ACT_GREEDY, ACT_GIVEN = 0, 1, 2
 ACT_HOST_REFERENCE, ACT_HOST_DEVICE_LAYOUT = 0, 1
+SWITCH_GRU_WINDOW_TC, SWITCH_GRU_BPTT_TC, SWITCH_DENSE_TC, SWITCH_WGRAD_TC, SWITCH_FUSED_HEAD, SWITCH_ALL_TC = range(6)
 
 _lib = None
 
@@ -65,12 +66,16 @@ _SIGNATURES = {
     "d2d_env_obs_dim": (C.c_int, [_P, C.c_int]),
     "d2d_env_state_rows": (C.c_int, [_P]),
     "d2d_env_timestep": (C.c_int, [_P]),
+    "d2d_env_episode": (C.c_int64, [_P]),
+    "d2d_env_set_episode": (C.c_int, [_P, C.c_int64]),
     "d2d_env_record_bytes": (C.c_int, [_P]),
     "d2d_env_mask_bytes": (C.c_int, [_P]),
     "d2d_env_set_replay": (C.c_int, [_P, _P, _P, C.c_int]),
     "d2d_env_reset": (C.c_int, [_P, _P, _P, _P]),
     "d2d_env_step": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, _P]),
     "d2d_env_step_random_access": (C.c_int, [_P, C.c_double, _P, _P, _P, _P, _P, _P, _P]),
+    "d2d_env_run_random_access": (C.c_int, [_P, C.c_double, C.c_int, C.c_int, _P, C.c_int64, _P, C.c_int64, _P, C.c_int64,
+                                            C.c_int, _P, _P, C.POINTER(C.c_int)]),
     "d2d_env_step_host": (C.c_int, [_P, _P, C.c_int, _P, _P, _P, _P, _P, _P, C.POINTER(C.c_uint64)]),
     "d2d_env_host_wait": (C.c_int, [_P, C.c_uint64]),
     "d2d_pack_actions": (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_int, _P]),
@@ -84,6 +89,9 @@ _SIGNATURES = {
     "d2d_net_tensor": (C.c_int, [_P, C.c_int, C.c_int, C.POINTER(C.c_int64), C.POINTER(C.c_int32),
                                  C.POINTER(C.c_int32)]),
     "d2d_net_forward": (C.c_int, [_P, _P, _P, C.c_int, C.c_int, C.c_int, C.c_int, _P, _P]),
+    "d2d_net_check_inputs": (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_int, _P, _P]),
+    "d2d_set_kernel_switch": (C.c_int, [C.c_int, C.c_int]),
+    "d2d_get_kernel_switch": (C.c_int, [C.c_int]),
     "d2d_net_rollout_step": (C.c_int, [_P, _P, _P, C.c_int, C.c_int, _P, _P]),
     "d2d_policy_head": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _P, _P, _P, _P, _P,
                                   C.c_uint64, C.c_uint64, C.c_int, _P]),
@@ -129,6 +137,11 @@ def check(code):
     if code != OK:
         raise D2DError(code, lib().d2d_last_error().decode("utf-8", "replace"))
     return code
+
+
+def set_kernel_switch(which: int, enabled: bool) -> None:
+    """A/B and debugging control of the kernel families (d2d_set_kernel_switch); process-wide."""
+    check(lib().d2d_set_kernel_switch(int(which), int(bool(enabled))))
 
 
 def launch_count() -> int:

@@ -61,12 +61,22 @@ class PPOBase:
                                policy_lr, scratch_bytes, self._gen, inputs_bf16_exact=self.exact_obs)
         self._act_dtype = action_dtype(self.dist_kind, self.n_actions)
         self._iter = 0
-        T, B, N, dev = self.T, self.B, self.n_agents, self.device
+        # rows of the global batch (all ranks): shards may be unequal (_dist.shard leaves a remainder)
+        rows = torch.tensor([float(self.B * self.T)], dtype=torch.float64, device=self.device)
+        self.rows_global = int(_dist.all_reduce_sum_(rows).item())
         # rollout storage, allocated once: observation blocks lead .. lead + T hold times 0 .. T
-        self.obs_buf = torch.zeros((self.lead + T + 1, self.obs_rows, B), dtype=torch.float32, device=dev)
-        self.act_buf = torch.zeros((T, N, B), dtype=self._act_dtype, device=dev)
-        self.logp_buf = torch.zeros((T, N, B), dtype=torch.float32, device=dev)
-        self.reward_buf = torch.zeros((T, B), dtype=torch.int32, device=dev)
+        self.obs_buf, self.act_buf, self.logp_buf, self.reward_buf = self._new_rollout_storage()
+        # test() rolls out into its OWN storage (allocated on first use): the reference's test() keeps local lists
+        # (d2d_ppo.py:341-383) and train() calls it between the epochs of an iteration (:450), so it must not touch
+        # the rollout the remaining epochs still update on
+        self._eval_storage = None
+
+    def _new_rollout_storage(self):
+        T, B, N, dev = self.T, self.B, self.n_agents, self.device
+        return (torch.zeros((self.lead + T + 1, self.obs_rows, B), dtype=torch.float32, device=dev),
+                torch.zeros((T, N, B), dtype=self._act_dtype, device=dev),
+                torch.zeros((T, N, B), dtype=torch.float32, device=dev),
+                torch.zeros((T, B), dtype=torch.int32, device=dev))
 
     # ------------------------------------------------------------------ checkpoints (d2d_ppo.py:269-277)
     def save(self, checkpoint_path):
@@ -86,62 +96,91 @@ class PPOBase:
         # one Philox stream per (seed, iteration): timestep t and env index key the draws inside an iteration
         return (self.seed * 0x9E3779B97F4A7C15 + self._iter * 0xD1B54A32D192ED03 + 0x2545F4914F6CDD1D) & (2 ** 64 - 1)
 
-    def _act(self, t, mode, forced=None):
+    def _act(self, t, mode, storage, forced=None):
         """select_action for all agents at time t: actions into act_buf[t], log-probs into logp_buf[t]."""
-        logits = self.policies.rollout_step(self.obs_buf, self.lead, t)
+        obs_buf, act_buf, logp_buf, _ = storage
+        logits = self.policies.rollout_step(obs_buf, self.lead, t)
         if forced is not None:
-            self.act_buf[t].copy_(forced)
+            act_buf[t].copy_(forced)
             mode = L.ACT_GIVEN
         policy_head(logits, self.n_agents, self.B, self.n_actions, self.policy_out, self.dist_kind, mode,
-                    self.act_buf[t:t + 1], self.logp_buf[t:t + 1], seed=self._sample_seed(),
+                    act_buf[t:t + 1], logp_buf[t:t + 1], seed=self._sample_seed(),
                     env_offset=self.env.env_offset, t_abs0=t)
 
-    def _run_episode(self, mode, forced_actions=None, state_buf=None, per_step=None):
+    def _run_episode(self, mode, forced_actions=None, state_buf=None, per_step=None, storage=None):
         """One lockstep episode of all B envs.  forced_actions: optional [T, N, B] device-layout actions
-        (teacher forcing for parity runs).  per_step(t) runs after the policy acted and before the env steps."""
+        (teacher forcing for parity runs).  per_step(t) runs after the policy acted and before the env steps.
+        storage: (obs, act, logp, reward) buffers to roll out into; default = the training rollout."""
         env = self.env
-        env.reset_into(self.obs_buf[self.lead], None if state_buf is None else state_buf[0])
+        training = storage is None
+        if training:
+            storage = (self.obs_buf, self.act_buf, self.logp_buf, self.reward_buf)
+        obs_buf, act_buf, _, reward_buf = storage
+        env.reset_into(obs_buf[self.lead], None if state_buf is None else state_buf[0])
         for t in range(self.T):
-            self._act(t, mode, None if forced_actions is None else forced_actions[t])
+            self._act(t, mode, storage, None if forced_actions is None else forced_actions[t])
             if per_step is not None:
                 per_step(t)
-            done = env.step_into(self.act_buf[t], self.obs_buf[self.lead + t + 1],
-                                 None if state_buf is None else state_buf[t + 1], self.reward_buf[t])
+            done = env.step_into(act_buf[t], obs_buf[self.lead + t + 1],
+                                 None if state_buf is None else state_buf[t + 1], reward_buf[t])
         assert done
-        self._iter += 1
+        if training:
+            self._iter += 1                 # a fresh sampling stream per training rollout; test() is greedy
         return env.compute_urllc()          # score per episode: 1 - discarded / received (d2d_ppo.py:329)
 
     # ------------------------------------------------------------------ evaluation (d2d_ppo.py:341-383)
-    def test(self, num_episodes):
-        """Greedy rollouts.  Runs ceil(num_episodes / B) lockstep batches and averages over every episode run.
-        Returns (mean URLLC score, mean Jain index, total channel errors, mean per-episode reward sum)."""
-        batches = max(1, -(-int(num_episodes) // self.B))
-        scores, jains, rewards, errors = [], [], [], 0
-        for _ in range(batches):
-            s = self._run_episode(L.ACT_GREEDY)
-            scores.append(s)
-            jains.append(self.env.compute_jains())
-            rewards.append(self.reward_buf.to(torch.float64).sum(0))     # reward.mean() over identical agents
+    def test(self, num_episodes, forced_actions=None):
+        """Greedy rollouts of exactly ``num_episodes`` episodes (split over the ranks; a rank runs its share as
+        ceil(share / B) lockstep batches and counts only the first ``share`` episodes).  Returns the reference's
+        4-tuple: (mean URLLC score, mean Jain index, total channel errors, mean per-episode sum of the
+        agent-mean reward).  Rolls out into evaluation-only storage: the training rollout is left untouched."""
+        share = _dist.shard(int(num_episodes))[1]
+        if self._eval_storage is None:
+            self._eval_storage = self._new_rollout_storage()
+        reward_buf = self._eval_storage[3]
+        dev = self.device
+        stats = torch.zeros(5, dtype=torch.float64, device=dev)
+        left = share
+        while left > 0:
+            n = min(left, self.B)
+            s = self._run_episode(L.ACT_GREEDY if forced_actions is None else L.ACT_GIVEN, forced_actions,
+                                  storage=self._eval_storage)
             ce = self.env.channel_errors
-            errors += int(ce.sum().item()) if torch.is_tensor(ce) else int(ce) * self.B
-        stats = torch.stack([torch.cat(scores).sum(), torch.cat(jains).sum(), torch.cat(rewards).sum(),
-                             torch.tensor(float(errors), dtype=torch.float64, device=self.device),
-                             torch.tensor(float(batches * self.B), dtype=torch.float64, device=self.device)])
+            ce = ce[:n].to(torch.float64).sum() if torch.is_tensor(ce) else \
+                torch.tensor(float(ce) * n, dtype=torch.float64, device=dev)
+            stats += torch.stack([s[:n].sum(), self.env.compute_jains()[:n].sum(),
+                                  reward_buf[:, :n].to(torch.float64).sum(),     # reward.mean() over equal copies
+                                  ce, torch.tensor(float(n), dtype=torch.float64, device=dev)])
+            left -= n
         _dist.all_reduce_sum_(stats)
-        n = stats[4].item()
+        n = max(stats[4].item(), 1.0)
         return stats[0].item() / n, stats[1].item() / n, int(stats[3].item()), stats[2].item() / n
 
     # ------------------------------------------------------------------ helpers shared by the train loops
     def _norm_stats(self, stats, cols, ddof):
         """mean / std / normalise-flags from (all-reduced) [n_cols, 4] sums; the reference normalises only if
-        EVERY column has a positive std (d2d_ppo.py:108, :122)."""
-        n = float(self.B * self.T * _dist.world_size())
+        EVERY column has a positive std (d2d_ppo.py:108, :122).  numpy / torch compute the std two-pass, so a
+        constant column gives exactly 0 there; the one-pass (sum, sum of squares) form leaves rounding noise of the
+        order 1e-16 * n * mean^2 instead, hence the gate is relative to the column's mean square."""
+        n = float(self.rows_global)
         mean = stats[:, cols[0]] / n
+        meansq = stats[:, cols[1]] / n
         var = (stats[:, cols[1]] - n * mean * mean) / (n - ddof)
         std = var.clamp(min=0).sqrt()
         # stays on the device (no host round trip between the statistics pass and the emit pass)
-        flags = (std > 0).all().to(torch.int32).expand(stats.shape[0]).contiguous()
+        flags = (var > 1e-9 * meansq).all().to(torch.int32).expand(stats.shape[0]).contiguous()
         return mean.contiguous(), std.contiguous(), flags
+
+    def _guard_exact_inputs(self):
+        """The tensor-core GRU window stages observations as ONE bf16 plane, which is exact for the integer-valued
+        observations of CombinatorialEnv / D2DEnv (``exact_obs``).  Checked on every collected rollout: a wrong flag
+        would silently truncate the inputs to 8 significant bits.  The count is read where the caller synchronises
+        anyway (scores.tolist())."""
+        if self.exact_obs and self.useRNN:
+            bad = int(self.policies.count_inexact_inputs(self.obs_buf, self.lead, 0, self.T + 1).item())
+            if bad:
+                raise RuntimeError(f"{bad} observation values are not exactly representable in bf16 although the env "
+                                   f"declares integer-valued observations: the tensor-core GRU path would truncate them")
 
     def _check_episodes(self, num_episodes):
         if num_episodes is not None and int(num_episodes) != self.B:

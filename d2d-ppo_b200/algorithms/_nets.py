@@ -144,6 +144,15 @@ class NetSet:
                                                    L.ptr(out), L.current_stream()))
         return out
 
+    def count_inexact_inputs(self, x, x_lead, t0, t1):
+        """Device u64 scalar: inputs of time blocks [t0, t1) that are not exactly representable in bf16 (the guard of
+        ``inputs_bf16_exact``, d2d_net_check_inputs)."""
+        out = torch.zeros(1, dtype=torch.int64, device=self.device)
+        with torch.cuda.device(self.device):
+            L.check(self._lib.d2d_net_check_inputs(self._h, L.ptr(x), int(x_lead), int(t0), int(t1), L.ptr(out),
+                                                   L.current_stream()))
+        return out
+
     def zero_grad(self):
         self.grads.zero_()
 

@@ -48,12 +48,11 @@ class CombinatorialRandomAccess:
         tot = torch.zeros(6, dtype=torch.float64, device=env.device)
         for _ in range(batches):
             env.reset(with_state=False)
-            rew = torch.zeros(B, dtype=torch.float64, device=env.device)
-            done = False
-            while not done:
-                _, _, r, done, _ = env.step_random_access(self.transmission_prob, with_obs=False, with_state=False)
-                r = torch.as_tensor(r, device=env.device)
-                rew += (r.reshape(B, -1)[:, 0] if r.dim() > 0 else r).to(torch.float64)
+            # the whole episode in one library call: steps enqueued back to back, rewards summed on the device
+            rew = torch.zeros(B, dtype=torch.int32, device=env.device)
+            steps = env.run_random_access(self.transmission_prob, env.episode_length, out_reward=rew, accumulate=True)
+            assert steps == env.episode_length
+            rew = rew.to(torch.float64)
             disc = torch.as_tensor(env.discarded_packets, device=env.device).to(torch.float64).sum()
             recv = torch.as_tensor(env.received_packets, device=env.device).to(torch.float64).sum()
             jains = torch.as_tensor(env.compute_jains(), device=env.device, dtype=torch.float64).sum()

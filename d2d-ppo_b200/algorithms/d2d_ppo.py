@@ -41,6 +41,7 @@ class D2DPPO(PPOBase):
         self.ret_buf = returns_emit(self.reward_buf, None, self.gamma, 0.97, last, None,
                                     self._norm_stats(stats, (2, 3), ddof=1))[1][:, 0, :]
         dones = [t == self.T - 1 for t in range(self.T)]
+        self._guard_exact_inputs()
         return (self.obs_buf[self.lead:], self.state_buf[:self.T], self.act_buf, self.logp_buf, self.reward_buf,
                 self.ret_buf, scores, dones)
 
@@ -49,7 +50,7 @@ class D2DPPO(PPOBase):
         """One epoch for the agent order ``cycle`` (default: a fresh shuffle).  Returns ([N] policy losses in
         cycle order, value loss)."""
         N, T, dev = self.n_agents, self.T, self.device
-        rows = self.B * T * _dist.world_size()
+        rows = self.rows_global
         if cycle is None:
             cycle = np.arange(N)
             self._np_rng.shuffle(cycle)

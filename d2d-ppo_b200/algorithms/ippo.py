@@ -44,6 +44,7 @@ class iPPO(PPOBase):
                                                   norm_a, norm_r, getattr(self, "adv_buf", None),
                                                   getattr(self, "ret_buf", None))
         dones = [t == self.T - 1 for t in range(self.T)]
+        self._guard_exact_inputs()
         return (self.obs_buf[self.lead:], self.act_buf, self.logp_buf, self.ret_buf, self.value_buf, self.adv_buf,
                 scores, dones)
 
@@ -51,7 +52,7 @@ class iPPO(PPOBase):
     def update_epoch(self, cliprange=0.1, beta=0.01):
         """One epoch: every agent's policy step, then its critic step.  Returns ([N] policy losses, [N] value
         losses) as host lists."""
-        rows = self.B * self.T * _dist.world_size()
+        rows = self.rows_global
         dev = self.device
         sums = torch.zeros((self.n_agents, 2), dtype=torch.float64, device=dev)
         self.policies.zero_grad()

@@ -142,7 +142,7 @@ __global__ void __launch_bounds__(256, 4) comb_step_kernel(const StepArgs a) {
       int8_t* q = reinterpret_cast<int8_t*>(a.ack) + b;
       for (int c = 0; c < C; ++c) q[(size_t)c * B] = (int8_t)((int)((acked >> c) & 1u) - (int)((nacked >> c) & 1u));
     }
-    a.reward[b] = n_success;                                      // :211
+    a.reward[b] = (a.reward_accum ? a.reward[b] : 0) + n_success;  // :211
     if (a.done) a.done[b] = (uint8_t)a.done_flag;                 // :233-236
   }
 }

@@ -49,6 +49,7 @@ struct StepArgs {
   int act_mode;  // 0 = actions from memory, 1 = fused random-access policy
   uint32_t tp_thr;
   int done_flag;
+  int reward_accum;  // 1: reward[b] += this step's reward (d2d_env_run_random_access), 0: overwrite
 };
 
 __device__ __forceinline__ const EnvParamsHdr* stage_params(const StepArgs& a, uint8_t* smem) {

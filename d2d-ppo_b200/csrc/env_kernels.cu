@@ -161,7 +161,7 @@ __global__ void __launch_bounds__(256) sc_step_kernel(const StepArgs a) {
         *o = (float)ack;
       }
     }
-    a.reward[b] = ack;                                          // :191 rewards = zeros(N) + ack
+    a.reward[b] = (a.reward_accum ? a.reward[b] : 0) + ack;     // :191 rewards = zeros(N) + ack
     if (a.done) a.done[b] = (uint8_t)a.done_flag;
   }
 }
@@ -304,7 +304,7 @@ __global__ void __launch_bounds__(256) sel_step_kernel(const StepArgs a) {
       if (a.ack) reinterpret_cast<float*>(a.ack)[(size_t)c * B + b] = v;
       if (a.state) a.state[((size_t)P->sum_dl + c) * B + b] = (float)((ch_new >> c) & 1u);             // :186
     }
-    a.reward[b] = n_success;                                     // :188
+    a.reward[b] = (a.reward_accum ? a.reward[b] : 0) + n_success;  // :188
     if (a.done) a.done[b] = (uint8_t)a.done_flag;
   }
 }
@@ -401,6 +401,7 @@ struct d2d_env {
   uint64_t seed, env_offset;
   int D, W, CB;  // max deadline, words per record, bytes per channel mask element
   int t;
+  long long episode = -1;   // index of the current episode (number of resets - 1): folded into the Philox counter
   bool is_reset;
   std::vector<int> deadlines, obs_off, obs_dim;
   std::vector<uint64_t> active;
@@ -595,6 +596,12 @@ extern "C" int d2d_env_state_rows(const d2d_env* e) { return e ? e->state_rows :
 extern "C" int d2d_env_timestep(const d2d_env* e) { return e ? e->t : D2D_ERR_INVALID; }
 extern "C" int d2d_env_record_bytes(const d2d_env* e) { return e ? e->W * 4 : D2D_ERR_INVALID; }
 extern "C" int d2d_env_mask_bytes(const d2d_env* e) { return e ? e->CB : D2D_ERR_INVALID; }
+extern "C" int64_t d2d_env_episode(const d2d_env* e) { return e ? e->episode : D2D_ERR_INVALID; }
+extern "C" int d2d_env_set_episode(d2d_env* e, int64_t next_episode) {
+  D2D_REQUIRE(e && next_episode >= 0, "d2d_env_set_episode: null env or negative episode index");
+  e->episode = next_episode - 1;   // the next reset() starts episode `next_episode`
+  return D2D_OK;
+}
 
 extern "C" int d2d_env_set_replay(d2d_env* e, const uint8_t* arrivals, const void* switches, int t_len) {
   D2D_REQUIRE(e, "d2d_env_set_replay: null env");
@@ -608,7 +615,10 @@ static int fill_args(d2d_env* e, StepArgs& a, uint32_t t, const char* who) {
   memset(&a, 0, sizeof(a));
   a.buf = e->buf, a.chan = e->chan, a.disc = e->disc, a.recv = e->recv, a.stats = e->stats;
   a.params = e->params, a.params_bytes = e->params_bytes;
-  a.B = e->B, a.t = t, a.k0 = (uint32_t)(e->seed & 0xFFFFFFFFull), a.k1 = (uint32_t)(e->seed >> 32);
+  // Philox streams: the counter's timestep field is t + episode * (T + 1), so that every episode of an env draws
+  // fresh traffic (replayed streams, arrival phases and the done flag use the plain episode timestep)
+  const uint32_t t_ctr = t + (uint32_t)((unsigned long long)std::max<long long>(e->episode, 0) * (unsigned)(e->T + 1));
+  a.B = e->B, a.t = t_ctr, a.k0 = (uint32_t)(e->seed & 0xFFFFFFFFull), a.k1 = (uint32_t)(e->seed >> 32);
   for (int r = 0; r < 10; ++r) a.rk0[r] = a.k0 + (uint32_t)r * 0x9E3779B9u, a.rk1[r] = a.k1 + (uint32_t)r * 0xBB67AE85u;
   a.env_offset = (uint32_t)e->env_offset, a.active = e->active[t], a.rng_mode = e->rng_mode;
   a.done_flag = (int)t >= e->T;
@@ -632,8 +642,12 @@ static int launch_env(K kernel, const StepArgs& a, int params_bytes, void* strea
 extern "C" int d2d_env_reset(d2d_env* e, float* obs, float* state, void* stream) {
   D2D_REQUIRE(e, "d2d_env_reset: null env");
   StepArgs a;
+  e->episode += 1;
   int rc = fill_args(e, a, 0u, "d2d_env_reset");
-  if (rc) return rc;
+  if (rc) {
+    e->episode -= 1;
+    return rc;
+  }
   a.obs = obs, a.state = state;
   if (e->kind == D2D_ENV_COMBINATORIAL) {
 #define D2D_RESET_CASE(WW, MT) rc = launch_env(comb_reset_kernel<WW, MT>, a, e->params_bytes, stream)
@@ -722,6 +736,46 @@ extern "C" int d2d_env_step_random_access(d2d_env* e, double tp, void* actions_o
   return env_step_impl(e, a, stream);
 }
 
+// n_steps fused random-access steps enqueued back to back by the library: the inner loop of
+// CombinatorialRandomAccess.run (algorithms/baselines.py:199-213) without a host round trip per step
+extern "C" int d2d_env_run_random_access(d2d_env* e, double tp, int n_steps, int auto_reset, float* obs,
+                                         int64_t obs_step_stride, float* state, int64_t state_step_stride,
+                                         int32_t* reward, int64_t reward_step_stride, int reward_accumulate,
+                                         uint8_t* done, void* stream, int* steps_done) {
+  D2D_REQUIRE(e && reward && n_steps >= 0, "d2d_env_run_random_access: null env / reward or negative n_steps");
+  D2D_REQUIRE(e->kind != D2D_ENV_CHANNEL_SELECTION,
+              "d2d_env_run_random_access: the reference defines no random-access policy for the selection env");
+  D2D_REQUIRE(tp >= 0.0 && tp <= 1.0, "d2d_env_run_random_access: transmission_prob must be in [0, 1]");
+  D2D_REQUIRE(!(reward_accumulate && reward_step_stride != 0),
+              "d2d_env_run_random_access: reward_accumulate sums into ONE i32 [B] buffer (reward_step_stride 0)");
+  if (steps_done) *steps_done = 0;
+  if (!e->is_reset) {
+    if (!auto_reset) {
+      set_error("d2d_env_run_random_access: reset() has not been called");
+      return D2D_ERR_STATE;
+    }
+  }
+  const uint32_t tp_thr = (uint32_t)std::min(65536.0, std::max(0.0, std::floor(tp * 65536.0 + 0.5)));
+  for (int i = 0; i < n_steps; ++i) {
+    float* obs_i = obs ? obs + (size_t)i * obs_step_stride : nullptr;
+    float* state_i = state ? state + (size_t)i * state_step_stride : nullptr;
+    if (!e->is_reset || e->t >= e->T) {
+      if (!auto_reset) break;               // episode over: the caller resets (as the reference's loop does)
+      // the reset's observation goes to the slot of the step that follows and is overwritten by it
+      int rc = d2d_env_reset(e, obs_i ? obs_i : nullptr, state_i, stream);
+      if (rc) return rc;
+    }
+    StepArgs a;
+    int rc = fill_args(e, a, (uint32_t)(e->t + 1), "d2d_env_run_random_access");
+    if (rc) return rc;
+    a.obs = obs_i, a.state = state_i, a.reward = reward + (size_t)i * reward_step_stride, a.done = done;
+    a.act_mode = 1, a.tp_thr = tp_thr, a.reward_accum = reward_accumulate ? 1 : 0;
+    if ((rc = env_step_impl(e, a, stream))) return rc;
+    if (steps_done) *steps_done = i + 1;
+  }
+  return D2D_OK;
+}
+
 extern "C" int d2d_pack_actions(const uint8_t* src, void* dst, int B, int N, int C, void* stream) {
   D2D_REQUIRE(src && dst && B > 0 && N > 0 && C > 0 && C <= D2D_MAX_CHANNELS, "d2d_pack_actions: bad argument");
   const int block = 256, grid = grid_for((long long)B * N, block);
@@ -781,7 +835,9 @@ extern "C" int d2d_env_step_host(d2d_env* e, const void* actions_host, int layou
               "d2d_env_step_host: D2D_ACT_HOST_REFERENCE is defined for the combinatorial env only");
   const bool need_pack = comb && layout == D2D_ACT_HOST_REFERENCE;
   cudaStream_t s = as_stream(stream);
-  // 1. host -> device on the copy-in stream, once the step of call k - 2 has consumed this slot
+  // 1. host -> device on the copy-in stream, once the step of call k - 2 has consumed this slot.  The copy is NOT
+  //    ordered after the caller's stream (that would serialise it behind the previous call's step and lose the
+  //    copy / compute overlap): actions_host must be complete on the host when the call is made (d2d_b200.h)
   if (reused) D2D_CUDA(cudaStreamWaitEvent(p->h2d, p->step_done[slot], 0));
   void* dst = need_pack ? (void*)p->stage[slot] : p->masks[slot];
   const size_t bytes = need_pack ? nb * e->C : nb * (comb ? e->CB : 1);

@@ -54,26 +54,22 @@ static View make_view(float* p, long long t_stride, int t_off, int N, int feat_p
   return v;
 }
 
-// D2D_DISABLE_TCGEN05=1 keeps every GEMM on the FP32 CUDA-core kernels (A/B comparison, debugging)
-// per-kernel A/B switches: D2D_NO_GRUTC / D2D_NO_BWDTC / D2D_NO_DENSETC / D2D_NO_WGRADTC = 1 route that GEMM family to
-// its FP32 CUDA-core kernel (read once per process)
-enum { kSwGruTc = 0, kSwBwdTc, kSwDenseTc, kSwWgradTc, kSwCount };
-static bool switched_off(int which) {
-  static int cache[kSwCount] = {-1, -1, -1, -1};
-  static const char* names[kSwCount] = {"D2D_NO_GRUTC", "D2D_NO_BWDTC", "D2D_NO_DENSETC", "D2D_NO_WGRADTC"};
-  if (cache[which] < 0) {
-    const char* e = getenv(names[which]);
-    cache[which] = (e && e[0] == '1') ? 1 : 0;
-  }
-  return cache[which] != 0;
+// Kernel-family switches (d2d_set_kernel_switch in the C ABI): an A/B and debugging control set explicitly by the
+// caller -- the library reads no environment variables.  A family that is switched off runs on its FP32 CUDA-core
+// kernel.  Not thread-safe; set before the first launch.
+enum { kSwGruTc = D2D_SWITCH_GRU_WINDOW_TC, kSwBwdTc = D2D_SWITCH_GRU_BPTT_TC, kSwDenseTc = D2D_SWITCH_DENSE_TC,
+       kSwWgradTc = D2D_SWITCH_WGRAD_TC, kSwFusedHead = D2D_SWITCH_FUSED_HEAD, kSwAllTc = D2D_SWITCH_ALL_TC, kSwCount };
+static int g_switch_off[kSwCount] = {0, 0, 0, 0, 0, 0};
+static bool switched_off(int which) { return g_switch_off[which] != 0; }
+static bool tc_enabled() { return g_switch_off[kSwAllTc] == 0; }
+
+extern "C" int d2d_set_kernel_switch(int which, int enabled) {
+  D2D_REQUIRE(which >= 0 && which < kSwCount, "d2d_set_kernel_switch: unknown kernel family %d", which);
+  g_switch_off[which] = enabled ? 0 : 1;
+  return D2D_OK;
 }
-static bool tc_enabled() {
-  static int disabled = -1;
-  if (disabled < 0) {
-    const char* e = getenv("D2D_DISABLE_TCGEN05");
-    disabled = (e && e[0] == '1') ? 1 : 0;
-  }
-  return !disabled;
+extern "C" int d2d_get_kernel_switch(int which) {
+  return (which >= 0 && which < kSwCount) ? (g_switch_off[which] ? 0 : 1) : D2D_ERR_INVALID;
 }
 
 template <int RPT, int OPT>
@@ -325,12 +321,7 @@ static void launch_head_fused_t(const HeadFusedArgs& a, int N, int tiles, cudaSt
 }
 
 static bool head_fused_eligible(const d2d_net* n) {
-  static int disabled = -1;
-  if (disabled < 0) {
-    const char* e = getenv("D2D_DISABLE_FUSED_HEAD");
-    disabled = (e && e[0] == '1') ? 1 : 0;
-  }
-  return !disabled && n->arch == D2D_NET_GRU && (n->H == 32 || n->H == 64) && n->O <= 16;
+  return !switched_off(kSwFusedHead) && n->arch == D2D_NET_GRU && (n->H == 32 || n->H == 64) && n->O <= 16;
 }
 
 static int launch_head_fused(const d2d_net* n, const float* params, const View& h, float* y1, const View& out, int t0,
@@ -761,6 +752,25 @@ extern "C" int d2d_net_forward(d2d_net* n, const float* params, const float* x, 
     if ((rc = forward_chunk(n, params, x, x_lead, c0, c1, padded, false, c, s))) return rc;
     D2D_CUDA(cudaMemcpyAsync(out + (long long)(c0 - t0) * per_t, c.logits, (size_t)(c1 - c0) * per_t * 4,
                              cudaMemcpyDeviceToDevice, s));
+  }
+  return D2D_OK;
+}
+
+// Guard of the `inputs_bf16_exact` promise (d2d_net_config): the tensor-core GRU window stages the observations as ONE
+// bf16 plane (the top 16 bits of the fp32 word), so an input with more than 8 significant bits would silently be
+// truncated.  Counts such inputs over time blocks [t0, t1) of every agent's rows.
+extern "C" int d2d_net_check_inputs(const d2d_net* n, const float* x, int x_lead, int t0, int t1,
+                                    unsigned long long* n_inexact, void* stream) {
+  D2D_REQUIRE(n && x && n_inexact && t1 > t0 && x_lead + t0 >= 0, "d2d_net_check_inputs: bad argument");
+  cudaStream_t s = as_stream(stream);
+  D2D_CUDA(cudaMemsetAsync(n_inexact, 0, sizeof(unsigned long long), s));
+  for (int g = 0; g < n->N; ++g) {
+    const long long count = (long long)n->in_dim[g] * n->B;
+    const float* base = x + ((long long)(x_lead + t0) * n->in_rows + n->in_off[g]) * n->B;
+    check_bf16_exact_kernel<<<dim3(grid_for(count, 256, 4096), t1 - t0), 256, 0, s>>>(base, count,
+                                                                                       (long long)n->in_rows * n->B,
+                                                                                       n_inexact);
+    D2D_LAUNCHED();
   }
   return D2D_OK;
 }

@@ -531,4 +531,15 @@ __global__ void adam_kernel(const AdamArgs a) {
   }
 }
 
+// inputs_bf16_exact guard: elements of x whose low 16 mantissa bits are not all zero (grid.y = time block)
+__global__ void check_bf16_exact_kernel(const float* x, long long count, long long t_stride,
+                                        unsigned long long* n_inexact) {
+  const float* p = x + (long long)blockIdx.y * t_stride;
+  unsigned int bad = 0;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += (long long)gridDim.x * blockDim.x)
+    bad += (__float_as_uint(p[i]) & 0xFFFFu) != 0u;
+  bad = __reduce_add_sync(0xFFFFFFFFu, bad);
+  if ((threadIdx.x & 31) == 0 && bad) atomicAdd(n_inexact, (unsigned long long)bad);
+}
+
 }  // namespace d2d

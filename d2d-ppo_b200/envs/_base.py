@@ -85,6 +85,7 @@ class LockstepEnv:
             if is_bern:
                 bern[k] = _rng.bernoulli_thr32(arrival_probs[k])
             else:
+                _rng.check_poisson_rate(lbdas[k], f"lbdas[{k}]")
                 cdf[k] = _rng.poisson_cdf_table(lbdas[k])
         active = np.array([self._active_mask(t) for t in range(T + 1)], dtype=np.uint64)
         sw = np.ascontiguousarray([_rng.bernoulli_thr16(p) for p in np.asarray(switch_probs, dtype=np.float64).ravel()],
@@ -155,6 +156,16 @@ class LockstepEnv:
             except Exception:
                 pass
             self._h = None
+
+    # ------------------------------------------------------------------ episode index of the Philox streams
+    @property
+    def episode(self):
+        """Index of the current episode (-1 before the first reset).  Every reset starts a fresh Philox stream."""
+        return int(self._lib.d2d_env_episode(self._h))
+
+    def set_episode(self, next_episode):
+        """The next reset() starts episode ``next_episode`` (resume a run, or reproduce a given episode)."""
+        L.check(self._lib.d2d_env_set_episode(self._h, int(next_episode)))
 
     # ------------------------------------------------------------------ replay streams (parity runs)
     def set_replay(self, arrivals, switches):
@@ -229,6 +240,28 @@ class LockstepEnv:
 
     def _new_ack(self):
         return None
+
+    def run_random_access(self, transmission_prob, n_steps, *, auto_reset=False, out_obs=None, obs_stride=0,
+                          out_state=None, state_stride=0, out_reward=None, reward_stride=0, accumulate=False):
+        """``n_steps`` fused random-access steps enqueued by the library in one call (d2d_env_run_random_access):
+        the inner loop of ``CombinatorialRandomAccess.run`` (baselines.py:199-213) without a Python round trip per
+        step.  out_obs / out_state: env-minor blocks, step i writes at element offset i * stride (stride 0: the same
+        block every step; None: not emitted).  out_reward int32: [B] (stride 0; ``accumulate=True`` adds every
+        step's reward into it) or [n_steps, B] with reward_stride = B.  auto_reset: reset whenever an episode ends
+        (or before the first step); otherwise the run stops at the end of the episode.  Returns the steps run."""
+        if out_reward is None:
+            out_reward = torch.zeros(self.n_envs, dtype=torch.int32, device=self.device)
+            self.last_run_reward = out_reward
+        done = torch.empty(self.n_envs, dtype=torch.uint8, device=self.device)
+        n_done = C.c_int(0)
+        with torch.cuda.device(self.device):
+            L.check(self._lib.d2d_env_run_random_access(
+                self._h, float(transmission_prob), int(n_steps), int(bool(auto_reset)), L.ptr(out_obs),
+                int(obs_stride), L.ptr(out_state), int(state_stride), L.ptr(out_reward), int(reward_stride),
+                int(bool(accumulate)), L.ptr(done), L.current_stream(), C.byref(n_done)))
+        self.timestep = int(self._lib.d2d_env_timestep(self._h))
+        self.done_tensor = done
+        return int(n_done.value)
 
     # ------------------------------------------------------------------ host-buffer step (pipelined copies)
     def step_host(self, host_actions, host_reward, *, layout="reference", host_done=None, with_obs=True,

@@ -99,6 +99,14 @@ int d2d_env_obs_dim(const d2d_env* env, int agent);     /* observation_space[k].
 int d2d_env_state_rows(const d2d_env* env);             /* state_space.shape[0]             */
 int d2d_env_timestep(const d2d_env* env);
 
+/* Episode index of the Philox streams.  The reference draws fresh traffic in every episode from numpy's global
+ * generator (combinatorial_env.py:68,117,180); here every reset() starts episode e = (number of resets - 1) and the
+ * Philox counter's timestep field is t + e * (episode_length + 1), so consecutive episodes of an env are
+ * independent.  d2d_env_set_episode makes the NEXT reset() start episode `next_episode` (checkpoint / resume,
+ * reproducing a given episode); d2d_env_episode returns the current one (-1 before the first reset). */
+int64_t d2d_env_episode(const d2d_env* env);
+int d2d_env_set_episode(d2d_env* env, int64_t next_episode);
+
 /* Replay streams (device, borrowed until the next set_replay/destroy):
  *   arrivals  u8 [t_len][N][B]           value device k would draw at timestep t (0 = reset)
  *   switches  combinatorial: mask [t_len][N][B], element = 1/2/4 bytes for C <= 8/16/32, bit c = flip
@@ -128,6 +136,23 @@ int d2d_env_step(d2d_env* env, const void* actions, float* obs, float* state, in
 int d2d_env_step_random_access(d2d_env* env, double transmission_prob, void* actions_out, float* obs,
                                float* state, int32_t* reward, uint8_t* done, void* ack, void* stream);
 
+/* n_steps steps of d2d_env_step_random_access enqueued back to back by the library: the inner loop of
+ * CombinatorialRandomAccess.run (algorithms/baselines.py:199-213) without one host call per step (at 8 ranks the
+ * per-step Python -> C launch path, not the GPU, bounded short runs).
+ *   auto_reset        1: an env that is not reset, or whose episode is over, is reset before the next step (the
+ *                     reset's observation lands in that step's obs slot and is overwritten by the step);
+ *                     0: the run stops at the end of the episode, as the reference's `while not done` loop
+ *   obs / state       f32 [..][obs_rows][B] / [..][state_rows][B]: step i writes at + i * *_step_stride floats
+ *                     (stride 0: every step overwrites the same block); NULL: not emitted
+ *   reward            i32: step i writes reward + i * reward_step_stride ([B] each); with reward_accumulate = 1
+ *                     (stride 0) every step ADDS its reward into the one [B] buffer (zero it first): the
+ *                     per-episode reward sum of baselines.py:211
+ *   done              u8 [B] of the last step (may be NULL);  *steps_done (may be NULL): steps actually run     */
+int d2d_env_run_random_access(d2d_env* env, double transmission_prob, int n_steps, int auto_reset, float* obs,
+                              int64_t obs_step_stride, float* state, int64_t state_step_stride, int32_t* reward,
+                              int64_t reward_step_stride, int reward_accumulate, uint8_t* done, void* stream,
+                              int* steps_done);
+
 /* pack reference-layout actions u8 [B][N][C] (0/1) into the bitmask layout above */
 int d2d_pack_actions(const uint8_t* actions_bnc, void* packed, int n_envs, int n_agents, int n_channels,
                      void* stream);
@@ -141,7 +166,9 @@ int d2d_pack_actions(const uint8_t* actions_bnc, void* packed, int n_envs, int n
  *   obs / state / ack: DEVICE pointers as in d2d_env_step (may be NULL)
  * The call is asynchronous and pipelined: the H2D copy runs on the handle's copy-in stream, pack + step on
  * `stream`, the D2H copy on the copy-out stream, so consecutive calls overlap.  Up to two calls are in flight;
- * actions_host must stay untouched until the call's step ran (d2d_env_host_wait of the same ticket suffices).
+ * actions_host must be COMPLETE ON THE HOST when the call is made (the copy-in stream is deliberately not ordered
+ * after `stream`: a caller that fills actions_host with asynchronous work must synchronise that work first) and
+ * must stay untouched until the call's step ran (d2d_env_host_wait of the same ticket suffices).
  * *ticket (may be NULL) identifies the call; d2d_env_host_wait(env, ticket) blocks the host thread until
  * reward_host / done_host of that call are valid. */
 #define D2D_ACT_HOST_REFERENCE 0
@@ -227,6 +254,25 @@ int d2d_net_tensor(const d2d_net* net, int agent, int index, int64_t* offset, in
  *   out     f32 [t1 - t0][N][O][B]                                                                           */
 int d2d_net_forward(d2d_net* net, const float* params, const float* x, int x_lead, int t0, int t1, int padded,
                     float* out, void* stream);
+
+/* Guard of the inputs_bf16_exact promise: counts the inputs of time blocks [t0, t1) (all agents' rows) that are NOT
+ * exactly representable in bf16, into *n_inexact (device, u64).  The learners run it over every rollout they
+ * collect and refuse to train on a non-zero count: a wrong flag would otherwise silently truncate the observations
+ * to 8 significant bits in the tensor-core GRU window. */
+int d2d_net_check_inputs(const d2d_net* net, const float* x, int x_lead, int t0, int t1,
+                         unsigned long long* n_inexact, void* stream);
+
+/* Kernel-family switches: A/B comparison and debugging (the library reads no environment variables).  A family that
+ * is switched off (enabled = 0) runs on its FP32 CUDA-core kernel; D2D_SWITCH_ALL_TC = 0 keeps every GEMM off the
+ * tensor cores.  Process-wide, not thread-safe: set before the first launch.  Default: everything enabled. */
+#define D2D_SWITCH_GRU_WINDOW_TC 0
+#define D2D_SWITCH_GRU_BPTT_TC 1
+#define D2D_SWITCH_DENSE_TC 2
+#define D2D_SWITCH_WGRAD_TC 3
+#define D2D_SWITCH_FUSED_HEAD 4
+#define D2D_SWITCH_ALL_TC 5
+int d2d_set_kernel_switch(int which, int enabled);
+int d2d_get_kernel_switch(int which);
 
 /* Rollout step (PPO.select_action's network call, d2d_ppo.py:302-303): forward of the single time block t on
  * the UNPADDED window.  The input projections of the previous L - 1 observations are kept in a ring inside the

@@ -108,8 +108,20 @@ class PhiloxSource:
         self.seed = seed
         self.env_level = env_level_switch
         self._cdf = {}
+        self.episode, self.episode_length = -1, None
+
+    def begin_episode(self, episode_length):
+        """Every reset() starts a fresh stream: the counter's timestep field is t + episode * (T + 1)
+        (csrc/env_kernels.cu: fill_args), so episode e of an env does not replay episode 0's traffic."""
+        self.episode += 1
+        self.episode_length = int(episode_length)
+
+    def ctr_t(self, t):
+        """Timestep field of the Philox counter for env timestep t of the current episode."""
+        return (int(t) + max(self.episode, 0) * (self.episode_length + 1 if self.episode_length else 0)) & 0xFFFFFFFF
 
     def arrival(self, t, dev, kind, traffic):
+        t = self.ctr_t(t)
         u = px.word32(self.seed, self.env, t, dev, px.PURPOSE_ARRIVAL)
         if kind == "poisson":
             lam = float(traffic.lbdas[dev])
@@ -119,6 +131,7 @@ class PhiloxSource:
         return (u.astype(np.uint64) < np.uint64(px.thr32(traffic.arrival_probs[dev]))).astype(np.int64)
 
     def switch(self, t, p):
+        t = self.ctr_t(t)
         p = np.asarray(p, dtype=np.float64)
         if self.env_level:  # ChannelSelectionEnv: one vector of C+1 channels per env
             lanes = px.lanes16(self.seed, self.env, t, px.ENV_LEVEL_DEVICE, px.PURPOSE_SWITCH, p.shape[0])
@@ -152,6 +165,8 @@ class _BufferEnv:
 
     def _reset_buffers(self):
         self.timestep = 0
+        if hasattr(self.source, "begin_episode"):
+            self.source.begin_episode(self.episode_length)
         self.buffers = np.zeros((self.B, self.n_agents, self.D), dtype=np.int64)
         for dev, kind in self.traffic.draws(0):
             self.buffers[:, dev, self.deadlines[dev] - 1] = self.source.arrival(0, dev, kind, self.traffic)

@@ -206,6 +206,12 @@ def main(argv):
     if "ppo" in what:
         from . import gen_golden_ppo
         gen_golden_ppo.main()
+    if "ppo_round2" in what:          # only the fixtures added in round 2 (the earlier files stay byte-identical)
+        from . import gen_golden_ppo
+        gen_golden_ppo.main(("round2",))
+    if "ppo_e256" in what:
+        from . import gen_golden_ppo
+        gen_golden_ppo.main(("e256",))
 
 
 if __name__ == "__main__":

@@ -14,6 +14,7 @@ Restated (file:line under /root/reference):
 * ``lambda_returns``                <- ``compute_gae`` d2d_ppo.py:100-110 (numpy float64, population std)
 * ``discounted_returns``            <- ``discount_rewards`` d2d_ppo.py:112-124 (float64 scan, fp32 unbiased std)
 * ``ippo_train_step`` / ``d2dppo_epoch`` <- ippo.py:194-217, d2d_ppo.py:198-216 and :413-446
+* ``greedy_test``                   <- ``test`` d2d_ppo.py:341-383, ippo.py:345-388 (greedy rollout, 4-tuple)
 
 Row order: the reference concatenates episodes along axis 0 (row = e * T + t); B lockstep envs running one
 episode each ARE ``num_episodes = B``.  Every function below takes rows in that episode-major order.
@@ -257,3 +258,36 @@ def d2dppo_epoch(pols, opts, critic, opt_c, xs, valids, states, actions, logp_ol
     opt_c.step(g)
     critic.update(opt_c.p)
     return losses, float(vloss.detach())
+
+
+# ----------------------------------------------------------------------------------------------
+# evaluation
+# ----------------------------------------------------------------------------------------------
+def greedy_test(pols, env, arch, combinatorial, history_len):
+    """``test(num_episodes)`` (d2d_ppo.py:341-383): greedy rollouts (probs > 0.5 per channel, or argmax) of the B
+    lockstep episodes of the oracle env ``env`` (= num_episodes = B).  Returns (actions [B*T, N(, C)] episode-major,
+    (mean URLLC score, mean Jain index, sum of channel errors, mean per-episode sum of reward.mean()))."""
+    B, N, T = env.B, env.n_agents, env.episode_length
+    obs, _ = env.reset()
+    hist = [[torch.tensor(np.asarray(obs[i]), dtype=torch.float32)] for i in range(N)]
+    acts, rew_sum = [], np.zeros(B)
+    done = False
+    while not done:
+        step_actions = []
+        for i in range(N):
+            if arch == "gru":
+                x = torch.stack(hist[i][-history_len:], dim=1)                  # unpadded window (d2d_ppo.py:361)
+            else:
+                x = hist[i][-1]
+            probs = net_forward(pols[i], x, policy_out_kind(arch, combinatorial))
+            step_actions.append((probs > 0.5).to(torch.int64) if combinatorial else probs.argmax(1))
+        a = torch.stack(step_actions, dim=1).numpy()                            # [B, N(, C)]
+        obs, _, reward, done, _ = env.step(a)
+        for i in range(N):
+            hist[i].append(torch.tensor(np.asarray(obs[i]), dtype=torch.float32))
+        acts.append(a)
+        rew_sum += np.asarray(reward, dtype=np.float64).mean(1)
+    acts = np.stack(acts, axis=1).reshape((B * T,) + acts[0].shape[1:])
+    errors = int(np.sum(getattr(env, "channel_errors", 0)))
+    return acts, (float(np.mean(env.compute_urllc())), float(np.mean(env.compute_jains())), errors,
+                  float(np.mean(rew_sum)))

@@ -338,3 +338,66 @@ def test_full_size_conservation_and_determinism(cuda_device):
         u = env.compute_urllc()
         assert float(u.min()) >= 0.0 and float(u.max()) <= 1.0
     assert sums[0] == sums[1]
+
+
+@pytest.mark.parametrize("name", ["comb_c3_load0.33", "d2d_c2", "sel_xp_gamma"])
+def test_philox_episodes_are_independent_and_match_oracle(name, cuda_device):
+    """Every reset() starts a fresh Philox stream (counter timestep field t + episode * (T + 1)): three consecutive
+    episodes match the oracle bit for bit, differ from each other, and set_episode() reproduces a given episode."""
+    from oracle.envs_np import PhiloxSource
+    from oracle.gen_golden import draw_actions
+    g = load_env_case(name)
+    kind, kw = g["kind"], dict(g["config"])
+    kw["episode_length"] = 12
+    B, T = 64, 12
+    act = draw_actions(kind, kw, B, T, 0.3, np.random.default_rng(1))
+    env = make_cuda_env(kind, kw, B, rng="philox", seed=77, env_offset=3, device=cuda_device)
+    orc = make_oracle(kind, kw, B, PhiloxSource(B, 77, env_offset=3, env_level_switch=(kind == "channel_selection")))
+    received = []
+    for episode in range(3):
+        _rollout_against_oracle(env, orc, kind, act, check_every=4)
+        assert env.episode == episode
+        received.append(to_np(env.received_packets).copy())
+    assert not np.array_equal(received[0], received[1]) and not np.array_equal(received[1], received[2])
+    env.set_episode(1)
+    env.reset()
+    for t in range(T):
+        env.step(act[t])
+    assert env.episode == 1 and np.array_equal(to_np(env.received_packets), received[1])
+
+
+@pytest.mark.parametrize("name", ["comb_c3_load0.33", "d2d_c2"])
+def test_run_random_access_equals_stepwise(name, cuda_device):
+    """d2d_env_run_random_access (steps enqueued by the library) == the same steps issued one call at a time:
+    observations, states, per-step rewards, counters, across an automatic reset; reward accumulation."""
+    import torch
+    g = load_env_case(name)
+    kind, kw = g["kind"], dict(g["config"])
+    kw["episode_length"] = T = 9
+    B, tp, n = 200, 0.3, 2 * T + 4
+    a = make_cuda_env(kind, kw, B, rng="philox", seed=5, device=cuda_device)
+    b = make_cuda_env(kind, kw, B, rng="philox", seed=5, device=cuda_device)
+    R, S = a.obs_layout[0], a.state_space.shape[0]
+    obs = torch.zeros((n, R, B), device=cuda_device)
+    state = torch.zeros((n, S, B), device=cuda_device)
+    rew = torch.zeros((n, B), dtype=torch.int32, device=cuda_device)
+    assert a.run_random_access(tp, n, auto_reset=True, out_obs=obs, obs_stride=R * B, out_state=state,
+                               state_stride=S * B, out_reward=rew, reward_stride=B) == n
+    for i in range(n):
+        if i % T == 0:
+            b.reset()
+        _, _, r, done, _ = b.step_random_access(tp)
+        assert torch.equal(obs[i], b.obs_rows_tensor) and torch.equal(state[i], b.state_rows_tensor), i
+        assert torch.equal(rew[i].to(r.dtype), r[:, 0]), i
+        assert done == ((i + 1) % T == 0)
+    assert a.timestep == b.timestep == n - 2 * T and a.episode == b.episode == 2
+    assert np.array_equal(to_np(a.received_packets), to_np(b.received_packets))
+    assert np.array_equal(to_np(a.discarded_packets), to_np(b.discarded_packets))
+    # without auto_reset the run stops at the end of the episode; accumulate sums the rewards of the steps run
+    a.reset()
+    acc = torch.zeros(B, dtype=torch.int32, device=cuda_device)
+    assert a.run_random_access(tp, T + 5, out_reward=acc, accumulate=True) == T
+    b.reset()
+    tot = sum(b.step_random_access(tp)[2][:, 0].to(torch.int32) for _ in range(T))
+    assert torch.equal(acc, tot)
+    assert a.run_random_access(tp, 3, out_reward=acc, accumulate=True) == 0

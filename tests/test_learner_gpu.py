@@ -367,3 +367,112 @@ def test_tensor_core_training_path_vs_autograd(H, Lh, E, T, I, C, exact, cuda_de
         for (name, _), gr in zip(vp.items(), torch.autograd.grad(vloss, list(vp.values()))):
             assert rel_err(val.tensor_view(val.grads, i, name), gr) < 2e-5, ("value", i, name)
         assert abs(vsum[i].item() / R - float(vloss.detach())) <= 1e-5 * max(1.0, float(vloss.detach()))
+
+
+def _categorical_grad_check(pol, x, lead, E, T, N, O, obs, acts, logp_old, weight, Lh, arch, dev, what):
+    """ppo_dlogits_kernel, Categorical branch (d2d_ppo.py:171-179,191-194 feeding train_step :198-216): surrogate
+    gradients of all agents in one launch against torch autograd on the oracle."""
+    from d2d_ppo_b200 import _lib as L
+    from _helpers import report_err
+    R = E * T
+    actions = acts.long().reshape(E, T, N).permute(1, 2, 0).contiguous().to(torch.uint8).to(dev)
+
+    def em(a):
+        return torch.as_tensor(a, dtype=torch.float32).reshape(E, T, N).permute(1, 2, 0).contiguous().to(dev)
+    sums = torch.zeros((N, 2), dtype=torch.float64, device=dev)
+    pol.zero_grad()
+    pol.policy_grad(x, lead, 0, T, L.DIST_CATEGORICAL, actions, em(logp_old), em(weight), 1, None, 1.0 / R, 0.1, 0.01,
+                    sums)
+    for i in range(N):
+        pp = {k: v.clone().requires_grad_(True) for k, v in pol.state_dict(i).items()}
+        xi, valid = (obs[:, i], None) if arch == "mlp" else P.windows(obs[:, i], T, Lh, True)
+        probs = P.net_forward(pp, xi, "softmax", valid)
+        loss, _ = P.surrogate(probs, acts[:, i], torch.as_tensor(logp_old[:, i]), torch.as_tensor(weight[:, i]), False,
+                              0.1, 0.01)
+        for (name, _), gr in zip(pp.items(), torch.autograd.grad(loss, list(pp.values()))):
+            err = report_err(f"{what}/grad/agent{i}/{name}", pol.tensor_view(pol.grads, i, name), gr)
+            # 2e-5 norm-wise; windows of 10 steps (xp_gamma.py) compound the 16-bit d(gh) operand of the BPTT kernel
+            # over more steps: measured 2.05e-5 on one bias vector, bound 3e-5
+            assert err < (3e-5 if Lh >= 10 else 2e-5), (what, i, name, err)
+        mine_loss = -(sums[i, 0].item() / R) - 0.01 * sums[i, 1].item() / R
+        assert abs(mine_loss - float(loss.detach())) <= 1e-5 * max(1.0, abs(float(loss.detach())))
+
+
+@pytest.mark.parametrize("case", ["ippo_d2denv_gru", "ippo_selenv_gru", "d2dppo_d2denv_gru", "d2dppo_d2denv_mlp",
+                                  "d2dppo_selenv_mlp"])
+def test_categorical_policy_gradients_reference_rollouts(case, cuda_device):
+    """Categorical PPO backward on the reference's own rollouts (D2DPPO / iPPO on D2DEnv and ChannelSelectionEnv,
+    through the thin wrapper env of SURVEY.md 8c(3)): initial reference weights, recorded observations, actions and
+    old log-probs; weights = the reference's advantages (iPPO) or the fixture's returns (D2DPPO)."""
+    g = load_ppo_case(case)
+    m = g["meta"]
+    N, arch, E, T, H, Lh = m["N"], m["arch"], m["E"], m["T"], m["hidden"], m["L"]
+    I = g["obs"].shape[2]
+    O = 2 if m["kind"] == "d2d" else g["config"]["n_channels"] + 1
+    lead = Lh - 1 if arch == "gru" else 0
+    x = _env_minor(g["obs"].reshape(E * T, N * I), E, T, lead, cuda_device)
+    exact = m["kind"] == "d2d"            # the selection env's 1/count acks are not exact in bf16
+    pol = _netset(cuda_device, arch, "softmax", N, E, [I] * N, [k * I for k in range(N)], N * I, H, O, Lh, exact=exact)
+    for i in range(N):
+        pol.load_state_dict(i, params_from(g, f"init/policy{i}"))
+    weight = g["advantages"] if "advantages" in g else np.repeat(g["returns"][:, None], N, 1)
+    _categorical_grad_check(pol, x, lead, E, T, N, O, torch.tensor(g["obs"]), torch.tensor(g["actions"]),
+                            g["logp_old"], weight.astype(np.float32), Lh, arch, cuda_device, case)
+
+
+@pytest.mark.parametrize("H,Lh,E,T,I,O,exact", [(64, 4, 260, 5, 9, 2, True), (64, 10, 256, 4, 24, 17, False),
+                                                (32, 3, 136, 6, 12, 5, True), (64, 1, 384, 3, 24, 17, False)])
+def test_categorical_tensor_core_training_path_vs_autograd(H, Lh, E, T, I, O, exact, cuda_device):
+    """Categorical (softmax) policies on the tcgen05 training kernels (>= 256 rows per time block, several tiles,
+    ragged last tile) with random weights: the shapes of config c2 (2 actions) and of xp_gamma.py (17 actions,
+    fractional observations -> FP32 forward feeding the tcgen05 BPTT kernel)."""
+    from d2d_ppo_b200 import _lib as L
+    from d2d_ppo_b200.algorithms._nets import policy_head
+    N = 3
+    torch.manual_seed(H * 100 + O)
+    gen = torch.Generator().manual_seed(H * 100 + Lh + O)
+    obs = torch.randint(-1, 4, (E * T, N, I), generator=gen).float()
+    if not exact:
+        obs = obs + torch.randint(0, 4, obs.shape, generator=gen).float() / 3.0
+    acts = torch.randint(0, O, (E * T, N), generator=gen)
+    adv = torch.randn(E * T, N, generator=gen)
+    lead = Lh - 1
+    x = _env_minor(obs.reshape(E * T, N * I).numpy(), E, T, lead, cuda_device)
+    pol = _netset(cuda_device, "gru", "softmax", N, E, [I] * N, [k * I for k in range(N)], N * I, H, O, Lh, exact=exact)
+    actions = acts.reshape(E, T, N).permute(1, 2, 0).contiguous().to(torch.uint8).to(cuda_device)
+    logits = pol.forward(x, lead, 0, T, padded=1)
+    logp = torch.empty((T, N, E), device=cuda_device)
+    policy_head(logits, N, E, O, L.OUT_SOFTMAX, L.DIST_CATEGORICAL, L.ACT_GIVEN, actions, logp)
+    noise = 0.05 * torch.randn(E * T, N, generator=gen).reshape(E, T, N).permute(1, 2, 0).contiguous().to(cuda_device)
+    logp_old = logp + noise
+    ratio = torch.exp(logp - logp_old)
+    near = ((ratio - 0.9).abs() < 2e-3) | ((ratio - 1.1).abs() < 2e-3)     # keep rows away from the clip kinks
+    logp_old = torch.where(near, logp_old + 0.01, logp_old)
+    _categorical_grad_check(pol, x, lead, E, T, N, O, obs, acts, _rows(logp_old), adv.numpy(), Lh, "gru", cuda_device,
+                            f"categorical_H{H}_L{Lh}_O{O}")
+
+
+def test_inputs_bf16_exact_guard_and_kernel_switches(cuda_device):
+    """d2d_net_check_inputs counts inputs that one bf16 plane cannot hold; the learners refuse such a rollout.
+    d2d_set_kernel_switch moves a kernel family to its FP32 kernel: same results within the parity tolerance."""
+    from d2d_ppo_b200 import _lib as L
+    E, T, I, H, Lh = 256, 3, 12, 32, 2
+    net = _netset(cuda_device, "gru", "sigmoid", 1, E, [I], [0], I, H, 4, Lh, exact=True)
+    x = torch.randint(-2, 5, (Lh - 1 + T, I, E), device=cuda_device).float()
+    x[:Lh - 1] = 0
+    assert int(net.count_inexact_inputs(x, Lh - 1, 0, T).item()) == 0
+    y = x.clone()
+    y[Lh, 3, 7] = 1.0 / 3.0
+    y[Lh + 1, 0, 200] = 1.00001
+    assert int(net.count_inexact_inputs(y, Lh - 1, 0, T).item()) == 2
+    assert int(net.count_inexact_inputs(y, Lh - 1, 0, 1).item()) == 0          # only the blocks asked for
+    ref = net.forward(x, Lh - 1, 0, T, padded=1).clone()
+    assert L.lib().d2d_get_kernel_switch(L.SWITCH_ALL_TC) == 1
+    L.set_kernel_switch(L.SWITCH_ALL_TC, False)
+    try:
+        fp32 = net.forward(x, Lh - 1, 0, T, padded=1).clone()
+    finally:
+        L.set_kernel_switch(L.SWITCH_ALL_TC, True)
+    assert not torch.equal(ref, fp32) and rel_err(ref, fp32) < 1e-5
+    with pytest.raises(L.D2DError):
+        L.set_kernel_switch(99, True)

@@ -61,11 +61,28 @@ def _inputs(g, arch, i, pad):
     return P.windows(obs, m["T"], m["L"], pad)
 
 
-@pytest.mark.parametrize("tag", ["small_gru", "small_mlp", "c3_gru"])
+def _adam_tol(tag):
+    return dict(min_tight=0.99, loose_frac=2e-3) if "e256" in tag else {}
+
+
+IPPO_CASES = ["small_gru", "small_mlp", "c3_gru", "d2denv_gru", "selenv_gru", "c3_e256"]
+D2DPPO_CASES = ["small_gru", "small_mlp", "c3_gru", "d2denv_gru", "d2denv_mlp", "selenv_mlp", "c3_e256"]
+
+
+def _replay_oracle(g, first, count):
+    """The numpy oracle env replaying episodes [first, first + count) of a learner fixture's streams."""
+    from _helpers import make_oracle
+    from oracle.envs_np import ReplaySource
+    kind = g["meta"].get("kind", "combinatorial")
+    src = ReplaySource(g["arrivals"][:, first:first + count], g["switches"][:, first:first + count])
+    return make_oracle(kind, g["config"], count, src)
+
+
+@pytest.mark.parametrize("tag", IPPO_CASES)
 def test_ippo_iteration(tag):
     g = load_ppo_case(f"ippo_{tag}")
     m = g["meta"]
-    N, arch = m["N"], m["arch"]
+    N, arch, comb = m["N"], m["arch"], m.get("combinatorial", True)
     actions = torch.tensor(g["actions"]).float()
     dones = list(g["dones"])
     # rollout quantities: log-probs from UNPADDED windows, values, then lambda-returns / returns per agent column
@@ -73,18 +90,16 @@ def test_ippo_iteration(tag):
     for i in range(N):
         pol, val = params_from(g, f"init/policy{i}"), params_from(g, f"init/value{i}")
         x, valid = _inputs(g, arch, i, pad=False)
-        probs = P.net_forward(pol, x, P.policy_out_kind(arch, True), valid)
-        logp, _ = P.logp_entropy(probs, actions[:, i], True)
+        probs = P.net_forward(pol, x, P.policy_out_kind(arch, comb), valid)
+        logp, _ = P.logp_entropy(probs, actions[:, i], comb)
         assert rel_err(logp, g["logp_old"][:, i]) < TOL
         values.append(P.net_forward(val, x, "identity", valid).squeeze(-1))
     values = torch.stack(values, 1)
     assert rel_err(values, g["values"]) < TOL
     # reward = number of successful devices, identical for all agents; recover it from the env replay
-    from _helpers import make_oracle
-    from oracle.envs_np import ReplaySource
-    env = make_oracle("combinatorial", g["config"], m["E"], ReplaySource(g["arrivals"], g["switches"]))
+    env = _replay_oracle(g, 0, m["E"])
     env.reset()
-    acts = g["actions"].reshape(m["E"], m["T"], N, -1)
+    acts = g["actions"].reshape((m["E"], m["T"]) + g["actions"].shape[1:])
     rew = np.stack([env.step(acts[:, t])[2] for t in range(m["T"])], axis=1).reshape(m["E"] * m["T"], N)
     adv = P.lambda_returns(rew, dones, g["values"], m["gamma"], 0.97)
     ret = P.discounted_returns(rew, m["gamma"], dones)
@@ -99,18 +114,31 @@ def test_ippo_iteration(tag):
         for i in range(N):
             x, valid = _inputs(g, arch, i, pad=True)
             pl, vl = P.ippo_train_step(pols[i], vals[i], opt_p[i], opt_v[i], x, valid, actions[:, i], logp_old[:, i],
-                                       ret[:, i], adv[:, i], arch, True)
+                                       ret[:, i], adv[:, i], arch, comb)
         assert rel_err(pl, g["policy_loss"][epoch]) < 1e-4 and rel_err(vl, g["value_loss"][epoch]) < 1e-4
     for i in range(N):
-        assert_params_close(pols[i], params_from(g, f"final/policy{i}"), params_from(g, f"init/policy{i}"), f"policy{i}")
-        assert_params_close(vals[i], params_from(g, f"final/value{i}"), params_from(g, f"init/value{i}"), f"value{i}")
+        assert_params_close(pols[i], params_from(g, f"final/policy{i}"), params_from(g, f"init/policy{i}"), f"policy{i}", **_adam_tol(tag))
+        assert_params_close(vals[i], params_from(g, f"final/value{i}"), params_from(g, f"init/value{i}"), f"value{i}", **_adam_tol(tag))
+    _check_greedy_test(g, "ippo")
 
 
-@pytest.mark.parametrize("tag", ["small_gru", "small_mlp", "c3_gru"])
+def _check_greedy_test(g, algo):
+    """The reference's test() with the updated policies on the fixture's extra replayed episodes."""
+    m = g["meta"]
+    if not m.get("E_test"):
+        return
+    pols = [params_from(g, f"final/policy{i}") for i in range(m["N"])]
+    env = _replay_oracle(g, m["E"], m["E_test"])
+    acts, res = P.greedy_test(pols, env, m["arch"], m.get("combinatorial", True), m["L"])
+    assert np.array_equal(acts.astype(np.uint8), g["test_actions"])
+    assert np.allclose(res, g["test_result"], rtol=1e-12, atol=1e-12), (res, g["test_result"])
+
+
+@pytest.mark.parametrize("tag", D2DPPO_CASES)
 def test_d2dppo_iteration(tag):
     g = load_ppo_case(f"d2dppo_{tag}")
     m = g["meta"]
-    N, arch = m["N"], m["arch"]
+    N, arch, comb = m["N"], m["arch"], m.get("combinatorial", True)
     actions = torch.tensor(g["actions"]).float()
     dones = list(g["dones"])
     logp_old = torch.tensor(g["logp_old"])
@@ -118,7 +146,7 @@ def test_d2dppo_iteration(tag):
     critic = params_from(g, "init/critic")
     for i in range(N):
         x, valid = _inputs(g, arch, i, pad=False)
-        logp, _ = P.logp_entropy(P.net_forward(pols[i], x, P.policy_out_kind(arch, True), valid), actions[:, i], True)
+        logp, _ = P.logp_entropy(P.net_forward(pols[i], x, P.policy_out_kind(arch, comb), valid), actions[:, i], comb)
         assert rel_err(logp, g["logp_old"][:, i]) < TOL
     rew = g["rewards_mean"]
     ret = P.discounted_returns(np.repeat(rew[:, None], N, 1), m["gamma"], dones).mean(1)
@@ -129,8 +157,9 @@ def test_d2dppo_iteration(tag):
     states = torch.tensor(g["states"])
     for epoch in range(m["n_epoch"]):
         losses, vl = P.d2dppo_epoch(pols, opts, critic, opt_c, xs, valids, states, actions, logp_old, rew, dones,
-                                    torch.tensor(g["returns"]), list(g["cycles"][epoch]), arch, True, m["gamma"], 0.01)
+                                    torch.tensor(g["returns"]), list(g["cycles"][epoch]), arch, comb, m["gamma"], 0.01)
         assert rel_err(losses, g["policy_loss"][epoch]) < 1e-4 and rel_err(vl, g["value_loss"][epoch]) < 1e-4
     for i in range(N):
-        assert_params_close(pols[i], params_from(g, f"final/policy{i}"), params_from(g, f"init/policy{i}"), f"policy{i}")
-    assert_params_close(critic, params_from(g, "final/critic"), params_from(g, "init/critic"), "critic")
+        assert_params_close(pols[i], params_from(g, f"final/policy{i}"), params_from(g, f"init/policy{i}"), f"policy{i}", **_adam_tol(tag))
+    assert_params_close(critic, params_from(g, "final/critic"), params_from(g, "init/critic"), "critic", **_adam_tol(tag))
+    _check_greedy_test(g, "d2dppo")
