@@ -33,6 +33,7 @@ OBS_DIM = MAX_DEADLINE + 2 * N_CHANNELS
 #   read  buffers D + channel mask 1 + counters 8                      (the action mask is NOT read: fused policy)
 #   write buffers D + channel mask 1 + counters 8 + obs 4(D+2C) + (reward 4 + done 1 + ack C) / N
 ALG_BYTES = (MAX_DEADLINE + 1 + 8) + (MAX_DEADLINE + 1 + 8 + 4 * OBS_DIM + (5 + N_CHANNELS) / N_AGENTS)
+LEAD_IN = 30      # untimed steps enqueued in front of the start event of the timed region (see run_native)
 TP = 0.2          # transmission probability of the random-access policy
 LOAD = 1 / 3      # xp_load.py:53 first load level
 FALLBACK_HBM = 6650.0
@@ -50,6 +51,8 @@ def parse():
     ap.add_argument("--cpu-learner-envs", type=int, default=64, help="envs of the CPU iPPO iteration baseline")
     ap.add_argument("--no-configs", action="store_true", help="skip the c1 / c2 / c4 / selection env-step sections")
     ap.add_argument("--no-learner", action="store_true", help="skip the learned-policy rollout / train SPS sections")
+    ap.add_argument("--learner-sections", default="rollout,gae,train_c3,train_c3_small,train_c2",
+                    help="comma list of the learner sections to run (development runs time one section at a time)")
     ap.add_argument("--rollout-envs", type=int, default=65536, help="envs per GPU of the learned-policy rollout (c3)")
     ap.add_argument("--train-envs", type=int, default=65536,
                     help="envs per GPU of the c3 train-SPS sections (BASELINE config 3 names 65,536)")
@@ -269,15 +272,16 @@ def bench_learner(args, dev, world, rank, barrier, max_over_ranks):
     env = CombinatorialEnv(n_envs=B, device=dev, seed=7, env_offset=rank * B, **kw)
     agent = iPPO(env, hidden_size=64, gamma=0.4, policy_lr=3e-4, value_lr=1e-3, useRNN=True, combinatorial=True,
                  history_len=6, early_stopping=False, seed=1, scratch_bytes=6 << 30)
+    sections = set(args.learner_sections.split(","))
     agent.create_rollouts(B)                                    # warm-up rollout (scratch allocations, clocks)
-    n_roll = 3
+    n_roll = 3 if "rollout" in sections else 1
     dt, launches = timed(lambda: [agent.create_rollouts(B) for _ in range(n_roll)])
     dt, launches = dt / n_roll, launches // n_roll
     flops = 2 * gru_flops_per_agent_step(30, 64, 6, 8) - (2 * 64 * 8 - 2 * 64)   # actor (O=8) + critic (O=1)
     steps = world * B * N_AGENTS * T
     hbm_peak, bf16_peak, peak_src = measured_peaks()
     issued = 2 * gru_tc_issued_flops(32, 64, 6)              # actor + critic windows on the tensor pipe
-    out["rollout_learned"] = {
+    rollout_entry = {
         "metric": "agent-steps/sec (env step + GRU actor + GRU critic, sampled actions, log-probs, values, "
                   "lambda-returns)", "value": steps / dt, "unit": "agent-steps/s", "envs_per_gpu": B,
         "config": "c3: iPPO useRNN=True hidden 64 history_len 6 on CombinatorialEnv setup_8_channels.p",
@@ -298,14 +302,16 @@ def bench_learner(args, dev, world, rank, barrier, max_over_ranks):
                      "fp32_ffma_peak_tflops": FFMA_PEAK_TFLOPS,
                      "peak_source": peak_src + " bf16_tflops_sustained"}}
 
+    if "rollout" in sections:
+        out["rollout_learned"] = rollout_entry
+
     # GAE / returns scans of that rollout: lambda-returns + discounted returns for T x N x B elements, two passes
     # (statistics; normalised fp32 emit), HBM-bound.  Algorithmic bytes per element: SURVEY.md section 8d
     from d2d_ppo_b200.algorithms._nets import returns_emit, returns_stats
 
     def gae_once():
         st = returns_stats(agent.reward_buf, agent.value_buf, 0.4, 0.97, 1)
-        na = agent._norm_stats(st, (0, 1), ddof=0)
-        nr = agent._norm_stats(st, (2, 3), ddof=1)
+        na, nr = agent._norm_stats(st)
         returns_emit(agent.reward_buf, agent.value_buf, 0.4, 0.97, 1, na, nr, agent.adv_buf, agent.ret_buf)
     for _ in range(3):
         gae_once()
@@ -322,7 +328,7 @@ def bench_learner(args, dev, world, rank, barrier, max_over_ranks):
     elems = T * N_AGENTS * B
     alg = 28 + 5 / N_AGENTS
     moved = 2 * (4 + 4 / N_AGENTS) + 8                                  # what the two passes actually read + write
-    out["gae_returns"] = {
+    gae_entry = {
         "metric": "elements/s of compute_gae + discount_rewards + both normalisations (d2d_ppo.py:100-124)",
         "value": elems / (gae_ms * 1e-3), "unit": "(t, agent, env) elements/s", "elements": elems, "ms": gae_ms,
         "l2": "256 MB flush buffer rewritten before every repetition; working set 0.9 GB",
@@ -336,6 +342,8 @@ def bench_learner(args, dev, world, rank, barrier, max_over_ranks):
                              "between the two launches", "kernel": "returns_scan_kernel<1>, <2>",
                      "peak_source": peak_src + " hbm_gbs"}}
     del flush
+    if "gae" in sections:
+        out["gae_returns"] = gae_entry
 
     del agent, env
     torch.cuda.empty_cache()
@@ -403,19 +411,26 @@ def bench_learner(args, dev, world, rank, barrier, max_over_ranks):
 
     # BASELINE config 3 names 65,536 envs: that is the headline train figure; the 4,096-env point is kept beside it
     Bt, Bs = args.train_envs, args.train_envs_small
-    out["train_ippo_c3"] = train_sps(c3_env(8), c3_ippo, Bt, N_AGENTS,
-                                     f"c3: iPPO GRU (H 64, L 6) on CombinatorialEnv setup_8_channels.p, {Bt} envs/GPU",
-                                     iters=1 if Bt > 16384 else 2, nets=(2, 32, 64, 6, [8, 1]))
-    out["train_d2dppo_c3"] = train_sps(c3_env(9), c3_d2dppo, Bt, N_AGENTS,
-                                       f"xp_load.py:78-106: D2DPPO GRU (H 64, L 6, gamma .6) on CombinatorialEnv "
-                                       f"setup_8_channels.p, {Bt} envs/GPU", iters=1 if Bt > 16384 else 2,
-                                       nets=(1, 32, 64, 6, [8]))
+    if "train_c3" not in sections:
+        Bt = 0
+    if "train_c3_small" not in sections:
+        Bs = 0
+    if Bt:
+        out["train_ippo_c3"] = train_sps(c3_env(8), c3_ippo, Bt, N_AGENTS,
+                                         f"c3: iPPO GRU (H 64, L 6) on CombinatorialEnv setup_8_channels.p, {Bt} envs/GPU",
+                                         iters=1 if Bt > 16384 else 2, nets=(2, 32, 64, 6, [8, 1]))
+        out["train_d2dppo_c3"] = train_sps(c3_env(9), c3_d2dppo, Bt, N_AGENTS,
+                                           f"xp_load.py:78-106: D2DPPO GRU (H 64, L 6, gamma .6) on CombinatorialEnv "
+                                           f"setup_8_channels.p, {Bt} envs/GPU", iters=1 if Bt > 16384 else 2,
+                                           nets=(1, 32, 64, 6, [8]))
     if Bs and Bs != Bt:
         out["train_ippo_c3_small"] = train_sps(c3_env(8), c3_ippo, Bs, N_AGENTS,
                                                f"c3 shape at {Bs} envs/GPU (round-1 bench shape)", nets=(2, 32, 64, 6, [8, 1]))
         out["train_d2dppo_c3_small"] = train_sps(c3_env(9), c3_d2dppo, Bs, N_AGENTS,
                                                  f"xp_load.py shape at {Bs} envs/GPU (round-1 bench shape)",
                                                  nets=(1, 32, 64, 6, [8]))
+    if "train_c2" not in sections:
+        return out
     c2 = presets.d2d_c2_kwargs()
     out["train_d2dppo_c2"] = train_sps(
         lambda B: D2DEnv(n_envs=B, device=dev, seed=10, env_offset=rank * B, **c2),
@@ -576,16 +591,29 @@ def run_native(args):
     per = np.array([ev[i].elapsed_time(ev[i + 1]) for i in range(n_probe)])
     kernel_ms = float(np.median(per))             # gaps that contain a reset launch do not move the median
     launches0 = _lib.launch_count()
+    t_at_start = env.timestep
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     t_begin = time.perf_counter()
+    # LEAD_IN untimed steps are enqueued IN FRONT of the start event: while the device works through them the host
+    # enqueues the K timed launches, so the device-side interval [e0, e1] holds exactly K steps and never waits for the
+    # host (a driver-lock hiccup of ~0.5 ms on the first launch after the barrier -- nvidia-smi polls the clocks
+    # concurrently -- cost 12 % of a 20-step window at 2 ranks)
+    run(LEAD_IN)
     e0.record()
     run(K)
     e1.record()
+    host_enqueue_ms = (time.perf_counter() - t_begin) * 1e3
     barrier()
     clocks = sampler.stop(t_begin, time.perf_counter())
-    launches = _lib.launch_count() - launches0
-    n_resets = launches - K
+    launches_all = _lib.launch_count() - launches0
+    # launches inside [e0, e1]: the K steps + the resets that fell between them (the lead-in's are not counted)
+    t_sim, n_resets = t_at_start, 0
+    for i in range(LEAD_IN + K):
+        if t_sim >= T:                           # auto_reset: an episode that is over is reset before the step
+            t_sim, n_resets = 0, n_resets + (i >= LEAD_IN)
+        t_sim += 1
+    launches = K + n_resets
     total_ms = max_over_ranks(e0.elapsed_time(e1))
     launch_ms = total_ms / max(launches, 1)       # average launch duration inside the timed region (resets included)
     value = world * B * N_AGENTS * K / (total_ms * 1e-3)
@@ -694,6 +722,7 @@ def run_native(args):
                                    "d2h_bytes_per_step": B * 4,
                                    "api": "same call with the device action layout (u8 channel bitmask [N,B])"}},
         "gpu_launches": int(launches), "resets_in_timed_region": n_resets, "clocks": clocks,
+        "host_enqueue_ms": host_enqueue_ms, "lead_in_steps": LEAD_IN, "launches_incl_lead_in": int(launches_all),
     }
     del obs_buf, env, host_actions, host_masks
     torch.cuda.empty_cache()

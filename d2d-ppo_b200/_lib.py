@@ -104,6 +104,7 @@ _SIGNATURES = {
                                    _P]),
     "d2d_returns_stats": (C.c_int, [_P, _P, _P, C.c_int, C.c_int, C.c_int, C.c_double, C.c_double, C.c_int, C.c_int,
                                     C.c_int, _P]),
+    "d2d_returns_norm_stats": (C.c_int, [_P, C.c_int, C.c_double, _P, _P, _P, _P, _P, _P, _P]),
     "d2d_returns_emit": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, C.c_int, C.c_int, C.c_int, C.c_double,
                                    C.c_double, C.c_int, _P]),
     "d2d_normalize": (C.c_int, [_P, _P, _P, _P, _P, C.c_int, C.c_int, C.c_int, C.c_int, _P]),

@@ -14,7 +14,7 @@ import torch
 
 from .. import _lib as L
 from . import _dist
-from ._nets import NetSet, action_dtype, policy_head
+from ._nets import NetSet, action_dtype, policy_head, returns_norm_stats
 
 
 class PPOBase:
@@ -157,19 +157,11 @@ class PPOBase:
         return stats[0].item() / n, stats[1].item() / n, int(stats[3].item()), stats[2].item() / n
 
     # ------------------------------------------------------------------ helpers shared by the train loops
-    def _norm_stats(self, stats, cols, ddof):
-        """mean / std / normalise-flags from (all-reduced) [n_cols, 4] sums; the reference normalises only if
-        EVERY column has a positive std (d2d_ppo.py:108, :122).  numpy / torch compute the std two-pass, so a
-        constant column gives exactly 0 there; the one-pass (sum, sum of squares) form leaves rounding noise of the
-        order 1e-16 * n * mean^2 instead, hence the gate is relative to the column's mean square."""
-        n = float(self.rows_global)
-        mean = stats[:, cols[0]] / n
-        meansq = stats[:, cols[1]] / n
-        var = (stats[:, cols[1]] - n * mean * mean) / (n - ddof)
-        std = var.clamp(min=0).sqrt()
-        # stays on the device (no host round trip between the statistics pass and the emit pass)
-        flags = (var > 1e-9 * meansq).all().to(torch.int32).expand(stats.shape[0]).contiguous()
-        return mean.contiguous(), std.contiguous(), flags
+    def _norm_stats(self, stats):
+        """(lambda-return norm, return norm), each (mean, std, flags), from the all-reduced [n_cols, 4] sums: numpy's
+        population std for compute_gae (d2d_ppo.py:108-109), torch's unbiased std for discount_rewards (:121-123); the
+        reference normalises only if EVERY column has a positive std.  One launch, no host round trip."""
+        return returns_norm_stats(stats, self.rows_global)
 
     def _guard_exact_inputs(self):
         """The tensor-core GRU window stages observations as ONE bf16 plane, which is exact for the integer-valued

@@ -224,6 +224,19 @@ def returns_stats(reward, value, gamma, lam, last_shard, want_adv=True, want_ret
     return stats
 
 
+def returns_norm_stats(stats, rows):
+    """(adv (mean, std, flags), ret (mean, std, flags)) from the all-reduced [n_cols, 4] sums and the global row count
+    (d2d_returns_norm_stats: one launch, everything stays on the device)."""
+    n_cols, dev = stats.shape[0], stats.device
+    f = torch.empty((4, n_cols), dtype=torch.float64, device=dev)
+    flags = torch.empty((2, n_cols), dtype=torch.int32, device=dev)
+    with torch.cuda.device(dev):
+        L.check(L.lib().d2d_returns_norm_stats(L.ptr(stats), n_cols, float(rows), L.ptr(f[0]), L.ptr(f[1]),
+                                               L.ptr(flags[0]), L.ptr(f[2]), L.ptr(f[3]), L.ptr(flags[1]),
+                                               L.current_stream()))
+    return (f[0], f[1], flags[0]), (f[2], f[3], flags[1])
+
+
 def returns_emit(reward, value, gamma, lam, last_shard, adv_norm=None, ret_norm=None, adv_out=None, ret_out=None):
     """Pass 2: repeat the scans and write the normalised fp32 lambda-returns / returns [T, n_cols, B].
     adv_norm / ret_norm: (mean, std, flags) of ``PPOBase._norm_stats`` or None to skip that scan."""

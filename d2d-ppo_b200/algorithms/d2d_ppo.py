@@ -39,7 +39,7 @@ class D2DPPO(PPOBase):
         _dist.all_reduce_sum_(stats)
         # discount_rewards on N identical columns, then .mean(1) (d2d_ppo.py:333,339): one column suffices
         self.ret_buf = returns_emit(self.reward_buf, None, self.gamma, 0.97, last, None,
-                                    self._norm_stats(stats, (2, 3), ddof=1))[1][:, 0, :]
+                                    self._norm_stats(stats)[1])[1][:, 0, :]
         dones = [t == self.T - 1 for t in range(self.T)]
         self._guard_exact_inputs()
         return (self.obs_buf[self.lead:], self.state_buf[:self.T], self.act_buf, self.logp_buf, self.reward_buf,
@@ -61,7 +61,7 @@ class D2DPPO(PPOBase):
         stats = returns_stats(self.reward_buf, values, self.gamma, 0.97, last, want_ret=False)
         _dist.all_reduce_sum_(stats)
         M0 = returns_emit(self.reward_buf, values, self.gamma, 0.97, last,
-                          self._norm_stats(stats, (0, 1), ddof=0), None)[0][:, 0, :]                 # [T, B]
+                          self._norm_stats(stats)[0], None)[0][:, 0, :]                 # [T, B]
         sums = torch.zeros((N, 2), dtype=torch.float64, device=dev)
         self.policies.zero_grad()
         self.policies.policy_grad(self.obs_buf, self.lead, 0, T, self.dist_kind, self.act_buf, self.logp_buf, M0, 0,

@@ -38,8 +38,7 @@ class iPPO(PPOBase):
         last = _dist.is_last_shard()
         stats = returns_stats(self.reward_buf, self.value_buf, self.gamma, 0.97, last)
         _dist.all_reduce_sum_(stats)
-        norm_a = self._norm_stats(stats, (0, 1), ddof=0)     # numpy std (ippo.py:100-101)
-        norm_r = self._norm_stats(stats, (2, 3), ddof=1)     # torch std  (ippo.py:114-115)
+        norm_a, norm_r = self._norm_stats(stats)             # numpy std (ippo.py:100-101) / torch std (:114-115)
         self.adv_buf, self.ret_buf = returns_emit(self.reward_buf, self.value_buf, self.gamma, 0.97, last,
                                                   norm_a, norm_r, getattr(self, "adv_buf", None),
                                                   getattr(self, "ret_buf", None))

@@ -985,6 +985,18 @@ extern "C" int d2d_returns_stats(const int32_t* reward, const float* value, doub
   return D2D_OK;
 }
 
+extern "C" int d2d_returns_norm_stats(const double* stats, int n_cols, double rows, double* adv_mean, double* adv_std,
+                                      int32_t* adv_norm, double* ret_mean, double* ret_std, int32_t* ret_norm,
+                                      void* stream) {
+  D2D_REQUIRE(stats && adv_mean && adv_std && adv_norm && ret_mean && ret_std && ret_norm,
+              "d2d_returns_norm_stats: null argument");
+  D2D_REQUIRE(n_cols >= 1 && n_cols <= D2D_MAX_AGENTS && rows >= 2.0, "d2d_returns_norm_stats: bad shape");
+  norm_stats_kernel<<<1, 64, 0, as_stream(stream)>>>(stats, n_cols, rows, adv_mean, adv_std, adv_norm, ret_mean,
+                                                     ret_std, ret_norm);
+  D2D_LAUNCHED();
+  return D2D_OK;
+}
+
 extern "C" int d2d_returns_emit(const int32_t* reward, const float* value, float* adv_out, float* ret_out,
                                 const double* adv_mean, const double* adv_std, const int32_t* adv_norm,
                                 const double* ret_mean, const double* ret_std, const int32_t* ret_norm, int T, int B,

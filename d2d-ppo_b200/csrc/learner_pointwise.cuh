@@ -369,8 +369,7 @@ __global__ void mse_dvalue_kernel(const MseArgs a) {
 // keeps the `r - v` quirk of :102; every other episode end gives out = r exactly (done zeroes the bootstrap).
 // ------------------------------------------------------------------------------------------------
 struct ScanArgs {
-  const int32_t* reward_i;   // [T][B] shared integer reward (number of successes / ack) or null
-  const float* reward_f;     // [T][N][B] per-agent float reward or null
+  const int32_t* reward_i;   // [T][B] integer reward shared by the columns (number of successes / ack)
   const float* value;        // [T][N][B]  (N = n_cols)
   double* adv_raw;           // [T][N][B] out (unnormalised lambda-return), may be null
   double* ret_raw;           // [T][N][B] out (unnormalised discounted return), may be null
@@ -388,67 +387,114 @@ struct ScanArgs {
 
 enum { kScanRaw = 0, kScanStats = 1, kScanEmit = 2 };
 
+// One thread per (column, env) walks the episode backwards in float64 as numpy does.  The chain is serial and short of
+// arithmetic, so the kernel lives on memory-level parallelism and on a lean instruction stream:
+//  * the U rows of the NEXT batch are requested before the current batch is reduced (two register buffers), and the
+//    rewards stay as loaded (int32 / fp32 bits) until they are reduced -- converting at load time waits for the load;
+//  * running row pointers with register strides instead of 64-bit index arithmetic per access (address arithmetic was
+//    40 % of the 141 thread-instructions per element of the first version: ncu opcode mix, profiles/r02_*);
+//  * the episode-end row (t = T - 1) is peeled, the main loop runs whole batches without predicates.
+// Normalisation multiplies by the float64 reciprocal of the std (one division per thread instead of one per element;
+// the result differs from numpy's quotient by at most one float64 ulp BEFORE the cast to fp32).
 template <int MODE>
-__global__ void __launch_bounds__(128, 12) returns_scan_kernel(const ScanArgs a) {
+__global__ void __launch_bounds__(128, 6) returns_scan_kernel(const ScanArgs a) {
   const int g = blockIdx.y;
   const bool do_adv = MODE == kScanRaw ? a.adv_raw != nullptr : (MODE == kScanStats ? a.want_adv : a.adv_out != nullptr);
   const bool do_ret = MODE == kScanRaw ? a.ret_raw != nullptr : (MODE == kScanStats ? a.want_ret : a.ret_out != nullptr);
   double s_adv = 0, q_adv = 0, s_ret = 0, q_ret = 0;
-  double am = 0, as = 1, rm_ = 0, rs_ = 1;
-  bool an = false, rn = false;
+  // "do not normalise" is the identity map (x - 0) * 1, exact in both precisions: no select per element
+  double am = 0.0, a_inv = 1.0;
+  float rmf = 0.f, rsf = 1.f, r_inv = 1.f;
   if (MODE == kScanEmit) {
-    if (do_adv) am = a.adv_mean[g], as = a.adv_std[g], an = a.adv_norm[g] != 0;
-    if (do_ret) rm_ = a.ret_mean[g], rs_ = a.ret_std[g], rn = a.ret_norm[g] != 0;
+    if (do_adv && a.adv_norm[g] != 0) am = a.adv_mean[g], a_inv = 1.0 / a.adv_std[g];
+    if (do_ret && a.ret_norm[g] != 0) rmf = (float)a.ret_mean[g], rsf = (float)a.ret_std[g], r_inv = 1.0f / rsf;
   }
-  const float rmf = (float)rm_, rsf = (float)rs_;
-  constexpr int U = 4;   // time steps loaded per batch: U independent row loads in flight ahead of the serial fp64 chain
-  const long long step = (long long)a.n_cols * a.B;
+  constexpr int U = 8;   // time steps per register buffer
+  const ptrdiff_t B = a.B, step = (ptrdiff_t)a.n_cols * a.B;
+  const double gamma = a.gamma, gl = a.gamma * a.lam;
+  const int T = a.T;
   for (int b = blockIdx.x * blockDim.x + threadIdx.x; b < a.B; b += gridDim.x * blockDim.x) {
+    // running pointers, all starting at the LAST row (t = T - 1) of this (column, env) and walked towards t = 0:
+    // lr / lv feed the loads (one batch ahead), oa / orr the stores
+    const int32_t* lr = a.reward_i + (ptrdiff_t)(T - 1) * B + b;
+    const ptrdiff_t col = ((ptrdiff_t)(T - 1) * a.n_cols + g) * B + b;
+    const float* lv = do_adv ? a.value + col : nullptr;
+    float* oa = (MODE == kScanEmit && do_adv) ? a.adv_out + col : nullptr;
+    float* orr = (MODE == kScanEmit && do_ret) ? a.ret_out + col : nullptr;
+    double* wa = (MODE == kScanRaw && do_adv) ? a.adv_raw + col : nullptr;
+    double* wr = (MODE == kScanRaw && do_ret) ? a.ret_raw + col : nullptr;
     double gae = 0.0, run = 0.0, v_next = 0.0;
-    for (int t_hi = a.T - 1; t_hi >= 0; t_hi -= U) {
-      float rr[U], vv[U];
-      const long long idx_hi = ((long long)t_hi * a.n_cols + g) * a.B + b;
+    auto emit = [&](double out_a, double run_v) {   // writes the row the output pointers stand on, then moves them up
+      if (do_adv) {
+        if (MODE == kScanRaw) *wa = out_a, wa -= step;
+        if (MODE == kScanEmit) __stcs(oa, (float)((out_a - am) * a_inv)), oa -= step;
+        if (MODE != kScanEmit) s_adv += out_a, q_adv += out_a * out_a;
+      }
+      if (do_ret) {
+        if (MODE == kScanRaw) *wr = run_v, wr -= step;
+        const float xf = (float)run_v;               // the reference casts to fp32 before normalising (:119)
+        if (MODE == kScanEmit) {
+          // (xf - mean) / std in fp32, as torch: quotient by Markstein's correction of x * rn(1 / std) (correctly
+          // rounded except for divisors with an all-ones mantissa), 3 FMA-pipe instructions instead of a division
+          const float x = xf - rmf, q = x * r_inv;
+          __stcs(orr, fmaf(fmaf(-q, rsf, x), r_inv, q)), orr -= step;
+        }
+        const double rf = (double)xf;
+        if (MODE != kScanEmit) s_ret += rf, q_ret += rf * rf;
+      }
+    };
+    auto row = [&](int raw, float vf) {              // a row that is not the episode end
+      const double r = (double)raw, v = (double)vf;
+      double out = 0.0;
+      if (do_adv) {
+        const double delta = r + gamma * v_next - v;
+        gae = delta + gl * gae;
+        out = gae + v;
+        v_next = v;
+      }
+      if (do_ret) run = r + run * gamma;
+      emit(out, run);
+    };
+    {   // t = T - 1 (done): delta = r - v, gae = delta, out = gae + v = r; the globally last row keeps r - v (:102)
+      const double r = (double)__ldg(lr), v = do_adv ? (double)__ldg(lv) : 0.0;
+      lr -= B;
+      if (do_adv) lv -= step;
+      const bool quirk = a.last_env_is_global_last && b == a.B - 1;
+      gae = quirk ? 0.0 : r - v;
+      v_next = v;
+      run = r;
+      emit(quirk ? r - v : gae + v, run);
+    }
+    // rows T - 2 .. 0: whole batches of U, double buffered; the rewards stay int32 until they are reduced
+    int rA[U], rB[U];
+    float vA[U], vB[U];
+    auto load = [&](int (&rr)[U], float (&vv)[U]) {
 #pragma unroll
       for (int u = 0; u < U; ++u) {
-        if (t_hi - u >= 0) {
-          rr[u] = a.reward_i ? (float)__ldg(a.reward_i + (long long)(t_hi - u) * a.B + b)
-                             : __ldg(a.reward_f + idx_hi - u * step);
-          vv[u] = do_adv ? __ldg(a.value + idx_hi - u * step) : 0.f;
-        }
+        rr[u] = __ldg(lr), lr -= B;
+        vv[u] = 0.f;
+        if (do_adv) vv[u] = __ldg(lv), lv -= step;
       }
+    };
+    auto reduce = [&](const int (&rr)[U], const float (&vv)[U]) {
 #pragma unroll
-      for (int u = 0; u < U; ++u) {
-        const int t = t_hi - u;
-        if (t < 0) break;
-        const long long idx = idx_hi - u * step;
-        const double r = (double)rr[u];
-        const double v = (double)vv[u];
-        if (do_adv) {
-          double out;
-          if (t == a.T - 1) {
-            // done: delta = r - v, gae = delta, out = gae + v = r;  the globally last row keeps r - v (:102)
-            const bool quirk = a.last_env_is_global_last && b == a.B - 1;
-            gae = quirk ? 0.0 : r - v;
-            out = quirk ? r - v : gae + v;
-          } else {
-            const double delta = r + a.gamma * v_next - v;
-            gae = delta + a.gamma * a.lam * gae;
-            out = gae + v;
-          }
-          v_next = v;
-          if (MODE == kScanRaw) a.adv_raw[idx] = out;
-          if (MODE == kScanEmit) __stcs(a.adv_out + idx, (float)(an ? (out - am) / as : out));
-          if (MODE != kScanEmit) s_adv += out, q_adv += out * out;
-        }
-        if (do_ret) {
-          run = (t == a.T - 1) ? r : r + run * a.gamma;
-          if (MODE == kScanRaw) a.ret_raw[idx] = run;
-          const float xf = (float)run;               // the reference casts to fp32 before normalising (:119)
-          if (MODE == kScanEmit) __stcs(a.ret_out + idx, rn ? (xf - rmf) / rsf : xf);
-          const double rf = (double)xf;
-          if (MODE != kScanEmit) s_ret += rf, q_ret += rf * rf;
-        }
-      }
+      for (int u = 0; u < U; ++u) row(rr[u], vv[u]);
+    };
+    const int n_batches = (T - 1) / U;
+    if (n_batches > 0) load(rA, vA);
+    for (int i = 0; i < n_batches; i += 2) {
+      if (i + 1 < n_batches) load(rB, vB);           // next batch in flight while this one is reduced
+      reduce(rA, vA);
+      if (i + 1 >= n_batches) break;
+      if (i + 2 < n_batches) load(rA, vA);
+      reduce(rB, vB);
+    }
+    for (int k = n_batches * U + 1; k < T; ++k) {    // the (T - 1) % U rows nearest to t = 0
+      const int raw = __ldg(lr);
+      lr -= B;
+      float vf = 0.f;
+      if (do_adv) vf = __ldg(lv), lv -= step;
+      row(raw, vf);
     }
   }
   if (MODE == kScanEmit) return;
@@ -457,6 +503,33 @@ __global__ void __launch_bounds__(128, 12) returns_scan_kernel(const ScanArgs a)
     double v = vals[k];
     for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xFFFFFFFFu, v, o);
     if ((threadIdx.x & 31) == 0 && v != 0.0) atomicAdd(&a.stats[4 * g + k], v);
+  }
+}
+
+// mean / std / normalise-flag of the lambda-returns (numpy population std, d2d_ppo.py:108-109) and of the returns (torch
+// unbiased std, :121-123) from the all-reduced [n_cols][4] sums; one block.  The reference normalises only if EVERY
+// column has a positive std; the one-pass (sum, sum of squares) form leaves rounding noise of the order
+// 1e-16 n mean^2 where numpy / torch give exactly 0, hence the gate is relative to the column's mean square.
+// out: [6][n_cols] doubles = adv mean, adv std, ret mean, ret std, then (as int32 pairs) the two flag vectors.
+__global__ void norm_stats_kernel(const double* __restrict__ stats, int n_cols, double rows, double* adv_mean,
+                                  double* adv_std, int* adv_norm, double* ret_mean, double* ret_std, int* ret_norm) {
+  const int c = threadIdx.x;
+  bool ok_a = true, ok_r = true;
+  double ma = 0, sa = 0, mr = 0, sr = 0;
+  if (c < n_cols) {
+    ma = stats[4 * c] / rows;
+    const double va = (stats[4 * c + 1] - rows * ma * ma) / rows;                 // ddof = 0
+    sa = sqrt(fmax(va, 0.0));
+    ok_a = va > 1e-9 * (stats[4 * c + 1] / rows);
+    mr = stats[4 * c + 2] / rows;
+    const double vr = (stats[4 * c + 3] - rows * mr * mr) / (rows - 1.0);         // ddof = 1
+    sr = sqrt(fmax(vr, 0.0));
+    ok_r = vr > 1e-9 * (stats[4 * c + 3] / rows);
+  }
+  const int all_a = __syncthreads_and(ok_a), all_r = __syncthreads_and(ok_r);
+  if (c < n_cols) {
+    adv_mean[c] = ma, adv_std[c] = sa, adv_norm[c] = all_a;
+    ret_mean[c] = mr, ret_std[c] = sr, ret_norm[c] = all_r;
   }
 }
 
@@ -476,12 +549,13 @@ struct NormArgs {
 __global__ void normalize_kernel(const NormArgs a) {
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < a.n; i += (long long)gridDim.x * blockDim.x) {
     const int g = (int)((i % a.per_t) / a.B);
-    if (a.fp32_math) {
-      const float x = (float)a.raw[i];
-      a.out[i] = a.do_norm[g] ? (x - (float)a.mean[g]) / (float)a.std[g] : x;
-    } else {
+    if (a.fp32_math) {   // the same Markstein quotient as returns_scan_kernel<kScanEmit> (bit-identical results)
+      const float xf = (float)a.raw[i];
+      const float sd = (float)a.std[g], inv = 1.0f / sd, x = xf - (float)a.mean[g], q = x * inv;
+      a.out[i] = a.do_norm[g] ? fmaf(fmaf(-q, sd, x), inv, q) : xf;
+    } else {   // reciprocal multiply, exactly as returns_scan_kernel<kScanEmit> does (bit-identical results)
       const double x = a.raw[i];
-      a.out[i] = (float)(a.do_norm[g] ? (x - a.mean[g]) / a.std[g] : x);
+      a.out[i] = (float)(a.do_norm[g] ? (x - a.mean[g]) * (1.0 / a.std[g]) : x);
     }
   }
 }

@@ -326,6 +326,14 @@ int d2d_adam_step(float* params, float* m, float* v, const float* grads, int n_a
  *   last_shard  1 if this GPU holds the globally last env (its final row keeps the r - v quirk of :102)  */
 int d2d_returns_scan(const int32_t* reward, const float* value, double* adv_raw, double* ret_raw, double* stats,
                      int T, int n_envs, int n_cols, double gamma, double lam, int last_shard, void* stream);
+/* Normalisation statistics from the (all-reduced over ranks) [n_cols][4] sums of d2d_returns_stats and the global row
+ * count: lambda-returns with numpy's population std (d2d_ppo.py:108-109), returns with torch's unbiased std
+ * (:121-123); *_norm = 1 iff EVERY column has a positive std (the reference's `.all()` gate), tested relative to the
+ * column's mean square (var > 1e-9 mean(x^2)) because the one-pass sums leave rounding noise where numpy / torch give
+ * an exact 0.  All outputs are device arrays of n_cols elements; one tiny launch, no host round trip. */
+int d2d_returns_norm_stats(const double* stats, int n_cols, double rows, double* adv_mean, double* adv_std,
+                           int32_t* adv_norm, double* ret_mean, double* ret_std, int32_t* ret_norm, void* stream);
+
 /* The same scans in two passes without fp64 intermediates in HBM (17 B per element instead of 45):
  * d2d_returns_stats accumulates `stats` only (want_adv / want_ret select the scans); after the caller has
  * reduced the statistics over ranks, d2d_returns_emit repeats the scans and writes the NORMALISED results
