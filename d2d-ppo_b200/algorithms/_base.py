@@ -70,6 +70,7 @@ class PPOBase:
         # (d2d_ppo.py:341-383) and train() calls it between the epochs of an iteration (:450), so it must not touch
         # the rollout the remaining epochs still update on
         self._eval_storage = None
+        self._logits = torch.empty((1, self.n_agents, self.n_actions, self.B), dtype=torch.float32, device=self.device)
 
     def _new_rollout_storage(self):
         T, B, N, dev = self.T, self.B, self.n_agents, self.device
@@ -99,7 +100,7 @@ class PPOBase:
     def _act(self, t, mode, storage, forced=None):
         """select_action for all agents at time t: actions into act_buf[t], log-probs into logp_buf[t]."""
         obs_buf, act_buf, logp_buf, _ = storage
-        logits = self.policies.rollout_step(obs_buf, self.lead, t)
+        logits = self.policies.rollout_step(obs_buf, self.lead, t, out=self._logits)
         if forced is not None:
             act_buf[t].copy_(forced)
             mode = L.ACT_GIVEN

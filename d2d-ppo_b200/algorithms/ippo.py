@@ -31,9 +31,10 @@ class iPPO(PPOBase):
         values [T, N, B], advantages [T, N, B], scores [B], dones [T] bools) -- device tensors, env-minor."""
         self._check_episodes(num_episodes)
 
-        def critic(t):    # agent.value_network(history) on the UNPADDED rollout window (ippo.py:305)
-            out = self.values.rollout_step(self.obs_buf, self.lead, t)
-            self.value_buf[t].copy_(out[0, :, 0, :])
+        N, B = self.n_agents, self.B
+
+        def critic(t):    # agent.value_network(history) on the UNPADDED rollout window (ippo.py:305), written in place
+            self.values.rollout_step(self.obs_buf, self.lead, t, out=self.value_buf[t].view(1, N, 1, B))
         scores = self._run_episode(L.ACT_SAMPLE, forced_actions, per_step=critic)
         last = _dist.is_last_shard()
         stats = returns_stats(self.reward_buf, self.value_buf, self.gamma, 0.97, last)

@@ -13,6 +13,7 @@ namespace d2d {
 struct EnvParamsHdr {
   int32_t N, C, D, T, homog, kind, sum_dl, obs_rows, state_rows;
   int32_t off_cdf, off_sw, off_nbr_off, off_nbr_idx, total_bytes;
+  int32_t self_nbr;   // single-channel env: every neighbourhood is the device itself (env.py:38-39 default)
   uint8_t deadline[D2D_MAX_AGENTS];
   uint8_t arrival_kind[D2D_MAX_AGENTS];
   uint16_t obs_off[D2D_MAX_AGENTS];

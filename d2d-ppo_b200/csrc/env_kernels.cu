@@ -78,8 +78,12 @@ __global__ void __launch_bounds__(256) comb_reset_kernel(const StepArgs a) {
 // ================================================================================================
 // D2DEnv (single channel)
 // ================================================================================================
-template <int W>
-__global__ void __launch_bounds__(256) sc_step_kernel(const StepArgs a) {
+// NK > 0: register-resident fast path for N <= NK devices (records and channel bits are loaded once, kept in
+// registers across the passes and stored once; the device loops are unrolled).  NK = 0: any N, records re-read
+// from L1 in the second pass.  With the default self-only neighbourhoods (env.py:38-39) the observation of device k
+// is emitted in the second pass from registers; other neighbourhoods take the gather pass at the end.
+template <int W, int NK>
+__global__ void __launch_bounds__(256, NK ? 5 : 4) sc_step_kernel(const StepArgs a) {
   extern __shared__ __align__(16) uint8_t smem[];
   const EnvParamsHdr* P = stage_params(a, smem);
   const uint32_t* cdf = reinterpret_cast<const uint32_t*>(smem + P->off_cdf);
@@ -88,67 +92,132 @@ __global__ void __launch_bounds__(256) sc_step_kernel(const StepArgs a) {
   const uint8_t* nbr_idx = smem + P->off_nbr_idx;
   const int N = P->N;
   const size_t B = (size_t)a.B;
+  const uint32_t Bu = (uint32_t)a.B;
   uint8_t* chan = reinterpret_cast<uint8_t*>(a.chan);
   const uint8_t* act = reinterpret_cast<const uint8_t*>(a.actions);
   uint8_t* act_out = reinterpret_cast<uint8_t*>(a.actions_out);
   const uint8_t* rp_sw = reinterpret_cast<const uint8_t*>(a.rp_sw);
+  const bool self_obs = a.obs != nullptr && P->self_nbr != 0;
+  constexpr int KR = NK ? NK : 1;
 
   for (int b = blockIdx.x * blockDim.x + threadIdx.x; b < a.B; b += gridDim.x * blockDim.x) {
     ArrivalWords arr_words;
     const uint32_t env = a.env_offset + (uint32_t)b;
     LaneWords pol_lanes, sw_lanes;   // one Philox call per eight devices for the 1-bit policy / switch draws
+    Rec<W> rec[KR];
+    uint32_t chv[KR], wantv[KR];
     // ---- pass 1 (env.py:125-127): attempts and the lone transmitter's channel ----
     uint64_t att = 0, good = 0;
-    for (int k = 0; k < N; ++k) {
-      const size_t idx = (size_t)k * B + b;
-      const Rec<W> r = rec_load<W>(a.buf, idx);
-      uint32_t want;
-      if (a.act_mode == 0) {
-        want = act[idx] != 0;
-      } else {
-        want = pol_lanes.get(a, env, k, kPurposePolicy) < a.tp_thr;
-        if (act_out) act_out[idx] = (uint8_t)want;
+    if constexpr (NK > 0) {
+#pragma unroll
+      for (int k = 0; k < NK; ++k) {           // every load of the env is issued before the first use
+        const size_t idx = (size_t)min(k, N - 1) * B + b;
+        rec[k] = rec_load<W>(a.buf, idx);
+        chv[k] = chan[idx];
+        wantv[k] = a.act_mode == 0 ? act[idx] : 0u;
       }
-      const uint64_t at = (want && rec_any<W>(r)) ? 1ull : 0ull;
-      att |= at << k;
-      good |= (at & (uint64_t)(chan[idx] & 1u)) << k;
+#pragma unroll
+      for (int k = 0; k < NK; ++k) {
+        if (k < N) {
+          uint32_t want = wantv[k] != 0;
+          if (a.act_mode != 0) {
+            want = pol_lanes.get(a, env, k, kPurposePolicy) < a.tp_thr;
+            if (act_out) act_out[(size_t)k * B + b] = (uint8_t)want;
+          }
+          const uint64_t at = (want && rec_any<W>(rec[k])) ? 1ull : 0ull;
+          att |= at << k;
+          good |= (at & (uint64_t)(chv[k] & 1u)) << k;
+        }
+      }
+    } else {
+      for (int k = 0; k < N; ++k) {
+        const size_t idx = (size_t)k * B + b;
+        const Rec<W> r = rec_load<W>(a.buf, idx);
+        uint32_t want;
+        if (a.act_mode == 0) {
+          want = act[idx] != 0;
+        } else {
+          want = pol_lanes.get(a, env, k, kPurposePolicy) < a.tp_thr;
+          if (act_out) act_out[idx] = (uint8_t)want;
+        }
+        const uint64_t at = (want && rec_any<W>(r)) ? 1ull : 0ull;
+        att |= at << k;
+        good |= (at & (uint64_t)(chan[idx] & 1u)) << k;
+      }
     }
     const int n_att = __popcll(att);
     // env.py:130-152: exactly one attempt is decoded iff its channel is good (binomial(1, state) is deterministic)
     const bool lone = n_att == 1;
     const bool decoded = lone && good != 0;
     const int ack = n_att > 1 ? -1 : (decoded ? 1 : 0);
-    if (lone && !decoded) a.stats[b] += 1;          // channel_errors (:147)
-    if (n_att > 1) a.stats[B + b] += 1;             // n_collisions   (:150)
+    const float ackf = (float)ack;
+    // Counters are read-modified-written only when they change.  Fast path: every counter this env may touch is
+    // requested here in ONE batch (one exposed DRAM latency instead of one per dependent update further down).
+    uint32_t discv[KR], recvv[KR], st0 = 0, st1 = 0;
+    if constexpr (NK > 0) {
+      if (lone && !decoded) st0 = a.stats[b];
+      if (n_att > 1) st1 = a.stats[B + b];
+#pragma unroll
+      for (int k = 0; k < NK; ++k) {
+        discv[k] = recvv[k] = 0;
+        if (k < N) {
+          const size_t idx = (size_t)k * B + b;
+          if (rec[k].w[0] & 0xFFu) discv[k] = a.disc[idx];    // slot 0 occupied: it may expire this step
+          if ((a.active >> k) & 1ull) recvv[k] = a.recv[idx];
+        }
+      }
+      if (lone && !decoded) a.stats[b] = st0 + 1;     // channel_errors (:147)
+      if (n_att > 1) a.stats[B + b] = st1 + 1;        // n_collisions   (:150)
+    } else {
+      if (lone && !decoded) a.stats[b] += 1;
+      if (n_att > 1) a.stats[B + b] += 1;
+    }
 
-    // ---- pass 2: serve, age, switch, arrive ----
-    for (int k = 0; k < N; ++k) {
+    // ---- pass 2: serve, age, switch, arrive (+ state row, + observation when the neighbourhood is the device) ----
+    auto second = [&](int k, Rec<W> r, uint32_t ch_old, uint32_t disc_v, uint32_t recv_v) {
       const size_t idx = (size_t)k * B + b;
-      Rec<W> r = rec_load<W>(a.buf, idx);
       rec_pop_earliest<W>(r, decoded && ((att >> k) & 1ull));   // :137-144
       const uint32_t expired = rec_age<W>(r);                   // :157
-      if (expired) a.disc[idx] += expired;                      // :158
+      if (expired) a.disc[idx] = (NK > 0 ? disc_v : a.disc[idx]) + expired;   // :158
       uint32_t sw;                                              // :107-109
       if (a.rng_mode == D2D_RNG_REPLAY) {
         sw = rp_sw[idx] & 1u;
       } else {
         sw = sw_lanes.get(a, env, k, kPurposeSwitch) < swthr[k];
       }
-      chan[idx] = (uint8_t)((chan[idx] ^ sw) & 1u);
+      const uint32_t ch_new = (ch_old ^ sw) & 1u;
+      chan[idx] = (uint8_t)ch_new;
+      const int dl = P->deadline[k];
       if ((a.active >> k) & 1ull) {                             // :162-180
         const uint32_t arrived = draw_arrival(a, P, cdf, k, b, arr_words);
-        rec_set_byte<W>(r, P->deadline[k] - 1, arrived);
-        if (arrived) a.recv[idx] += arrived;
+        rec_set_byte<W>(r, dl - 1, arrived);
+        if (arrived) a.recv[idx] = (NK > 0 ? recv_v : a.recv[idx]) + arrived;
       }
       rec_store<W>(a.buf, idx, r);
+      const float chf = ch_new ? 1.0f : 0.0f;
       if (a.state) {                                            // :189-190
-        rec_emit<W>(r, P->deadline[k], a.state + (size_t)P->sbuf_off[k] * B + b, B);
-        a.state[((size_t)P->sum_dl + k) * B + b] = (float)chan[idx];
+        emit_slots<W>(r, dl, a.state + (size_t)P->sbuf_off[k] * B + b, Bu);
+        st_f32(a.state + ((size_t)P->sum_dl + k) * B + b, chf);
+      }
+      if (self_obs) {                                           // :183-187 with neighbourhoods[k] = [k]
+        float* o = emit_slots<W>(r, dl, a.obs + (size_t)P->obs_off[k] * B + b, Bu);
+        st_f32(o, chf);                                         // post-switch channel
+        st_f32(next_row(o, Bu), ackf);
+      }
+    };
+    if constexpr (NK > 0) {
+#pragma unroll
+      for (int k = 0; k < NK; ++k)
+        if (k < N) second(k, rec[k], chv[k], discv[k], recvv[k]);
+    } else {
+      for (int k = 0; k < N; ++k) {
+        const size_t idx = (size_t)k * B + b;
+        second(k, rec_load<W>(a.buf, idx), chan[idx], 0u, 0u);
       }
     }
-    if (a.state) a.state[((size_t)P->sum_dl + N) * B + b] = (float)ack;
-    // ---- pass 3: neighbourhood observations (env.py:183-187), channel is the post-switch state ----
-    if (a.obs) {
+    if (a.state) st_f32(a.state + ((size_t)P->sum_dl + N) * B + b, ackf);
+    // ---- pass 3: general neighbourhood observations (env.py:183-187), channel is the post-switch state ----
+    if (a.obs && !self_obs) {
       for (int k = 0; k < N; ++k) {
         float* o = a.obs + (size_t)P->obs_off[k] * B + b;
         for (int j = nbr_off[k]; j < nbr_off[k + 1]; ++j) {
@@ -158,7 +227,7 @@ __global__ void __launch_bounds__(256) sc_step_kernel(const StepArgs a) {
           o += (size_t)P->deadline[i] * B;
         }
         for (int j = nbr_off[k]; j < nbr_off[k + 1]; ++j, o += B) *o = (float)chan[(size_t)nbr_idx[j] * B + b];
-        *o = (float)ack;
+        *o = ackf;
       }
     }
     a.reward[b] = (a.reward_accum ? a.reward[b] : 0) + ack;     // :191 rewards = zeros(N) + ack
@@ -222,17 +291,19 @@ __global__ void __launch_bounds__(256) sc_reset_kernel(const StepArgs a) {
 constexpr int kCountPlanes = 7;  // bit-sliced per-channel attempt counters, counts up to 127 >= N
 
 template <int W>
-__global__ void __launch_bounds__(256) sel_step_kernel(const StepArgs a) {
+__global__ void __launch_bounds__(256, 4) sel_step_kernel(const StepArgs a) {
   extern __shared__ __align__(16) uint8_t smem[];
   const EnvParamsHdr* P = stage_params(a, smem);
   const uint32_t* cdf = reinterpret_cast<const uint32_t*>(smem + P->off_cdf);
   const uint32_t* swthr = reinterpret_cast<const uint32_t*>(smem + P->off_sw);
   const int N = P->N, C1 = P->C + 1;
   const size_t B = (size_t)a.B;
+  const uint32_t Bu = (uint32_t)a.B;
   uint32_t* chan = reinterpret_cast<uint32_t*>(a.chan);
   const uint8_t* act = reinterpret_cast<const uint8_t*>(a.actions);
   const uint32_t* rp_sw = reinterpret_cast<const uint32_t*>(a.rp_sw);
   const uint32_t cmask = C1 >= 32 ? 0xFFFFFFFFu : ((1u << C1) - 1u);
+  const int n_planes = 32 - __clz(N);     // a channel is picked by at most N devices: bits(N) counter planes suffice
 
   for (int b = blockIdx.x * blockDim.x + threadIdx.x; b < a.B; b += gridDim.x * blockDim.x) {
     ArrivalWords arr_words;
@@ -242,6 +313,7 @@ __global__ void __launch_bounds__(256) sel_step_kernel(const StepArgs a) {
     uint32_t plane[kCountPlanes];
 #pragma unroll
     for (int j = 0; j < kCountPlanes; ++j) plane[j] = 0;
+#pragma unroll 4
     for (int k = 0; k < N; ++k) {
       const size_t idx = (size_t)k * B + b;
       const Rec<W> r = rec_load<W>(a.buf, idx);
@@ -249,9 +321,11 @@ __global__ void __launch_bounds__(256) sel_step_kernel(const StepArgs a) {
       uint32_t carry = (sel != 0 && rec_any<W>(r)) ? (1u << sel) : 0u;
 #pragma unroll
       for (int j = 0; j < kCountPlanes; ++j) {
-        const uint32_t s = plane[j] ^ carry;
-        carry &= plane[j];
-        plane[j] = s;
+        if (j < n_planes) {
+          const uint32_t s = plane[j] ^ carry;
+          carry &= plane[j];
+          plane[j] = s;
+        }
       }
     }
     uint32_t selected = 0, multi = 0;
@@ -261,28 +335,44 @@ __global__ void __launch_bounds__(256) sel_step_kernel(const StepArgs a) {
       if (j > 0) multi |= plane[j];
     }
     const uint32_t win = plane[0] & ~multi & ch;                 // :140-141 one attempt on a good channel
-    a.stats[b] += __popc(selected & ch);                         // :132 selected_channel_qualities
-    a.stats[B + b] += __popc(selected);                          // :133 number_selected_channel
+    if (selected) {                                              // counters move only when somebody transmitted
+      const uint32_t s0 = a.stats[b], s1 = a.stats[B + b];
+      a.stats[b] = s0 + __popc(selected & ch);                   // :132 selected_channel_qualities
+      a.stats[B + b] = s1 + __popc(selected);                    // :133 number_selected_channel
+    }
 
-    // ---- pass 2 ----
+    // ---- pass 2: device k + 1's record and counters are fetched while device k is processed ----
     int n_success = 0;
+    Rec<W> r_nx = rec_load<W>(a.buf, (size_t)b);                 // second touch of the record: L1 hit
+    uint32_t sel_nx = act[b];
+    uint32_t disc_nx = (r_nx.w[0] & 0xFFu) ? a.disc[b] : 0u;
+    uint32_t recv_nx = (a.active & 1ull) ? a.recv[b] : 0u;
+#pragma unroll 1
     for (int k = 0; k < N; ++k) {
       const size_t idx = (size_t)k * B + b;
-      Rec<W> r = rec_load<W>(a.buf, idx);
-      const uint32_t sel = act[idx];
+      Rec<W> r = r_nx;
+      const uint32_t sel = sel_nx, disc_v = disc_nx, recv_v = recv_nx;
+      if (k + 1 < N) {
+        const size_t nx = idx + B;
+        r_nx = rec_load<W>(a.buf, nx);
+        sel_nx = act[nx];
+        disc_nx = (r_nx.w[0] & 0xFFu) ? a.disc[nx] : 0u;
+        if ((a.active >> (k + 1)) & 1ull) recv_nx = a.recv[nx];
+      }
       const bool success = sel != 0 && rec_any<W>(r) && ((win >> sel) & 1u);   // :142
       n_success += success;
       rec_pop_earliest<W>(r, success);
       const uint32_t expired = rec_age<W>(r);
-      if (expired) a.disc[idx] += expired;
+      if (expired) a.disc[idx] = disc_v + expired;
+      const int dl = P->deadline[k];
       if ((a.active >> k) & 1ull) {
         const uint32_t arrived = draw_arrival(a, P, cdf, k, b, arr_words);
-        rec_set_byte<W>(r, P->deadline[k] - 1, arrived);
-        if (arrived) a.recv[idx] += arrived;
+        rec_set_byte<W>(r, dl - 1, arrived);
+        if (arrived) a.recv[idx] = recv_v + arrived;
       }
       rec_store<W>(a.buf, idx, r);
-      if (a.obs) rec_emit<W>(r, P->deadline[k], a.obs + (size_t)P->obs_off[k] * B + b, B);
-      if (a.state) rec_emit<W>(r, P->deadline[k], a.state + (size_t)P->sbuf_off[k] * B + b, B);
+      if (a.obs) emit_slots<W>(r, dl, a.obs + (size_t)P->obs_off[k] * B + b, Bu);
+      if (a.state) emit_slots<W>(r, dl, a.state + (size_t)P->sbuf_off[k] * B + b, Bu);
     }
     uint32_t sw;                                                 // :104-107 C+1 scalar draws
     if (a.rng_mode == D2D_RNG_REPLAY) {
@@ -293,16 +383,48 @@ __global__ void __launch_bounds__(256) sel_step_kernel(const StepArgs a) {
     }
     const uint32_t ch_new = (ch ^ sw) & cmask;
     chan[b] = ch_new;
-    // ack/nack vector (:129-137): 0 unused, -1 bad channel, 1/count good channel
-    for (int c = 0; c < C1; ++c) {
+    // ack/nack vector (:129-137): 0 unused, -1 bad channel, 1/count good channel -- computed once per channel into
+    // registers, then streamed to every device's observation rows with a running row pointer
+    float v[D2D_MAX_CHANNELS];
+#pragma unroll
+    for (int c = 0; c < D2D_MAX_CHANNELS; ++c) {
       int cnt = 0;
 #pragma unroll
-      for (int j = 0; j < kCountPlanes; ++j) cnt |= (int)((plane[j] >> c) & 1u) << j;
-      const float v = cnt == 0 ? 0.0f : (((ch >> c) & 1u) ? P->inv_count[cnt] : -1.0f);
-      if (a.obs)
-        for (int k = 0; k < N; ++k) a.obs[((size_t)P->obs_off[k] + P->deadline[k] + c) * B + b] = v;   // :181-184
-      if (a.ack) reinterpret_cast<float*>(a.ack)[(size_t)c * B + b] = v;
-      if (a.state) a.state[((size_t)P->sum_dl + c) * B + b] = (float)((ch_new >> c) & 1u);             // :186
+      for (int j = 0; j < kCountPlanes; ++j)
+        if (j < n_planes) cnt |= (int)((plane[j] >> c) & 1u) << j;
+      v[c] = cnt == 0 ? 0.0f : (((ch >> c) & 1u) ? P->inv_count[cnt] : -1.0f);
+    }
+    if (a.obs) {                                                 // :181-184
+      for (int k = 0; k < N; ++k) {
+        float* o = a.obs + ((size_t)P->obs_off[k] + P->deadline[k]) * B + b;
+#pragma unroll
+        for (int c = 0; c < D2D_MAX_CHANNELS; ++c) {
+          if (c < C1) {
+            st_f32(o, v[c]);
+            o = next_row(o, Bu);
+          }
+        }
+      }
+    }
+    if (a.ack) {
+      float* q = reinterpret_cast<float*>(a.ack) + b;
+#pragma unroll
+      for (int c = 0; c < D2D_MAX_CHANNELS; ++c) {
+        if (c < C1) {
+          st_f32(q, v[c]);
+          q = next_row(q, Bu);
+        }
+      }
+    }
+    if (a.state) {                                               // :186
+      float* q = a.state + (size_t)P->sum_dl * B + b;
+#pragma unroll
+      for (int c = 0; c < D2D_MAX_CHANNELS; ++c) {
+        if (c < C1) {
+          st_f32(q, ((ch_new >> c) & 1u) ? 1.0f : 0.0f);
+          q = next_row(q, Bu);
+        }
+      }
     }
     a.reward[b] = (a.reward_accum ? a.reward[b] : 0) + n_success;  // :188
     if (a.done) a.done[b] = (uint8_t)a.done_flag;
@@ -525,6 +647,9 @@ extern "C" int d2d_env_create(const d2d_env_config* cfg, d2d_env** out) {
   EnvParamsHdr h;
   memset(&h, 0, sizeof(h));
   h.N = N, h.C = C, h.D = e->D, h.T = e->T, h.homog = e->homog, h.kind = e->kind, h.sum_dl = e->sum_dl;
+  h.self_nbr = 1;
+  for (int k = 0; k < N && e->kind == D2D_ENV_SINGLE_CHANNEL; ++k)
+    if (nbr_off[k + 1] - nbr_off[k] != 1 || nbr_idx[nbr_off[k]] != k) h.self_nbr = 0;
   h.off_cdf = align16((int)sizeof(EnvParamsHdr));
   h.off_sw = h.off_cdf + align16(N * D2D_POISSON_KMAX * 4);
   h.off_nbr_off = h.off_sw + align16(n_sw * 4);
@@ -631,10 +756,12 @@ static int fill_args(d2d_env* e, StepArgs& a, uint32_t t, const char* who) {
   return D2D_OK;
 }
 
+// one_per_thread: ceil(B / 256) short blocks (the hardware block scheduler balances them better than a persistent
+// grid-stride launch, whose ~3.5 envs per resident thread leave a 4-vs-3 iteration imbalance)
 template <typename K>
-static int launch_env(K kernel, const StepArgs& a, int params_bytes, void* stream) {
+static int launch_env(K kernel, const StepArgs& a, int params_bytes, void* stream, bool one_per_thread = false) {
   const int block = 256;
-  kernel<<<grid_for(a.B, block), block, params_bytes, as_stream(stream)>>>(a);
+  kernel<<<grid_for(a.B, block, one_per_thread ? (1 << 20) : 8), block, params_bytes, as_stream(stream)>>>(a);
   D2D_LAUNCHED();
   return D2D_OK;
 }
@@ -682,13 +809,16 @@ static int env_step_impl(d2d_env* e, StepArgs& a, void* stream) {
          : e->W == 4 ? launch_comb_step<4>(a, e->N, e->C, e->CB, as_stream(stream))
                      : launch_comb_step<8>(a, e->N, e->C, e->CB, as_stream(stream));
   } else if (e->kind == D2D_ENV_SINGLE_CHANNEL) {
-    rc = e->W == 2 ? launch_env(sc_step_kernel<2>, a, e->params_bytes, stream)
-         : e->W == 4 ? launch_env(sc_step_kernel<4>, a, e->params_bytes, stream)
-                     : launch_env(sc_step_kernel<8>, a, e->params_bytes, stream);
+    if (e->N <= 4 && e->W == 2) rc = launch_env(sc_step_kernel<2, 4>, a, e->params_bytes, stream, true);
+    else if (e->N <= 4 && e->W == 4) rc = launch_env(sc_step_kernel<4, 4>, a, e->params_bytes, stream, true);
+    else
+      rc = e->W == 2 ? launch_env(sc_step_kernel<2, 0>, a, e->params_bytes, stream, true)
+           : e->W == 4 ? launch_env(sc_step_kernel<4, 0>, a, e->params_bytes, stream, true)
+                       : launch_env(sc_step_kernel<8, 0>, a, e->params_bytes, stream, true);
   } else {
-    rc = e->W == 2 ? launch_env(sel_step_kernel<2>, a, e->params_bytes, stream)
-         : e->W == 4 ? launch_env(sel_step_kernel<4>, a, e->params_bytes, stream)
-                     : launch_env(sel_step_kernel<8>, a, e->params_bytes, stream);
+    rc = e->W == 2 ? launch_env(sel_step_kernel<2>, a, e->params_bytes, stream, true)
+         : e->W == 4 ? launch_env(sel_step_kernel<4>, a, e->params_bytes, stream, true)
+                     : launch_env(sel_step_kernel<8>, a, e->params_bytes, stream, true);
   }
   if (rc) return rc;
   e->t += 1;
