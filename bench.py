@@ -470,13 +470,24 @@ def bench_env_configs(dev, hbm_peak, steps=200):
         env._reset_device(True, False, out_obs=obs)
         for _ in range(5):
             one()
-        ev = [torch.cuda.Event(enable_timing=True) for _ in range(steps + 1)]
-        ev[0].record()
-        for i in range(steps):
-            one()
-            ev[i + 1].record()
-        torch.cuda.synchronize()
-        ms = float(np.median([ev[i].elapsed_time(ev[i + 1]) for i in range(steps)]))
+        if tp is not None:
+            # the product path of CombinatorialRandomAccess.run: the steps are enqueued by the library in one call
+            # (d2d_env_run_random_access); 30 untimed lead-in steps in front of the start event (see run_native)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            env.run_random_access(tp, LEAD_IN, auto_reset=True, out_obs=obs, out_reward=rew)
+            e0.record()
+            env.run_random_access(tp, steps, auto_reset=True, out_obs=obs, out_reward=rew)
+            e1.record()
+            torch.cuda.synchronize()
+            ms = e0.elapsed_time(e1) / steps         # resets (1 in 200 launches) included
+        else:
+            ev = [torch.cuda.Event(enable_timing=True) for _ in range(steps + 1)]
+            ev[0].record()
+            for i in range(steps):
+                one()
+                ev[i + 1].record()
+            torch.cuda.synchronize()
+            ms = float(np.median([ev[i].elapsed_time(ev[i + 1]) for i in range(steps)]))
         rate = B * N / (ms * 1e-3)
         out.append({"config": label, "envs": B, "n_agents": N, "agent_steps_per_s": rate, "kernel_ms": ms,
                     "alg_bytes_per_agent_step": alg, "achieved_gbs": rate * alg / 1e9,

@@ -401,3 +401,34 @@ def test_run_random_access_equals_stepwise(name, cuda_device):
     tot = sum(b.step_random_access(tp)[2][:, 0].to(torch.int32) for _ in range(T))
     assert torch.equal(acc, tot)
     assert a.run_random_access(tp, 3, out_reward=acc, accumulate=True) == 0
+
+
+@pytest.mark.parametrize("n_agents,B", [(64, 96), (40, 64), (32, 32)])
+def test_grouped_device_mapping_matches_oracle(n_agents, B, cuda_device):
+    """Many devices per env and few envs (xp_n_agents.py sweep at N >= 32, B a multiple of 32): the step kernel maps a
+    block to 32 envs x 8 device groups and combines the per-channel masks through shared memory.  Bit exact against
+    the oracle with actions from memory and with the fused random-access policy."""
+    from d2d_ppo_b200.presets import n_agents_sweep_kwargs
+    from oracle import philox_np as px
+    from oracle.envs_np import PhiloxSource
+    from oracle.gen_golden import draw_actions
+    kw = n_agents_sweep_kwargs(n_agents, load=0.5, episode_length=20)
+    T, C = 20, kw["n_channels"]
+    act = draw_actions("combinatorial", kw, B, T, 0.15, np.random.default_rng(n_agents))
+    env = make_cuda_env("combinatorial", kw, B, rng="philox", seed=n_agents + 1, env_offset=11, device=cuda_device)
+    orc = make_oracle("combinatorial", kw, B, PhiloxSource(B, n_agents + 1, env_offset=11))
+    _rollout_against_oracle(env, orc, "combinatorial", act, check_every=3)
+    # fused policy: the oracle is fed the action bits the kernel draws (Philox policy stream of episode 1)
+    env.reset()
+    orc.reset()
+    envs = np.arange(B) + 11
+    tp = 0.1
+    for t in range(1, T + 1):
+        obs, state, rew, done, _ = env.step_random_access(tp)
+        tc = orc.source.ctr_t(t)
+        a = np.stack([px.lanes16(n_agents + 1, envs, tc, k, px.PURPOSE_POLICY, C) < px.thr16(tp)
+                      for k in range(n_agents)], axis=1)
+        o_obs, o_state, o_rew, o_done, _ = orc.step(a)
+        assert np.array_equal(cat_obs(obs), cat_obs(o_obs)), t
+        assert np.array_equal(to_np(state), o_state) and np.array_equal(to_np(rew), o_rew), t
+    _check_state(env, orc, "combinatorial", "fused policy")
