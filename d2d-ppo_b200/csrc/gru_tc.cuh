@@ -8,29 +8,35 @@
 // h_last (H floats per row) is written: the [rows x 3H] projections live in TMEM, h lives in registers and in
 // shared memory as the next step's A operand.
 //
-// fp32 parity on tensor cores: every fp32 operand is split into three bf16 planes (v = p0 + p1 + p2, 24 mantissa
-// bits), and a product keeps the six plane pairs with i + j <= 2 (error ~2^-24 per term, measured 1.1e-6 norm-wise
-// on a K = 64 GEMM incl. the tensor core's own accumulation).  Observations are small integers (exact in bf16), so
-// the input projection needs only x(1 plane) x W_ih(3 planes).
+// fp32 parity on tensor cores: every fp32 operand is split into TWO fp16 planes (v = p0 + p1, p0 = rn16(v),
+// p1 = rn16(v - p0): 22 significant bits, absolute error <= 2^-25 for |v| <= 1) and a product keeps the three plane
+// pairs p0 q0 + p0 q1 + p1 q0 (the dropped p1 q1 term is 2^-24 relative).  Weights are pre-scaled by 2^6 so that their
+// low planes stay out of the fp16 subnormal range; the accumulators then carry 64 x the pre-activation and the factor
+// is folded into the gate constants.  Measured (CPU emulation on the reference's c3 weights, 6 recurrent steps):
+// 1.3e-7 norm-wise, the same as fp32 itself and as the earlier 3-plane bf16 scheme, which needed 6 products per GEMM
+// instead of 3 and 3 operand planes in shared memory instead of 2.  Observations are small integers (exact in fp16 up
+// to 2048), so the input projection needs only x (1 plane) x W_ih (2 planes).
 //
 // CTA = 16 warps (512 threads: 128 registers each; a 17th warp would be charged as four and leave 96, which spills
 // the prefetched observations in store mode).  Two 128-row tiles ("slots") are in flight per CTA so that the tensor
 // pipe works on one slot while the other slot's gates are evaluated:
 //   warps 0-7  : slot 0; warp w serves TMEM lane quadrant w % 4 (rows 32 (w % 4) + lane) and the hidden units of
 //                half (w / 4) % 2: stage x, read gate pre-activations with tcgen05.ld, gate maths, write h
-//                (3 bf16 planes) + next x into the canonical K-major smem layout
+//                (2 fp16 planes) + next x into the canonical K-major smem layout
 //   warps 8-15 : the same for slot 1
 //   the first thread of each slot also issues that slot's tcgen05.mma batch once the slot's operands are in place:
 //                TMEM columns [0, H) r, [H, 2H) z, [2H, 3H) gh_n, [3H, 4H) gi_n (the n gate needs gi_n and gh_n
-//                separately); h W_hh^T is ONE N = 3H MMA per (plane pair, k-step) over W_hh's natural [r; z; n] rows,
-//                x W_ih^T is split instead (r, z onto [0, 2H), n into [3H, 4H)): 36 MMAs per step, A tiles fetched once
+//                separately).  x W_ih^T is ONE N = 4H MMA per (plane, k-step) over W_ih stored as [r; z; 0; n] (the zero
+//                block initialises the gh_n columns); h W_hh^T is ONE N = 3H MMA per (plane pair, k-step) over W_hh's
+//                natural [r; z; n] rows: 4 + 12 = 16 MMAs per step (36 with 3 bf16 planes), A tiles fetched once
 // Hand-offs are mbarriers: a_ready[slot] (256 arrivals: operands staged) and d_ready[slot] (tcgen05.commit).
 // The kernel is bound by the gate maths (6 MUFU per (row, unit, step)), not by the tensor pipe: sigmoid / tanh use
-// ex2.approx + rcp.approx (rel. error ~2^-21), the bf16 planes are cut by integer masking instead of F2F.
-// Shared memory (H = 64, I <= 32): W_ih planes 40 KB + W_hh planes 72 KB + h planes 2 x 48 KB + x 2 x 8 KB = 225 KB;
+// ex2.approx + rcp.approx (rel. error ~2^-21).
+// Shared memory (H = 64, I <= 32): W_ih planes 32 KB + W_hh planes 48 KB + h planes 2 x 32 KB + x 2 x 8 KB = 160 KB;
 // TMEM: 2 slots x 4H = 512 columns.
 #pragma once
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 
 #include "learner_kernels.cuh"
 
@@ -79,6 +85,23 @@ __device__ __forceinline__ uint64_t desc_adv(uint64_t base, uint32_t byte_off) {
 // instruction descriptor: D = F32, A = B = BF16, both K-major, M = 128
 __device__ __forceinline__ uint32_t idesc_bf16(int n) {
   return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(kM >> 4) << 24);
+}
+// the same with A = B = FP16 (a_format = b_format = 0)
+__device__ __forceinline__ uint32_t idesc_f16(int n) {
+  return (1u << 4) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(kM >> 4) << 24);
+}
+constexpr float kWScale = 64.0f;              // weights are staged as 64 w: their low fp16 planes stay normal
+constexpr float kInvWScale = 1.0f / 64.0f;
+// (a, b) -> two fp16 planes, each as a packed half2 word (element a in the low half): v = p0 + p1 + O(2^-24 |v|)
+__device__ __forceinline__ void split2h(float a, float b, uint32_t& p0, uint32_t& p1) {
+  const __half2 h0 = __floats2half2_rn(a, b);
+  const float2 f0 = __half22float2(h0);
+  const __half2 h1 = __floats2half2_rn(a - f0.x, b - f0.y);
+  p0 = *reinterpret_cast<const uint32_t*>(&h0), p1 = *reinterpret_cast<const uint32_t*>(&h1);
+}
+__device__ __forceinline__ void split2h1(float v, __half& p0, __half& p1) {
+  p0 = __float2half_rn(v);
+  p1 = __float2half_rn(v - __half2float(p0));
 }
 __device__ __forceinline__ void mma_bf16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, bool accum) {
   const uint32_t acc = accum ? 1u : 0u;
@@ -145,12 +168,12 @@ __device__ __forceinline__ uint32_t pack2(__nv_bfloat16 a, __nv_bfloat16 b) {
 
 template <int H>
 struct Smem {
-  static constexpr int kWih = 3 * H * kKx;        // bf16 elements of W_ih planes 1, 2: rows [r; z; n]
-  static constexpr int kWih0 = 4 * H * kKx;       // plane 0: rows [r; z; 0; n] (the zero block initialises the gh_n columns)
+  static constexpr int kWih = 4 * H * kKx;        // fp16 elements of one W_ih plane: rows [r; z; 0; n] (the zero block
+                                                  // initialises / leaves alone the gh_n accumulator columns)
   static constexpr int kWhh = 3 * H * H;
   static constexpr int kAh = kM * H;
   static constexpr int kAx = kM * kKx;
-  static constexpr size_t bytes = (size_t)(kWih0 + 2 * kWih + 3 * kWhh + 2 * 3 * kAh + 2 * kAx) * 2 + 4 * H * 4 + 64;
+  static constexpr size_t bytes = (size_t)(2 * kWih + 2 * kWhh + 2 * 2 * kAh + 2 * kAx) * 2 + 4 * H * 4 + 64;
 };
 
 }  // namespace tc
@@ -162,10 +185,10 @@ __global__ void __launch_bounds__(tc::kThreads, 1) gru_window_tc_kernel(const Gr
   using S = Smem<H>;
   static_assert(H % 16 == 0 && H >= 16 && H <= 64, "H in {16, 32, 48, 64}");
   extern __shared__ __align__(1024) uint8_t smem_raw[];
-  __nv_bfloat16* wih = reinterpret_cast<__nv_bfloat16*>(smem_raw);      // plane 0 [4H][kKx], planes 1, 2 [3H][kKx]
-  __nv_bfloat16* whh = wih + S::kWih0 + 2 * S::kWih;                    // [3 planes][3H][H]
-  __nv_bfloat16* ah = whh + 3 * S::kWhh;                                // [2 slots][3 planes][128][H]
-  __nv_bfloat16* ax = ah + 2 * 3 * S::kAh;                              // [2 slots][128][kKx]
+  __half* wih = reinterpret_cast<__half*>(smem_raw);                    // [2 planes][4H][kKx], rows [r; z; 0; n]
+  __half* whh = wih + 2 * S::kWih;                                      // [2 planes][3H][H]
+  __half* ah = whh + 2 * S::kWhh;                                       // [2 slots][2 planes][128][H]
+  __half* ax = ah + 2 * 2 * S::kAh;                                     // [2 slots][128][kKx]
   float* bias = reinterpret_cast<float*>(ax + 2 * S::kAx);              // [2H] b_ih + b_hh (r, z), [H] b_in, [H] b_hn
   uint64_t* bars = reinterpret_cast<uint64_t*>(bias + 4 * H);           // a_ready[2], d_ready[2]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 4);
@@ -180,22 +203,22 @@ __global__ void __launch_bounds__(tc::kThreads, 1) gru_window_tc_kernel(const Gr
   const float* bih = a.w + g * a.w_agent_stride + a.bih_off[g];
   const float* bhh = a.w + g * a.w_agent_stride + a.bhh_off[g];
 
-  // ---- one-time setup: weights -> three bf16 planes in the canonical layout, biases, barriers, TMEM ----
-  for (int i = tid; i < 3 * H * kKx; i += kThreads) {
-    const int n = i / kKx, k = i % kKx;
-    __nv_bfloat16 p0, p1, p2;
-    split3(k < I ? Wih[(long long)n * I + k] : 0.f, p0, p1, p2);
-    const int o = canon16(n, k, kKx);
-    wih[canon16(n < 2 * H ? n : n + H, k, kKx)] = p0;
-    wih[S::kWih0 + o] = p1, wih[S::kWih0 + S::kWih + o] = p2;
+  // ---- one-time setup: 64 x weights -> two fp16 planes in the canonical layout, biases, barriers, TMEM ----
+  for (int i = tid; i < 4 * H * kKx; i += kThreads) {
+    const int n4 = i / kKx, k = i % kKx;          // row of the [r; z; 0; n] arrangement
+    const int n = n4 < 2 * H ? n4 : n4 - H;       // row of W_ih ([r; z; n]); rows [2H, 3H) of the arrangement are zero
+    const bool zero = n4 >= 2 * H && n4 < 3 * H;
+    __half p0, p1;
+    split2h1((!zero && k < I) ? kWScale * Wih[(long long)n * I + k] : 0.f, p0, p1);
+    const int o = canon16(n4, k, kKx);
+    wih[o] = p0, wih[S::kWih + o] = p1;
   }
-  for (int i = tid; i < H * kKx; i += kThreads) wih[canon16(2 * H + i / kKx, i % kKx, kKx)] = __float2bfloat16_rn(0.f);
   for (int i = tid; i < 3 * H * H; i += kThreads) {
     const int n = i / H, k = i % H;
-    __nv_bfloat16 p0, p1, p2;
-    split3(Whh[i], p0, p1, p2);
+    __half p0, p1;
+    split2h1(kWScale * Whh[i], p0, p1);
     const int o = canon16(n, k, H);
-    whh[o] = p0, whh[S::kWhh + o] = p1, whh[2 * S::kWhh + o] = p2;
+    whh[o] = p0, whh[S::kWhh + o] = p1;
   }
   // biases, pre-scaled for the ex2-based gates: sigmoid(a) = 1 / (1 + 2^(-a log2 e))
   for (int i = tid; i < 4 * H; i += kThreads) {
@@ -232,56 +255,42 @@ __global__ void __launch_bounds__(tc::kThreads, 1) gru_window_tc_kernel(const Gr
     const int half = (warp >> 2) & 1;
     const int row = ((warp & 3) << 5) + lane;
     const uint32_t lane_addr = (uint32_t)((warp & 3) << 5) << 16;
-    __nv_bfloat16* my_ax = ax + slot * S::kAx;
-    __nv_bfloat16* my_ah = ah + slot * 3 * S::kAh;
+    __half* my_ax = ax + slot * S::kAx;
+    __half* my_ah = ah + slot * 2 * S::kAh;
     const int u0 = half * HH;
     uint32_t ph = 0, ph_a = 0;
     float h[HH];
     const bool issuer = (tid & (kGateThreads - 1)) == 0;
-    const uint32_t id3 = idesc_bf16(3 * H), id2 = idesc_bf16(2 * H), id1 = idesc_bf16(H);
-    const uint32_t sbo_h = (H >> 3) * 128;   // bytes between 8-row groups of a [.][H] tile
+    const uint32_t id3 = idesc_f16(3 * H), id4 = idesc_f16(4 * H);
     // base descriptors of the slot's operand tiles, built once
     const uint32_t d_slot = tmem + (uint32_t)slot * (4 * H);
     const uint64_t dx = desc16(smem_u32(ax + slot * S::kAx), kKx), dwih = desc16(smem_u32(wih), kKx);
-    const uint64_t dah = desc16(smem_u32(ah + slot * 3 * S::kAh), H), dwhh = desc16(smem_u32(whh), H);
+    const uint64_t dah = desc16(smem_u32(ah + slot * 2 * S::kAh), H), dwhh = desc16(smem_u32(whh), H);
     // the slot's MMA batch for the step whose operands were just published (first_step: h = 0, input projection only)
     auto issue = [&](bool first_step) {
       mbar_wait(&a_ready[slot], ph_a);
       ph_a ^= 1u;
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       // Accumulator columns of the slot: [0, H) r, [H, 2H) z, [2H, 3H) gh_n, [3H, 4H) gi_n (the n gate needs both
-      // separately).  The hidden projection is ONE N = 3H MMA per (plane pair, k-step) over W_hh's natural [r; z; n]
-      // rows: the A tile is fetched once instead of twice (N = 2H + N = H), which is what limits this kernel.
-      // input projection, x exact in bf16: plane 0 [r; z; 0] initialises [0, 3H) (zeros into the gh_n columns),
-      // planes 1, 2 accumulate onto r, z; the n rows of all planes go to [3H, 4H)
-      constexpr uint32_t sbo_x = (kKx >> 3) * 128;
+      // separately), all scaled by 64 (kWScale).
+      // input projection, x exact in fp16: ONE N = 4H MMA per (plane, k-step) over W_ih stored as [r; z; 0; n]; the
+      // first one initialises all 4H columns (zeros into the gh_n columns)
 #pragma unroll
-      for (int k16 = 0; k16 < kKx / 16; ++k16) mma_bf16(d_slot, desc_adv(dx, k16 * 256), desc_adv(dwih, k16 * 256), id3, k16 > 0);
-#pragma unroll
-      for (int j = 1; j < 3; ++j)
+      for (int j = 0; j < 2; ++j)
 #pragma unroll
         for (int k16 = 0; k16 < kKx / 16; ++k16)
-          mma_bf16(d_slot, desc_adv(dx, k16 * 256), desc_adv(dwih, (S::kWih0 + (j - 1) * S::kWih) * 2 + k16 * 256), id2,
-                   true);
-#pragma unroll
-      for (int j = 0; j < 3; ++j)
-#pragma unroll
-        for (int k16 = 0; k16 < kKx / 16; ++k16) {
-          const uint32_t off = j == 0 ? (3 * H / 8) * sbo_x : (S::kWih0 + (j - 1) * S::kWih) * 2 + (2 * H / 8) * sbo_x;
-          mma_bf16(d_slot + 3 * H, desc_adv(dx, k16 * 256), desc_adv(dwih, off + k16 * 256), id1, !(j == 0 && k16 == 0));
-        }
+          mma_bf16(d_slot, desc_adv(dx, k16 * 256), desc_adv(dwih, j * S::kWih * 2 + k16 * 256), id4, j + k16 > 0);
       if (!first_step) {
-        // hidden projection, plane pairs (i, j) with i + j <= 2
+        // hidden projection, plane pairs h0 w0, h0 w1, h1 w0: ONE N = 3H MMA per (pair, k-step) over W_hh's natural
+        // [r; z; n] rows, accumulated onto the r, z and gh_n columns
 #pragma unroll
-        for (int i = 0; i < 3; ++i)
+        for (int pr = 0; pr < 3; ++pr) {
+          const int i = pr == 2 ? 1 : 0, j = pr == 1 ? 1 : 0;
 #pragma unroll
-          for (int j = 0; j < 3; ++j) {
-            if (i + j > 2) continue;
-#pragma unroll
-            for (int k16 = 0; k16 < H / 16; ++k16)
-              mma_bf16(d_slot, desc_adv(dah, (i * S::kAh) * 2 + k16 * 256), desc_adv(dwhh, (j * S::kWhh) * 2 + k16 * 256),
-                       id3, true);
-          }
+          for (int k16 = 0; k16 < H / 16; ++k16)
+            mma_bf16(d_slot, desc_adv(dah, (i * S::kAh) * 2 + k16 * 256), desc_adv(dwhh, (j * S::kWhh) * 2 + k16 * 256),
+                     id3, true);
+        }
       }
       asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];"
                    ::"r"(smem_u32(&d_ready[slot]))
@@ -297,14 +306,14 @@ __global__ void __launch_bounds__(tc::kThreads, 1) gru_window_tc_kernel(const Gr
         xr[k] = (ok && kk < I) ? xp[(long long)kk * a.B] : 0.f;
       }
     };
-    auto stage_x = [&](const float* xr) {              // exact in bf16: the top halves of the fp32 words
+    auto stage_x = [&](const float* xr) {              // integer-valued observations: exact in one fp16 plane
 #pragma unroll
       for (int kc = 0; kc < KH / 8; ++kc) {
         uint4 v;
-        v.x = pack_hi(__float_as_uint(xr[kc * 8 + 0]), __float_as_uint(xr[kc * 8 + 1]));
-        v.y = pack_hi(__float_as_uint(xr[kc * 8 + 2]), __float_as_uint(xr[kc * 8 + 3]));
-        v.z = pack_hi(__float_as_uint(xr[kc * 8 + 4]), __float_as_uint(xr[kc * 8 + 5]));
-        v.w = pack_hi(__float_as_uint(xr[kc * 8 + 6]), __float_as_uint(xr[kc * 8 + 7]));
+        const __half2 a0 = __floats2half2_rn(xr[kc * 8 + 0], xr[kc * 8 + 1]), a1 = __floats2half2_rn(xr[kc * 8 + 2], xr[kc * 8 + 3]);
+        const __half2 a2 = __floats2half2_rn(xr[kc * 8 + 4], xr[kc * 8 + 5]), a3 = __floats2half2_rn(xr[kc * 8 + 6], xr[kc * 8 + 7]);
+        v.x = *reinterpret_cast<const uint32_t*>(&a0), v.y = *reinterpret_cast<const uint32_t*>(&a1);
+        v.z = *reinterpret_cast<const uint32_t*>(&a2), v.w = *reinterpret_cast<const uint32_t*>(&a3);
         *reinterpret_cast<uint4*>(my_ax + canon16(row, half * KH + kc * 8, kKx)) = v;
       }
     };
@@ -348,7 +357,7 @@ __global__ void __launch_bounds__(tc::kThreads, 1) gru_window_tc_kernel(const Gr
           tmem_ld8(d + 3 * H + c * 8, pin);
           tmem_ld8(d + 2 * H + c * 8, phn);      // zero at the window's first step (written by the zero block)
           asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-          uint32_t q0[8], q1[8], q2[8];
+          float hv8[8];
           const float4* bz = reinterpret_cast<const float4*>(bias + u0 + c * 8);   // 16-byte aligned: u0 + 8c
           const float4 br0 = bz[0], br1 = bz[1];
           const float4 bz0 = bz[H / 4], bz1 = bz[H / 4 + 1];
@@ -358,17 +367,18 @@ __global__ void __launch_bounds__(tc::kThreads, 1) gru_window_tc_kernel(const Gr
           const float b_z[8] = {bz0.x, bz0.y, bz0.z, bz0.w, bz1.x, bz1.y, bz1.z, bz1.w};
           const float b_i[8] = {bi0.x, bi0.y, bi0.z, bi0.w, bi1.x, bi1.y, bi1.z, bi1.w};
           const float b_h[8] = {bh0.x, bh0.y, bh0.z, bh0.w, bh1.x, bh1.y, bh1.z, bh1.w};
+          constexpr float kSig = -1.4426950408889634f * kInvWScale;   // accumulators carry 64 x the pre-activation
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
-            const float r = rcp_approx(1.0f + ex2_approx(fmaf(pr[j], -1.4426950408889634f, b_r[j])));
-            const float z = rcp_approx(1.0f + ex2_approx(fmaf(pz[j], -1.4426950408889634f, b_z[j])));
-            const float ghn = phn[j] + b_h[j];
-            const float pre = fmaf(r, ghn, pin[j] + b_i[j]);
+            const float r = rcp_approx(1.0f + ex2_approx(fmaf(pr[j], kSig, b_r[j])));
+            const float z = rcp_approx(1.0f + ex2_approx(fmaf(pz[j], kSig, b_z[j])));
+            const float ghn = fmaf(phn[j], kInvWScale, b_h[j]);
+            const float pre = fmaf(r, ghn, fmaf(pin[j], kInvWScale, b_i[j]));
             // tanh(v) = 1 - 2 / (1 + 2^(2 v log2 e))
             const float nn = fmaf(-2.0f, rcp_approx(1.0f + ex2_approx(2.8853900817779268f * pre)), 1.0f);
             const float hv = fmaf(z, h[c * 8 + j] - nn, nn);   // (1 - z) n + z h
             h[c * 8 + j] = hv;
-            split3_trunc(hv, q0[j], q1[j], q2[j]);
+            hv8[j] = hv;
             if (STORE && b < a.B) {   // rows of a warp are consecutive envs: every store below is one 128-byte line
               const long long f = (long long)(u0 + c * 8 + j) * a.B;
               const long long hb = (long long)H * a.B;
@@ -377,13 +387,12 @@ __global__ void __launch_bounds__(tc::kThreads, 1) gru_window_tc_kernel(const Gr
             }
           }
           if (has_next) {
+            uint32_t q0[4], q1[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) split2h(hv8[2 * j], hv8[2 * j + 1], q0[j], q1[j]);
             const int o = canon16(row, u0 + c * 8, H);
-            *reinterpret_cast<uint4*>(my_ah + o) =
-                make_uint4(pack_hi(q0[0], q0[1]), pack_hi(q0[2], q0[3]), pack_hi(q0[4], q0[5]), pack_hi(q0[6], q0[7]));
-            *reinterpret_cast<uint4*>(my_ah + S::kAh + o) =
-                make_uint4(pack_hi(q1[0], q1[1]), pack_hi(q1[2], q1[3]), pack_hi(q1[4], q1[5]), pack_hi(q1[6], q1[7]));
-            *reinterpret_cast<uint4*>(my_ah + 2 * S::kAh + o) =
-                make_uint4(pack_hi(q2[0], q2[1]), pack_hi(q2[2], q2[3]), pack_hi(q2[4], q2[5]), pack_hi(q2[6], q2[7]));
+            *reinterpret_cast<uint4*>(my_ah + o) = make_uint4(q0[0], q0[1], q0[2], q0[3]);
+            *reinterpret_cast<uint4*>(my_ah + S::kAh + o) = make_uint4(q1[0], q1[1], q1[2], q1[3]);
           }
         }
         if (has_next) {
