@@ -53,7 +53,7 @@ struct GruTcArgs {
   int padded;    // 1: steps before the episode start run on zero inputs; 0: they do not exist (rollout windows)
   // training direction (store = 1, padded = 1): every step's gate activations and hidden state are kept for BPTT
   int store;
-  View acts;     // [.. 4H ..] r, z, n, gh_n of step 0; step s is acts_step floats further
+  View acts;     // [.. 4H ..] r, z, n, gh_n of step 0; step s is acts_step floats further (p == nullptr: not kept)
   View hs;       // [.. H ..]  h after step 0; step s is hs_step floats further (h_out is not written when store = 1)
   long long acts_step, hs_step;
 };
@@ -345,8 +345,8 @@ __global__ void __launch_bounds__(tc::kThreads, 1) gru_window_tc_kernel(const Gr
         const bool first = s == s0;
         float* acts_row = nullptr;
         float* hs_row = nullptr;
-        if (STORE && b < a.B) {
-          acts_row = view_ptr(a.acts, g, t, a.B, b) + (long long)s * a.acts_step;
+        if (STORE && b < a.B) {   // acts.p == nullptr: only h is kept (the recomputing BPTT kernel, gru_bptt_tc.cuh)
+          if (a.acts.p) acts_row = view_ptr(a.acts, g, t, a.B, b) + (long long)s * a.acts_step;
           hs_row = view_ptr(a.hs, g, t, a.B, b) + (long long)s * a.hs_step;
         }
 #pragma unroll
@@ -382,7 +382,7 @@ __global__ void __launch_bounds__(tc::kThreads, 1) gru_window_tc_kernel(const Gr
             if (STORE && b < a.B) {   // rows of a warp are consecutive envs: every store below is one 128-byte line
               const long long f = (long long)(u0 + c * 8 + j) * a.B;
               const long long hb = (long long)H * a.B;
-              acts_row[f] = r, acts_row[f + hb] = z, acts_row[f + 2 * hb] = nn, acts_row[f + 3 * hb] = ghn;
+              if (acts_row) acts_row[f] = r, acts_row[f + hb] = z, acts_row[f + 2 * hb] = nn, acts_row[f + 3 * hb] = ghn;
               hs_row[f] = hv;
             }
           }

@@ -18,6 +18,7 @@
 
 #include "gru_tc.cuh"
 #include "gru_bwd_tc.cuh"
+#include "gru_bptt_tc.cuh"
 #include "wgrad_tc.cuh"
 #include "dense_tc.cuh"
 #include "head_fused.cuh"
@@ -58,8 +59,9 @@ static View make_view(float* p, long long t_stride, int t_off, int N, int feat_p
 // caller -- the library reads no environment variables.  A family that is switched off runs on its FP32 CUDA-core
 // kernel.  Not thread-safe; set before the first launch.
 enum { kSwGruTc = D2D_SWITCH_GRU_WINDOW_TC, kSwBwdTc = D2D_SWITCH_GRU_BPTT_TC, kSwDenseTc = D2D_SWITCH_DENSE_TC,
-       kSwWgradTc = D2D_SWITCH_WGRAD_TC, kSwFusedHead = D2D_SWITCH_FUSED_HEAD, kSwAllTc = D2D_SWITCH_ALL_TC, kSwCount };
-static int g_switch_off[kSwCount] = {0, 0, 0, 0, 0, 0};
+       kSwWgradTc = D2D_SWITCH_WGRAD_TC, kSwFusedHead = D2D_SWITCH_FUSED_HEAD, kSwAllTc = D2D_SWITCH_ALL_TC,
+       kSwBpttRecompute = D2D_SWITCH_BPTT_RECOMPUTE, kSwCount };
+static int g_switch_off[kSwCount] = {0, 0, 0, 0, 0, 0, 0};
 static bool switched_off(int which) { return g_switch_off[which] != 0; }
 static bool tc_enabled() { return g_switch_off[kSwAllTc] == 0; }
 
@@ -347,6 +349,30 @@ static int launch_head_fused(const d2d_net* n, const float* params, const View& 
 static bool gru_bwd_tc_eligible(const d2d_net* n) {
   return tc_enabled() && !switched_off(kSwBwdTc) && n->arch == D2D_NET_GRU && (n->H == 32 || n->H == 64) && n->L >= 1;
 }
+static bool gru_tc_eligible(const d2d_net* n);
+
+// recomputing BPTT (gru_bptt_tc.cuh): needs the inputs exact in one fp16 plane (integer observations) and I <= 32;
+// then the forward kernel keeps only h of every step
+static bool gru_bptt_recompute_eligible(const d2d_net* n) {
+  return gru_bwd_tc_eligible(n) && gru_tc_eligible(n) && !switched_off(kSwBpttRecompute);
+}
+
+template <int H>
+static int launch_gru_bptt_tc_h(const d2d_net* n, const GruBpttArgs& a, cudaStream_t s, int* strips) {
+  static bool attr = false;
+  if (!attr) {
+    D2D_CUDA(cudaFuncSetAttribute(gru_bptt_tc_kernel<H>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  (int)tcr::Smem<H>::bytes));
+    attr = true;
+  }
+  const int tiles = (a.t1 - a.t0) * ((n->B + tc::kM - 1) / tc::kM);
+  if (tiles <= 0) return D2D_OK;
+  const int gx = std::max(1, std::min(std::min(tiles, 148 / n->N), n->n_strips));
+  gru_bptt_tc_kernel<H><<<dim3(gx, n->N), tcr::kThreads, tcr::Smem<H>::bytes, s>>>(a);
+  D2D_LAUNCHED();
+  *strips = gx;
+  return D2D_OK;
+}
 
 template <int H>
 static int launch_gru_bwd_tc_h(const d2d_net* n, const GruBwdTcArgs& a, cudaStream_t s, int* strips) {
@@ -388,7 +414,8 @@ static long long floats_per_t(const d2d_net* n, bool train) {
   const long long H = n->H, O = n->O, L = n->arch == D2D_NET_GRU ? n->L : 0;
   long long f = H + O;                                // y1, logits
   if (n->arch == D2D_NET_GRU) f += 3 * H + 3 * H;     // gi, gh
-  if (n->arch == D2D_NET_GRU) f += train ? L * H + 4 * L * H : 2 * H;   // hs (+ acts)
+  // hs of every step; the 4H activations per step only for the BPTT kernels that do not recompute them
+  if (n->arch == D2D_NET_GRU) f += train ? L * H + (gru_bptt_recompute_eligible(n) ? 0 : 4 * L * H) : 2 * H;
   if (train) f += O + H;                              // dl, dy1
   if (train && n->arch == D2D_NET_GRU) f += 2 * H + 3 * H;   // dh ping-pong, dgi
   return f * NB;
@@ -418,7 +445,7 @@ static int plan_chunk(d2d_net* n, bool train, int n_t, Chunk& c) {
     c.gh = take((long long)Tc * 3 * H * NB);
     if (train) {
       c.hs = take((long long)L * Tc * H * NB);
-      c.acts = take((long long)L * Tc * 4 * H * NB);
+      if (!gru_bptt_recompute_eligible(n)) c.acts = take((long long)L * Tc * 4 * H * NB);
     } else {
       c.hs = take((long long)2 * Tc * H * NB);
     }
@@ -468,7 +495,8 @@ static int forward_chunk(d2d_net* n, const float* params, const float* x, int x_
     if (use_tc) {
       const View hl = make_view(hs_ptr(n, c, train, L - 1), H * NB, -c0, N, H, B);
       if (train) {
-        const View av = make_view(c.acts, 4 * H * NB, -c0, N, 4 * H, B);
+        View av = make_view(c.acts, 4 * H * NB, -c0, N, 4 * H, B);
+        if (!c.acts) av.p = nullptr;          // the recomputing BPTT kernel needs h only
         const View hv = make_view(c.hs, H * NB, -c0, N, H, B);
         rc = launch_gru_tc(n, params, xin, hl, c0, c1, padded, s, &av, &hv, (long long)c.Tc * 4 * H * NB,
                            (long long)c.Tc * H * NB);
@@ -540,7 +568,7 @@ static int forward_chunk(d2d_net* n, const float* params, const float* x, int x_
 
 // backward of chunk [c0, c1) given c.dl = d(loss)/d(pre-activation outputs); accumulates into grads
 static int backward_chunk(d2d_net* n, const float* params, const float* x, int x_lead, int c0, int c1,
-                          const Chunk& c, float* grads, cudaStream_t s) {
+                          const Chunk& c, float* grads, float inv_rows, cudaStream_t s) {
   const int N = n->N, B = n->B, H = n->H, O = n->O;
   const long long NB = (long long)N * B;
   View xin;
@@ -585,7 +613,48 @@ static int backward_chunk(d2d_net* n, const float* params, const float* x, int x
   const View dgh = make_view(c.gh, 3 * H * NB, -c0, N, 3 * H, B);
   Wt whh{&n->o_whh, &n->o_bhh, nullptr, H, 3 * H};
   const bool fused = gru_bwd_tc_eligible(n);
-  if (fused) {
+  if (fused && gru_bptt_recompute_eligible(n)) {
+    // one kernel walks the whole window backwards and RECOMPUTES every step's gates from (x, h_prev) on the tensor
+    // cores: the forward kernel kept only h.  d(gi) is accumulated per observation, dW_hh / db_hh per CTA.
+    GruBpttArgs ba;
+    memset(&ba, 0, sizeof(ba));
+    ba.x = xin;
+    ba.hs = make_view(c.hs, H * NB, -c0, N, H, B);
+    ba.dh = make_view(dh_cur, H * NB, -c0, N, H, B);
+    ba.dgi = dgi;
+    ba.w = params, ba.w_agent_stride = n->stride;
+    for (int g = 0; g < N; ++g) {
+      ba.wih_off[g] = n->o_wih[g], ba.whh_off[g] = n->o_whh[g], ba.bih_off[g] = n->o_bih[g], ba.bhh_off[g] = n->o_bhh[g];
+      ba.in_dim[g] = n->in_dim[g];
+    }
+    ba.hs_step = (long long)c.Tc * H * NB;
+    // d(gh) ~ 1 / rows (the loss is a mean): the kernel scales it into the fp16 range by a power of two taken from the
+    // largest |dh| of the chunk
+    {
+      unsigned int* amax = reinterpret_cast<unsigned int*>(n->partial + (long long)n->N * n->n_strips * n->part_stride);
+      D2D_CUDA(cudaMemsetAsync(amax, 0, 4, s));
+      const long long cnt = (long long)(c1 - c0) * H * NB;
+      absmax_kernel<<<grid_for(cnt, 256), 256, 0, s>>>(dh_cur, cnt, amax);
+      D2D_LAUNCHED();
+      ba.dh_absmax = reinterpret_cast<const float*>(amax);
+    }
+    (void)inv_rows;
+    ba.L = L, ba.B = B, ba.t0 = c0, ba.t1 = c1;
+    ba.partial = n->partial, ba.part_stride = n->part_stride;
+    int strips = 0;
+    rc = n->H == 32 ? launch_gru_bptt_tc_h<32>(n, ba, s, &strips) : launch_gru_bptt_tc_h<64>(n, ba, s, &strips);
+    if (rc) return rc;
+    if (strips > 0) {   // dW_hh / db_hh: fixed-order sum of the per-CTA partials
+      WreduceArgs r;
+      memset(&r, 0, sizeof(r));
+      r.partial = n->partial, r.part_stride = n->part_stride, r.n_strips = strips, r.grads = grads;
+      r.g_agent_stride = n->stride, r.out_dim = 3 * H, r.with_bias = 1;
+      for (int g = 0; g < N; ++g) r.w_off[g] = n->o_whh[g], r.b_off[g] = n->o_bhh[g], r.in_dim[g] = H;
+      const int total = 3 * H * H + 3 * H;
+      wreduce_kernel<<<dim3((total + 255) / 256, N), 256, 0, s>>>(r);
+      D2D_LAUNCHED();
+    }
+  } else if (fused) {
     // one kernel walks the whole window backwards (d(h) in registers, d(gh) W_hh on tcgen05); it leaves d(gh) of
     // step s in the first 3H features of that step's activation block and d(gi) accumulated per observation
     GruBwdTcArgs ba;
@@ -692,7 +761,7 @@ extern "C" int d2d_net_create(const d2d_net_config* cfg, d2d_net** out) {
   }
   n->n_strips = 64;
   n->part_stride = (long long)std::max(3 * H, std::max(H, O)) * std::max(n->max_in, 3 * H) + 3 * H + 64;
-  cudaError_t e = cudaMalloc((void**)&n->partial, (size_t)n->N * n->n_strips * n->part_stride * 4);
+  cudaError_t e = cudaMalloc((void**)&n->partial, (size_t)n->N * n->n_strips * n->part_stride * 4 + 64);   // + scalars
   if (e != cudaSuccess) {
     set_error("d2d_net_create: cudaMalloc failed: %s", cudaGetErrorString(e));
     delete n;
@@ -898,7 +967,7 @@ extern "C" int d2d_ppo_policy_grad(d2d_net* n, const float* params, const float*
     const long long rows = (long long)(c1 - c0) * n->B;
     ppo_dlogits_kernel<<<grid_for(rows, 128), 128, 0, s>>>(h);
     D2D_LAUNCHED();
-    if ((rc = backward_chunk(n, params, x, x_lead, c0, c1, c, grads, s))) return rc;
+    if ((rc = backward_chunk(n, params, x, x_lead, c0, c1, c, grads, inv_rows, s))) return rc;
   }
   return D2D_OK;
 }
@@ -928,7 +997,7 @@ extern "C" int d2d_value_grad(d2d_net* n, const float* params, const float* x, i
     const long long rows = (long long)(c1 - c0) * n->B;
     mse_dvalue_kernel<<<dim3(grid_for(rows, 128), n->N), 128, 0, s>>>(m);
     D2D_LAUNCHED();
-    if ((rc = backward_chunk(n, params, x, x_lead, c0, c1, c, grads, s))) return rc;
+    if ((rc = backward_chunk(n, params, x, x_lead, c0, c1, c, grads, inv_rows, s))) return rc;
   }
   return D2D_OK;
 }

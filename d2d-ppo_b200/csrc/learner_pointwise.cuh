@@ -616,4 +616,13 @@ __global__ void check_bf16_exact_kernel(const float* x, long long count, long lo
   if ((threadIdx.x & 31) == 0 && bad) atomicAdd(n_inexact, (unsigned long long)bad);
 }
 
+// max |x| over a buffer, as the bit pattern of a non-negative float (atomicMax on uint32); *out zeroed by the caller
+__global__ void absmax_kernel(const float* __restrict__ x, long long n, unsigned int* out) {
+  float m = 0.f;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    m = fmaxf(m, fabsf(x[i]));
+  for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xFFFFFFFFu, m, o));
+  if ((threadIdx.x & 31) == 0 && m > 0.f) atomicMax(out, __float_as_uint(m));
+}
+
 }  // namespace d2d
