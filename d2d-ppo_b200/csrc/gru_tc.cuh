@@ -56,6 +56,11 @@ struct GruTcArgs {
   View acts;     // [.. 4H ..] r, z, n, gh_n of step 0; step s is acts_step floats further (p == nullptr: not kept)
   View hs;       // [.. H ..]  h after step 0; step s is hs_step floats further (h_out is not written when store = 1)
   long long acts_step, hs_step;
+  // fused network head (kernel template OMAX > 0, inference direction): out = W2 relu(W1 h_last + b1) + b2 is written
+  // instead of h_last (reference: the `layers` Sequential of RNN, d2d_ppo.py:36-41,54)
+  View out;      // [.. O ..] pre-activation outputs
+  int w1_off[D2D_MAX_AGENTS], b1_off[D2D_MAX_AGENTS], w2_off[D2D_MAX_AGENTS], b2_off[D2D_MAX_AGENTS];
+  int O;
 };
 
 namespace tc {
@@ -174,12 +179,20 @@ struct Smem {
   static constexpr int kAh = kM * H;
   static constexpr int kAx = kM * kKx;
   static constexpr size_t bytes = (size_t)(2 * kWih + 2 * kWhh + 2 * 2 * kAh + 2 * kAx) * 2 + 4 * H * 4 + 64;
+  // fused head: W1 planes [2][H][H] fp16, then fp32: b1 [H], W2^T [H][OMAX], b2 [OMAX], partial sums [2 slots][128][OMAX]
+  static constexpr size_t head_bytes(int omax) {
+    return (size_t)2 * H * H * 2 + (size_t)(H + H * omax + omax + 2 * kM * omax) * 4 + 16;
+  }
 };
 
 }  // namespace tc
 
-// STORE: the training direction (a.store); compile time so that the rollout kernel carries none of the store code
-template <int H, bool STORE>
+// STORE: the training direction (a.store); compile time so that the rollout kernel carries none of the store code.
+// OMAX > 0 (inference direction only): the network head is fused behind the last step -- Linear(H, H) as one more
+// two-plane GEMM on the h planes the step already staged (12 MMAs), ReLU and Linear(H, O <= OMAX) on the CUDA cores from
+// TMEM, the two unit halves of a row combined through shared memory -- and the kernel writes the O pre-activation
+// outputs instead of h_last: no head kernel, no h_last round trip through HBM.
+template <int H, bool STORE, int OMAX = 0>
 __global__ void __launch_bounds__(tc::kThreads, 1) gru_window_tc_kernel(const GruTcArgs a) {
   using namespace tc;
   using S = Smem<H>;
@@ -194,6 +207,14 @@ __global__ void __launch_bounds__(tc::kThreads, 1) gru_window_tc_kernel(const Gr
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 4);
   uint64_t* a_ready = bars;
   uint64_t* d_ready = bars + 2;
+  constexpr bool HEAD = OMAX > 0;
+  static_assert(!(HEAD && STORE), "the fused head is for the inference direction");
+  constexpr int OP = HEAD ? OMAX : 1;
+  __half* w1p = reinterpret_cast<__half*>(smem_raw + ((S::bytes + 15) & ~(size_t)15));   // [2 planes][H][H]
+  float* b1s = reinterpret_cast<float*>(w1p + 2 * H * H);                                 // [H]
+  float* w2t = b1s + H;                                                                   // [H][OP] = W2[o][j]
+  float* b2s = w2t + H * OP;                                                              // [OP]
+  float* part = b2s + OP;                                                                 // [2 slots][128][OP]
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int g = blockIdx.y;
@@ -219,6 +240,22 @@ __global__ void __launch_bounds__(tc::kThreads, 1) gru_window_tc_kernel(const Gr
     split2h1(kWScale * Whh[i], p0, p1);
     const int o = canon16(n, k, H);
     whh[o] = p0, whh[S::kWhh + o] = p1;
+  }
+  if constexpr (HEAD) {
+    const float* base = a.w + g * a.w_agent_stride;
+    for (int i = tid; i < H * H; i += kThreads) {
+      const int n = i / H, k = i % H;
+      __half p0, p1;
+      split2h1(kWScale * base[a.w1_off[g] + i], p0, p1);
+      const int o = canon16(n, k, H);
+      w1p[o] = p0, w1p[H * H + o] = p1;
+    }
+    for (int i = tid; i < H * OP; i += kThreads) {
+      const int j = i / OP, o = i % OP;
+      w2t[i] = o < a.O ? base[a.w2_off[g] + o * H + j] : 0.f;
+    }
+    for (int i = tid; i < H; i += kThreads) b1s[i] = base[a.b1_off[g] + i];
+    for (int i = tid; i < OP; i += kThreads) b2s[i] = i < a.O ? base[a.b2_off[g] + i] : 0.f;
   }
   // biases, pre-scaled for the ex2-based gates: sigmoid(a) = 1 / (1 + 2^(-a log2 e))
   for (int i = tid; i < 4 * H; i += kThreads) {
@@ -297,6 +334,24 @@ __global__ void __launch_bounds__(tc::kThreads, 1) gru_window_tc_kernel(const Gr
                    : "memory");
     };
 
+    const uint64_t dw1 = desc16(smem_u32(w1p), H);
+    const uint32_t idh = idesc_f16(H);
+    auto issue_head = [&]() {   // Y1 = h_last W1^T (x 64) into the slot's columns [0, H): h0 w0, h0 w1, h1 w0
+      mbar_wait(&a_ready[slot], ph_a);
+      ph_a ^= 1u;
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+#pragma unroll
+      for (int pr = 0; pr < 3; ++pr) {
+        const int i = pr == 2 ? 1 : 0, j = pr == 1 ? 1 : 0;
+#pragma unroll
+        for (int k16 = 0; k16 < H / 16; ++k16)
+          mma_bf16(d_slot, desc_adv(dah, (i * S::kAh) * 2 + k16 * 256), desc_adv(dw1, (j * H * H) * 2 + k16 * 256), idh,
+                   pr + k16 > 0);
+      }
+      asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];"
+                   ::"r"(smem_u32(&d_ready[slot]))
+                   : "memory");
+    };
     auto load_x = [&](int t_obs, int b, float* xr) {   // this thread's half of the row's observation -> registers
       const bool ok = b < a.B;
       const float* xp = view_ptr(a.x, g, t_obs, a.B, ok ? b : 0);
@@ -386,7 +441,7 @@ __global__ void __launch_bounds__(tc::kThreads, 1) gru_window_tc_kernel(const Gr
               hs_row[f] = hv;
             }
           }
-          if (has_next) {
+          if (has_next || HEAD) {   // the head GEMM reads h_last from the same operand tiles
             uint32_t q0[4], q1[4];
 #pragma unroll
             for (int j = 0; j < 4; ++j) split2h(hv8[2 * j], hv8[2 * j + 1], q0[j], q1[j]);
@@ -400,6 +455,43 @@ __global__ void __launch_bounds__(tc::kThreads, 1) gru_window_tc_kernel(const Gr
           publish();
           if (issuer) issue(false);
           __syncwarp();
+        } else if constexpr (HEAD) {
+          publish();
+          if (issuer) issue_head();
+          __syncwarp();
+          mbar_wait(&d_ready[slot], ph);
+          ph ^= 1u;
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+          float po[OP];
+#pragma unroll
+          for (int o = 0; o < OP; ++o) po[o] = 0.f;
+#pragma unroll
+          for (int c = 0; c < HH / 8; ++c) {
+            float y[8];
+            tmem_ld8(d + c * 8, y);
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const int u = u0 + c * 8 + j;
+              const float yv = fmaxf(fmaf(y[j], kInvWScale, b1s[u]), 0.f);     // relu(W1 h + b1)
+#pragma unroll
+              for (int o = 0; o < OP; ++o) po[o] = fmaf(w2t[u * OP + o], yv, po[o]);
+            }
+          }
+          // the row's two unit halves live in different warps: half 1 hands its partial sums over through shared memory
+          float* pp = part + ((size_t)slot * kM + row) * OP;
+          if (half == 1) {
+#pragma unroll
+            for (int o = 0; o < OP; ++o) pp[o] = po[o];
+          }
+          asm volatile("bar.sync %0, %1;" ::"r"(1 + slot), "r"(kGateThreads) : "memory");
+          if (half == 0 && b < a.B) {
+            float* op = view_ptr(a.out, g, t, a.B, b);
+#pragma unroll
+            for (int o = 0; o < OP; ++o)
+              if (o < a.O) op[(long long)o * a.B] = po[o] + pp[o] + b2s[o];
+          }
+          // TMEM reads of this tile are complete before the next tile's first MMA: its publish() fences them
         } else {
           // TMEM reads of this tile are complete before the next tile's first MMA: its publish() fences them
           if (b < a.B && !STORE) {

@@ -60,8 +60,8 @@ static View make_view(float* p, long long t_stride, int t_off, int N, int feat_p
 // kernel.  Not thread-safe; set before the first launch.
 enum { kSwGruTc = D2D_SWITCH_GRU_WINDOW_TC, kSwBwdTc = D2D_SWITCH_GRU_BPTT_TC, kSwDenseTc = D2D_SWITCH_DENSE_TC,
        kSwWgradTc = D2D_SWITCH_WGRAD_TC, kSwFusedHead = D2D_SWITCH_FUSED_HEAD, kSwAllTc = D2D_SWITCH_ALL_TC,
-       kSwBpttRecompute = D2D_SWITCH_BPTT_RECOMPUTE, kSwCount };
-static int g_switch_off[kSwCount] = {0, 0, 0, 0, 0, 0, 0};
+       kSwBpttRecompute = D2D_SWITCH_BPTT_RECOMPUTE, kSwWindowHead = D2D_SWITCH_WINDOW_HEAD, kSwCount };
+static int g_switch_off[kSwCount] = {0, 0, 0, 0, 0, 0, 0, 0};
 static bool switched_off(int which) { return g_switch_off[which] != 0; }
 static bool tc_enabled() { return g_switch_off[kSwAllTc] == 0; }
 
@@ -273,44 +273,60 @@ static bool gru_tc_eligible(const d2d_net* n) {
          (n->H == 16 || n->H == 32 || n->H == 48 || n->H == 64);
 }
 
-template <int H, bool STORE>
+template <int H, bool STORE, int OMAX>
 static int launch_gru_tc_hs(const d2d_net* n, const GruTcArgs& a, cudaStream_t s) {
+  const size_t smem = OMAX > 0 ? ((tc::Smem<H>::bytes + 15) & ~(size_t)15) + tc::Smem<H>::head_bytes(OMAX) : tc::Smem<H>::bytes;
   static bool attr = false;
   if (!attr) {
-    D2D_CUDA(cudaFuncSetAttribute(gru_window_tc_kernel<H, STORE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                  (int)tc::Smem<H>::bytes));
+    D2D_CUDA(cudaFuncSetAttribute(gru_window_tc_kernel<H, STORE, OMAX>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  (int)smem));
     attr = true;
   }
   const int pairs = (a.t1 - a.t0) * ((n->B + 2 * tc::kM - 1) / (2 * tc::kM));
   if (pairs <= 0) return D2D_OK;
   const int gx = std::max(1, std::min(pairs, 148 / n->N));   // one CTA per SM (all of its shared memory and TMEM)
-  gru_window_tc_kernel<H, STORE><<<dim3(gx, n->N), tc::kThreads, tc::Smem<H>::bytes, s>>>(a);
+  gru_window_tc_kernel<H, STORE, OMAX><<<dim3(gx, n->N), tc::kThreads, smem, s>>>(a);
   D2D_LAUNCHED();
   return D2D_OK;
 }
 
 template <int H>
-static int launch_gru_tc_h(const d2d_net* n, const GruTcArgs& a, cudaStream_t s) {
-  return a.store ? launch_gru_tc_hs<H, true>(n, a, s) : launch_gru_tc_hs<H, false>(n, a, s);
+static int launch_gru_tc_h(const d2d_net* n, const GruTcArgs& a, cudaStream_t s, bool head) {
+  if (a.store) return launch_gru_tc_hs<H, true, 0>(n, a, s);
+  if constexpr (H == 32 || H == 64) {
+    if (head) {
+      if (a.O <= 1) return launch_gru_tc_hs<H, false, 1>(n, a, s);
+      if (a.O <= 8) return launch_gru_tc_hs<H, false, 8>(n, a, s);
+      return launch_gru_tc_hs<H, false, 16>(n, a, s);
+    }
+  }
+  return launch_gru_tc_hs<H, false, 0>(n, a, s);
 }
 
+static bool head_fused_eligible(const d2d_net* n);
+
+// head_out != nullptr (inference direction): the network head is fused behind the window and *head_out receives the
+// pre-activation outputs; h_out is then not written
 static int launch_gru_tc(const d2d_net* n, const float* params, const View& x, const View& h_out, int t0, int t1,
                          int padded, cudaStream_t s, const View* acts = nullptr, const View* hs = nullptr,
-                         long long acts_step = 0, long long hs_step = 0) {
+                         long long acts_step = 0, long long hs_step = 0, const View* head_out = nullptr) {
   GruTcArgs a;
   memset(&a, 0, sizeof(a));
   a.x = x, a.h_out = h_out, a.w = params, a.w_agent_stride = n->stride;
-  if (acts) a.store = 1, a.acts = *acts, a.hs = *hs, a.acts_step = acts_step, a.hs_step = hs_step;
+  if (hs) a.store = 1, a.acts = *acts, a.hs = *hs, a.acts_step = acts_step, a.hs_step = hs_step;
   for (int g = 0; g < n->N; ++g) {
     a.wih_off[g] = n->o_wih[g], a.whh_off[g] = n->o_whh[g], a.bih_off[g] = n->o_bih[g], a.bhh_off[g] = n->o_bhh[g];
     a.in_dim[g] = n->in_dim[g];
+    a.w1_off[g] = n->o_w1[g], a.b1_off[g] = n->o_b1[g], a.w2_off[g] = n->o_w2[g], a.b2_off[g] = n->o_b2[g];
   }
-  a.L = n->L, a.B = n->B, a.t0 = t0, a.t1 = t1, a.padded = padded;
+  a.L = n->L, a.B = n->B, a.t0 = t0, a.t1 = t1, a.padded = padded, a.O = n->O;
+  const bool head = head_out != nullptr;
+  if (head) a.out = *head_out;
   switch (n->H) {
-    case 16: return launch_gru_tc_h<16>(n, a, s);
-    case 32: return launch_gru_tc_h<32>(n, a, s);
-    case 48: return launch_gru_tc_h<48>(n, a, s);
-    default: return launch_gru_tc_h<64>(n, a, s);
+    case 16: return launch_gru_tc_h<16>(n, a, s, false);
+    case 32: return launch_gru_tc_h<32>(n, a, s, head);
+    case 48: return launch_gru_tc_h<48>(n, a, s, false);
+    default: return launch_gru_tc_h<64>(n, a, s, head);
   }
 }
 
@@ -500,6 +516,9 @@ static int forward_chunk(d2d_net* n, const float* params, const float* x, int x_
         const View hv = make_view(c.hs, H * NB, -c0, N, H, B);
         rc = launch_gru_tc(n, params, xin, hl, c0, c1, padded, s, &av, &hv, (long long)c.Tc * 4 * H * NB,
                            (long long)c.Tc * H * NB);
+      } else if (head_fused_eligible(n) && !switched_off(kSwWindowHead)) {
+        // inference direction: the head is fused behind the window, the kernel writes the outputs directly
+        return launch_gru_tc(n, params, xin, hl, c0, c1, padded, s, nullptr, nullptr, 0, 0, &lg);
       } else {
         rc = launch_gru_tc(n, params, xin, hl, c0, c1, padded, s);
       }
@@ -863,6 +882,10 @@ extern "C" int d2d_net_rollout_step(d2d_net* n, const float* params, const float
   const bool use_tc = gru_tc_eligible(n);
   if (use_tc) {   // the tensor-core window kernel re-reads the L observations (L x I floats per row): no ring needed
     const View hl = make_view(hs_ptr(n, c, false, L - 1), H * NB, -t, N, H, B);
+    if (head_fused_eligible(n) && !switched_off(kSwWindowHead)) {   // window + head in ONE launch, outputs written in place
+      const View lgo = make_view(out, O * NB, -t, N, O, B);
+      return launch_gru_tc(n, params, xin, hl, t, t + 1, 0, s, nullptr, nullptr, 0, 0, &lgo);
+    }
     if ((rc = launch_gru_tc(n, params, xin, hl, t, t + 1, 0, s))) return rc;
   }
   if (!use_tc && !n->gi_ring) D2D_CUDA(cudaMalloc((void**)&n->gi_ring, (size_t)L * 3 * H * NB * 4));

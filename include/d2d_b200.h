@@ -271,6 +271,7 @@ int d2d_net_check_inputs(const d2d_net* net, const float* x, int x_lead, int t0,
 #define D2D_SWITCH_WGRAD_TC 3
 #define D2D_SWITCH_FUSED_HEAD 4
 #define D2D_SWITCH_ALL_TC 5
+#define D2D_SWITCH_WINDOW_HEAD 7      /* 0: the network head runs as its own kernel behind the GRU window kernel */
 #define D2D_SWITCH_BPTT_RECOMPUTE 6   /* 0: the BPTT kernel reads stored activations instead of recomputing the gates */
 int d2d_set_kernel_switch(int which, int enabled);
 int d2d_get_kernel_switch(int which);
