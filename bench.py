@@ -544,6 +544,9 @@ def run_native(args):
         raise SystemExit("for --gpus N > 1 launch with torch.distributed.run (one rank per GPU)")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    # host threads and first-touch pinned buffers on the GPU's NUMA node (the e2e leg streams pinned memory)
+    from d2d_ppo_b200 import _affinity
+    numa = _affinity.bind_to_gpu_numa(local) if world > 1 else None
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
 
@@ -725,6 +728,7 @@ def run_native(args):
                        "the host every step; two calls in flight",
                 "bound": "PCIe: 48 B of actions per env-step",
                 "h2d_gbs_per_rank": h2d_gbs_rank, "h2d_gbs_all_ranks": h2d_gbs_rank * world,
+                "numa_binding": None if numa is None else {"node": numa[0], "cpus": numa[1]},
                 "limiter": "host -> device copy of the u8 [B,N,C] actions (50.3 MB per step and rank) over each GPU's "
                            "PCIe link; with N ranks the N concurrent pinned-memory copies share the host's memory / "
                            "root-complex bandwidth, so the per-rank rate drops as N grows (no collective is involved); "

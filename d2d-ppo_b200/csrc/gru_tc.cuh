@@ -59,6 +59,7 @@ struct GruTcArgs {
   // fused network head (kernel template OMAX > 0, inference direction): out = W2 relu(W1 h_last + b1) + b2 is written
   // instead of h_last (reference: the `layers` Sequential of RNN, d2d_ppo.py:36-41,54)
   View out;      // [.. O ..] pre-activation outputs
+  View y1;       // [.. H ..] relu(W1 h_last + b1), kept for the backward pass (store mode with a fused head)
   int w1_off[D2D_MAX_AGENTS], b1_off[D2D_MAX_AGENTS], w2_off[D2D_MAX_AGENTS], b2_off[D2D_MAX_AGENTS];
   int O;
 };
@@ -188,7 +189,7 @@ struct Smem {
 }  // namespace tc
 
 // STORE: the training direction (a.store); compile time so that the rollout kernel carries none of the store code.
-// OMAX > 0 (inference direction only): the network head is fused behind the last step -- Linear(H, H) as one more
+// OMAX > 0: the network head is fused behind the last step -- Linear(H, H) as one more
 // two-plane GEMM on the h planes the step already staged (12 MMAs), ReLU and Linear(H, O <= OMAX) on the CUDA cores from
 // TMEM, the two unit halves of a row combined through shared memory -- and the kernel writes the O pre-activation
 // outputs instead of h_last: no head kernel, no h_last round trip through HBM.
@@ -208,7 +209,6 @@ __global__ void __launch_bounds__(tc::kThreads, 1) gru_window_tc_kernel(const Gr
   uint64_t* a_ready = bars;
   uint64_t* d_ready = bars + 2;
   constexpr bool HEAD = OMAX > 0;
-  static_assert(!(HEAD && STORE), "the fused head is for the inference direction");
   constexpr int OP = HEAD ? OMAX : 1;
   __half* w1p = reinterpret_cast<__half*>(smem_raw + ((S::bytes + 15) & ~(size_t)15));   // [2 planes][H][H]
   float* b1s = reinterpret_cast<float*>(w1p + 2 * H * H);                                 // [H]
@@ -474,6 +474,7 @@ __global__ void __launch_bounds__(tc::kThreads, 1) gru_window_tc_kernel(const Gr
             for (int j = 0; j < 8; ++j) {
               const int u = u0 + c * 8 + j;
               const float yv = fmaxf(fmaf(y[j], kInvWScale, b1s[u]), 0.f);     // relu(W1 h + b1)
+              if (STORE && b < a.B) view_ptr(a.y1, g, t, a.B, b)[(long long)u * a.B] = yv;   // for the backward pass
 #pragma unroll
               for (int o = 0; o < OP; ++o) po[o] = fmaf(w2t[u * OP + o], yv, po[o]);
             }

@@ -292,14 +292,19 @@ static int launch_gru_tc_hs(const d2d_net* n, const GruTcArgs& a, cudaStream_t s
 
 template <int H>
 static int launch_gru_tc_h(const d2d_net* n, const GruTcArgs& a, cudaStream_t s, bool head) {
-  if (a.store) return launch_gru_tc_hs<H, true, 0>(n, a, s);
   if constexpr (H == 32 || H == 64) {
+    if (head && a.store) {
+      if (a.O <= 1) return launch_gru_tc_hs<H, true, 1>(n, a, s);
+      if (a.O <= 8) return launch_gru_tc_hs<H, true, 8>(n, a, s);
+      return launch_gru_tc_hs<H, true, 16>(n, a, s);
+    }
     if (head) {
       if (a.O <= 1) return launch_gru_tc_hs<H, false, 1>(n, a, s);
       if (a.O <= 8) return launch_gru_tc_hs<H, false, 8>(n, a, s);
       return launch_gru_tc_hs<H, false, 16>(n, a, s);
     }
   }
+  if (a.store) return launch_gru_tc_hs<H, true, 0>(n, a, s);
   return launch_gru_tc_hs<H, false, 0>(n, a, s);
 }
 
@@ -309,7 +314,8 @@ static bool head_fused_eligible(const d2d_net* n);
 // pre-activation outputs; h_out is then not written
 static int launch_gru_tc(const d2d_net* n, const float* params, const View& x, const View& h_out, int t0, int t1,
                          int padded, cudaStream_t s, const View* acts = nullptr, const View* hs = nullptr,
-                         long long acts_step = 0, long long hs_step = 0, const View* head_out = nullptr) {
+                         long long acts_step = 0, long long hs_step = 0, const View* head_out = nullptr,
+                         const View* y1_out = nullptr) {
   GruTcArgs a;
   memset(&a, 0, sizeof(a));
   a.x = x, a.h_out = h_out, a.w = params, a.w_agent_stride = n->stride;
@@ -322,6 +328,7 @@ static int launch_gru_tc(const d2d_net* n, const float* params, const View& x, c
   a.L = n->L, a.B = n->B, a.t0 = t0, a.t1 = t1, a.padded = padded, a.O = n->O;
   const bool head = head_out != nullptr;
   if (head) a.out = *head_out;
+  if (y1_out) a.y1 = *y1_out;
   switch (n->H) {
     case 16: return launch_gru_tc_h<16>(n, a, s, false);
     case 32: return launch_gru_tc_h<32>(n, a, s, head);
@@ -514,6 +521,9 @@ static int forward_chunk(d2d_net* n, const float* params, const float* x, int x_
         View av = make_view(c.acts, 4 * H * NB, -c0, N, 4 * H, B);
         if (!c.acts) av.p = nullptr;          // the recomputing BPTT kernel needs h only
         const View hv = make_view(c.hs, H * NB, -c0, N, H, B);
+        if (head_fused_eligible(n) && !switched_off(kSwWindowHead))   // window + head + y1 in one launch
+          return launch_gru_tc(n, params, xin, hl, c0, c1, padded, s, &av, &hv, (long long)c.Tc * 4 * H * NB,
+                               (long long)c.Tc * H * NB, &lg, &y1);
         rc = launch_gru_tc(n, params, xin, hl, c0, c1, padded, s, &av, &hv, (long long)c.Tc * 4 * H * NB,
                            (long long)c.Tc * H * NB);
       } else if (head_fused_eligible(n) && !switched_off(kSwWindowHead)) {
