@@ -94,6 +94,8 @@ _SIGNATURES = {
     "d2d_set_kernel_switch": (C.c_int, [C.c_int, C.c_int]),
     "d2d_get_kernel_switch": (C.c_int, [C.c_int]),
     "d2d_net_rollout_step": (C.c_int, [_P, _P, _P, C.c_int, C.c_int, _P, _P]),
+    "d2d_net_rollout_act": (C.c_int, [_P, _P, _P, C.c_int, C.c_int, C.c_int, C.c_int, _P, _P, C.c_uint64, C.c_uint64,
+                                      C.c_int, _P, _P]),
     "d2d_policy_head": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _P, _P, _P, _P, _P,
                                   C.c_uint64, C.c_uint64, C.c_int, _P]),
     "d2d_ppo_policy_grad": (C.c_int, [_P, _P, _P, C.c_int, C.c_int, C.c_int, C.c_int, _P, _P, _P, C.c_int, _P,

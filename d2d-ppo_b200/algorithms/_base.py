@@ -14,7 +14,7 @@ import torch
 
 from .. import _lib as L
 from . import _dist
-from ._nets import NetSet, action_dtype, policy_head, returns_norm_stats
+from ._nets import NetSet, action_dtype, returns_norm_stats
 
 
 class PPOBase:
@@ -70,7 +70,6 @@ class PPOBase:
         # (d2d_ppo.py:341-383) and train() calls it between the epochs of an iteration (:450), so it must not touch
         # the rollout the remaining epochs still update on
         self._eval_storage = None
-        self._logits = torch.empty((1, self.n_agents, self.n_actions, self.B), dtype=torch.float32, device=self.device)
 
     def _new_rollout_storage(self):
         T, B, N, dev = self.T, self.B, self.n_agents, self.device
@@ -100,13 +99,11 @@ class PPOBase:
     def _act(self, t, mode, storage, forced=None):
         """select_action for all agents at time t: actions into act_buf[t], log-probs into logp_buf[t]."""
         obs_buf, act_buf, logp_buf, _ = storage
-        logits = self.policies.rollout_step(obs_buf, self.lead, t, out=self._logits)
         if forced is not None:
             act_buf[t].copy_(forced)
             mode = L.ACT_GIVEN
-        policy_head(logits, self.n_agents, self.B, self.n_actions, self.policy_out, self.dist_kind, mode,
-                    act_buf[t:t + 1], logp_buf[t:t + 1], seed=self._sample_seed(),
-                    env_offset=self.env.env_offset, t_abs0=t)
+        self.policies.rollout_act(obs_buf, self.lead, t, self.dist_kind, mode, act_buf[t], logp_buf[t],
+                                  seed=self._sample_seed(), env_offset=self.env.env_offset, t_abs0=t)
 
     def _run_episode(self, mode, forced_actions=None, state_buf=None, per_step=None, storage=None):
         """One lockstep episode of all B envs.  forced_actions: optional [T, N, B] device-layout actions

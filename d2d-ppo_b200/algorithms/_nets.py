@@ -144,6 +144,17 @@ class NetSet:
                                                    L.ptr(out), L.current_stream()))
         return out
 
+    def rollout_act(self, x, x_lead, t, dist_kind, act_mode, actions_t, logp_t, seed=0, env_offset=0, t_abs0=0,
+                    logits_out=None):
+        """select_action of all agents at time t in one call (d2d_net_rollout_act): forward on the unpadded window,
+        then action (sampled / greedy / given) and log-prob into ``actions_t`` / ``logp_t`` ([N, B] blocks of time t).
+        One kernel launch when the tensor-core window kernel takes the net."""
+        with torch.cuda.device(self.device):
+            L.check(self._lib.d2d_net_rollout_act(self._h, L.ptr(self.params), L.ptr(x), int(x_lead), int(t),
+                                                  int(dist_kind), int(act_mode), L.ptr(actions_t), L.ptr(logp_t),
+                                                  int(seed) & 0xFFFFFFFFFFFFFFFF, int(env_offset), int(t_abs0),
+                                                  L.ptr(logits_out), L.current_stream()))
+
     def count_inexact_inputs(self, x, x_lead, t0, t1):
         """Device u64 scalar: inputs of time blocks [t0, t1) that are not exactly representable in bf16 (the guard of
         ``inputs_bf16_exact``, d2d_net_check_inputs)."""

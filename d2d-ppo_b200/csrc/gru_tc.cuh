@@ -39,6 +39,7 @@
 #include <cuda_fp16.h>
 
 #include "learner_kernels.cuh"
+#include "learner_pointwise.cuh"
 
 namespace d2d {
 
@@ -60,6 +61,10 @@ struct GruTcArgs {
   // instead of h_last (reference: the `layers` Sequential of RNN, d2d_ppo.py:36-41,54)
   View out;      // [.. O ..] pre-activation outputs
   View y1;       // [.. H ..] relu(W1 h_last + b1), kept for the backward pass (store mode with a fused head)
+  // select_action fused behind the head (policy nets at rollout time): sel.actions != nullptr -> the epilogue turns the
+  // outputs into probabilities, selects / reads the action and writes action + log-prob (d2d_ppo.py:159-181);
+  // out.p may then be null
+  DistArgs sel;
   int w1_off[D2D_MAX_AGENTS], b1_off[D2D_MAX_AGENTS], w2_off[D2D_MAX_AGENTS], b2_off[D2D_MAX_AGENTS];
   int O;
 };
@@ -487,10 +492,21 @@ __global__ void __launch_bounds__(tc::kThreads, 1) gru_window_tc_kernel(const Gr
           }
           asm volatile("bar.sync %0, %1;" ::"r"(1 + slot), "r"(kGateThreads) : "memory");
           if (half == 0 && b < a.B) {
-            float* op = view_ptr(a.out, g, t, a.B, b);
 #pragma unroll
-            for (int o = 0; o < OP; ++o)
-              if (o < a.O) op[(long long)o * a.B] = po[o] + pp[o] + b2s[o];
+            for (int o = 0; o < OP; ++o) po[o] += pp[o] + b2s[o];
+            if (a.out.p) {
+              float* op = view_ptr(a.out, g, t, a.B, b);
+#pragma unroll
+              for (int o = 0; o < OP; ++o)
+                if (o < a.O) op[(long long)o * a.B] = po[o];
+            }
+            if (!STORE && OMAX > 1 && a.sel.actions) {   // PPO.select_action on the row's outputs, in registers
+              float lg_[OP], pr_[kMaxOut];       // copies: the helpers index by a runtime count (local memory)
+#pragma unroll
+              for (int o = 0; o < OP; ++o) lg_[o] = po[o];
+              head_probs(a.sel, lg_, 1, pr_);
+              policy_select(a.sel, g, t, b, pr_);
+            }
           }
           // TMEM reads of this tile are complete before the next tile's first MMA: its publish() fences them
         } else {

@@ -315,7 +315,7 @@ static bool head_fused_eligible(const d2d_net* n);
 static int launch_gru_tc(const d2d_net* n, const float* params, const View& x, const View& h_out, int t0, int t1,
                          int padded, cudaStream_t s, const View* acts = nullptr, const View* hs = nullptr,
                          long long acts_step = 0, long long hs_step = 0, const View* head_out = nullptr,
-                         const View* y1_out = nullptr) {
+                         const View* y1_out = nullptr, const DistArgs* sel = nullptr) {
   GruTcArgs a;
   memset(&a, 0, sizeof(a));
   a.x = x, a.h_out = h_out, a.w = params, a.w_agent_stride = n->stride;
@@ -328,6 +328,7 @@ static int launch_gru_tc(const d2d_net* n, const float* params, const View& x, c
   a.L = n->L, a.B = n->B, a.t0 = t0, a.t1 = t1, a.padded = padded, a.O = n->O;
   const bool head = head_out != nullptr;
   if (head) a.out = *head_out;
+  if (sel) a.sel = *sel;
   if (y1_out) a.y1 = *y1_out;
   switch (n->H) {
     case 16: return launch_gru_tc_h<16>(n, a, s, false);
@@ -972,6 +973,45 @@ extern "C" int d2d_policy_head(int N, int B, int O, int n_t, int out_kind, int d
   policy_head_kernel<<<dim3(grid_for(rows, 128), N), 128, 0, as_stream(stream)>>>(h);
   D2D_LAUNCHED();
   return D2D_OK;
+}
+
+// PPO.select_action for all agents at time t in as few launches as possible: GRU window + head + action selection +
+// log-prob in ONE kernel when the tensor-core window kernel takes the net, else rollout_step + policy_head
+extern "C" int d2d_net_rollout_act(d2d_net* n, const float* params, const float* x, int x_lead, int t, int dist_kind,
+                                   int act_mode, void* actions, float* logp, uint64_t seed, uint64_t env_offset,
+                                   int t_abs0, float* logits_out, void* stream) {
+  D2D_REQUIRE(n && params && x && actions && logp, "d2d_net_rollout_act: null argument");
+  D2D_REQUIRE(n->out_kind != D2D_OUT_IDENTITY, "d2d_net_rollout_act: net has no probability output");
+  D2D_REQUIRE(act_mode >= 0 && act_mode <= 2 && (dist_kind == 0 || dist_kind == 1), "d2d_net_rollout_act: bad mode");
+  int rc = check_range(n, x_lead, t, t + 1, "d2d_net_rollout_act");
+  if (rc) return rc;
+  cudaStream_t s = as_stream(stream);
+  const int N = n->N, B = n->B, H = n->H, O = n->O;
+  const long long NB = (long long)N * B;
+  if (gru_tc_eligible(n) && head_fused_eligible(n) && !switched_off(kSwWindowHead) && O > 1 && n->B % 4 == 0) {
+    HeadArgs h;
+    fill_head(h, N, B, O, n->out_kind, dist_kind);
+    h.act_mode = act_mode, h.actions = actions, h.logp = logp, h.act_t_off = -t;
+    h.k0 = (uint32_t)(seed & 0xFFFFFFFFull), h.k1 = (uint32_t)(seed >> 32), h.env_offset = (uint32_t)env_offset;
+    h.t_abs_off = t_abs0 - t;
+    Chunk c;
+    if ((rc = plan_chunk(n, false, 1, c))) return rc;
+    View xin;
+    memset(&xin, 0, sizeof(xin));
+    xin.p = const_cast<float*>(x), xin.t_stride = (long long)n->in_rows * B, xin.t_off = x_lead;
+    for (int g = 0; g < N; ++g) xin.f_off[g] = n->in_off[g];
+    const View hl = make_view(hs_ptr(n, c, false, n->L - 1), H * NB, -t, N, H, B);
+    View lgo = make_view(logits_out, O * NB, -t, N, O, B);   // p == nullptr: outputs are not written
+    const DistArgs sel = h;
+    return launch_gru_tc(n, params, xin, hl, t, t + 1, 0, s, nullptr, nullptr, 0, 0, &lgo, nullptr, &sel);
+  }
+  // generic path: outputs into the chunk scratch (or the caller's buffer), then the head kernel
+  Chunk c;
+  if ((rc = plan_chunk(n, false, 1, c))) return rc;
+  float* lg = logits_out ? logits_out : c.logits;
+  if ((rc = d2d_net_rollout_step(n, params, x, x_lead, t, lg, stream))) return rc;
+  return d2d_policy_head(N, B, O, 1, n->out_kind, dist_kind, act_mode, lg, actions, logp, nullptr, nullptr, seed,
+                         env_offset, t_abs0, stream);
 }
 
 extern "C" int d2d_ppo_policy_grad(d2d_net* n, const float* params, const float* x, int x_lead, int t0, int t1,

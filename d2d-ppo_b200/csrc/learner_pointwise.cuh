@@ -91,10 +91,10 @@ enum { kActSample = 0, kActGreedy = 1, kActGiven = 2 };
 constexpr int kMaxOut = 32;
 constexpr float kProbEps = 1.1920928955078125e-07f;  // torch.finfo(float32).eps
 
-struct HeadArgs {
-  View logits;           // [.. A ..] pre-activation outputs of the last Linear
-  View probs;            // optional out [.. A ..] (p == nullptr: not written)
-  int A, B, t0, t1, n_agents;
+// what select_action needs besides the probabilities (also embedded in the GRU window kernel's arguments, which
+// selects the action in its epilogue: gru_tc.cuh)
+struct DistArgs {
+  int A, B, n_agents;
   int out_kind, dist_kind, act_mode;
   // actions: Bernoulli -> channel bitmask (mask_bytes per element), Categorical -> u8 index;  layout [t][N][B]
   void* actions;
@@ -105,6 +105,12 @@ struct HeadArgs {
   float* entropy;           // may be null
   uint32_t k0, k1, env_offset;
   int t_abs_off;            // Philox timestep = t + t_abs_off
+};
+
+struct HeadArgs : DistArgs {
+  View logits;           // [.. A ..] pre-activation outputs of the last Linear
+  View probs;            // optional out [.. A ..] (p == nullptr: not written)
+  int t0, t1;
   // ---- loss / backward (ppo_dlogits_kernel) ----
   const float* logp_old;    // [t][N][B]
   const float* weight;      // per-row weight (advantage or HAPPO M): [t][N][B] if weight_per_agent else [t][B]
@@ -117,7 +123,7 @@ struct HeadArgs {
   double* loss_sums;        // [N][2]: sum over rows of min(surr1, surr2), sum of entropy
 };
 
-__device__ __forceinline__ void head_probs(const HeadArgs& a, const float* lg, long long sB, float* p) {
+__device__ __forceinline__ void head_probs(const DistArgs& a, const float* lg, long long sB, float* p) {
   if (a.out_kind == kOutSigmoid) {
     for (int j = 0; j < a.A; ++j) p[j] = sigmoidf_(lg[j * sB]);
   } else if (a.out_kind == kOutSoftmax) {
@@ -140,19 +146,19 @@ __device__ __forceinline__ float bce_logits(float x, float y) {
   return (1.0f - y) * x - (fminf(x, 0.f) - log1pf(expf(-fabsf(x))));
 }
 
-__device__ __forceinline__ uint32_t load_action(const HeadArgs& a, long long idx) {
+__device__ __forceinline__ uint32_t load_action(const DistArgs& a, long long idx) {
   if (a.dist_kind == kDistCategorical || a.mask_bytes == 1) return reinterpret_cast<const uint8_t*>(a.actions)[idx];
   if (a.mask_bytes == 2) return reinterpret_cast<const uint16_t*>(a.actions)[idx];
   return reinterpret_cast<const uint32_t*>(a.actions)[idx];
 }
-__device__ __forceinline__ void store_action(const HeadArgs& a, long long idx, uint32_t v) {
+__device__ __forceinline__ void store_action(const DistArgs& a, long long idx, uint32_t v) {
   if (a.dist_kind == kDistCategorical || a.mask_bytes == 1) reinterpret_cast<uint8_t*>(a.actions)[idx] = (uint8_t)v;
   else if (a.mask_bytes == 2) reinterpret_cast<uint16_t*>(a.actions)[idx] = (uint16_t)v;
   else reinterpret_cast<uint32_t*>(a.actions)[idx] = v;
 }
 
 // log-prob and entropy of action `act` under probs p (registers)
-__device__ __forceinline__ void dist_logp_entropy(const HeadArgs& a, const float* p, uint32_t act, float& logp,
+__device__ __forceinline__ void dist_logp_entropy(const DistArgs& a, const float* p, uint32_t act, float& logp,
                                                   float& ent) {
   if (a.dist_kind == kDistBernoulli) {
     float sl = 0.f, se = 0.f;
@@ -179,7 +185,59 @@ __device__ __forceinline__ void dist_logp_entropy(const HeadArgs& a, const float
   }
 }
 
-// act_mode sample / greedy / given -> actions, logp, entropy (rollout: select_action; training: evaluate)
+// select_action / evaluate of one (agent g, time t, env b) row from its probabilities p (registers): act_mode
+// sample / greedy / given -> action, log-prob, entropy (reference d2d_ppo.py:159-196)
+__device__ __forceinline__ void policy_select(const DistArgs& a, int g, int t, int b, const float* p) {
+  const long long idx = (long long)(t + a.act_t_off) * a.act_t_stride + (long long)g * a.B + b;
+  uint32_t act = 0;
+  if (a.act_mode == kActGiven) {
+    act = load_action(a, idx);
+  } else {
+    if (a.dist_kind == kDistBernoulli) {
+      if (a.act_mode == kActGreedy) {
+        for (int j = 0; j < a.A; ++j) act |= (uint32_t)(p[j] > 0.5f) << j;      // d2d_ppo.py:166
+      } else {
+        for (int blk = 0; blk * 4 < a.A; ++blk) {
+          const uint4 r = philox4x32_10(a.env_offset + (uint32_t)b, (uint32_t)(t + a.t_abs_off),
+                                        (uint32_t)g | (kPurposePolicy << 16), (uint32_t)blk, a.k0, a.k1);
+          const uint32_t u[4] = {r.x, r.y, r.z, r.w};
+          for (int l = 0; l < 4 && blk * 4 + l < a.A; ++l) {
+            const int j = blk * 4 + l;
+            const double thr = (double)p[j] * 4294967296.0;          // P(u32 < thr) = p at 2^-32 resolution
+            act |= (uint32_t)((double)u[l] < thr) << j;
+          }
+        }
+      }
+    } else {
+      if (a.act_mode == kActGreedy) {
+        float best = p[0];
+        for (int j = 1; j < a.A; ++j)
+          if (p[j] > best) best = p[j], act = (uint32_t)j;            // argmax, first maximum (d2d_ppo.py:176)
+      } else {
+        const uint4 r = philox4x32_10(a.env_offset + (uint32_t)b, (uint32_t)(t + a.t_abs_off),
+                                      (uint32_t)g | (kPurposePolicy << 16), 0u, a.k0, a.k1);
+        double s = 0.0;
+        for (int j = 0; j < a.A; ++j) s += (double)p[j];
+        const double uu = ((double)r.x + 0.5) * (1.0 / 4294967296.0) * s;
+        double c = 0.0;
+        act = (uint32_t)(a.A - 1);
+        for (int j = 0; j < a.A; ++j) {
+          c += (double)p[j];
+          if (uu < c) {
+            act = (uint32_t)j;
+            break;
+          }
+        }
+      }
+    }
+    store_action(a, idx, act);
+  }
+  float logp, ent;
+  dist_logp_entropy(a, p, act, logp, ent);
+  if (a.logp) a.logp[idx] = logp;
+  if (a.entropy) a.entropy[idx] = ent;
+}
+
 __global__ void policy_head_kernel(const HeadArgs a) {
   const int g = blockIdx.y;
   const long long n = (long long)(a.t1 - a.t0) * a.B;
@@ -192,54 +250,7 @@ __global__ void policy_head_kernel(const HeadArgs a) {
       float* q = view_ptr(a.probs, g, t, a.B, b);
       for (int j = 0; j < a.A; ++j) q[(long long)j * a.B] = p[j];
     }
-    const long long idx = (long long)(t + a.act_t_off) * a.act_t_stride + (long long)g * a.B + b;
-    uint32_t act = 0;
-    if (a.act_mode == kActGiven) {
-      act = load_action(a, idx);
-    } else {
-      if (a.dist_kind == kDistBernoulli) {
-        if (a.act_mode == kActGreedy) {
-          for (int j = 0; j < a.A; ++j) act |= (uint32_t)(p[j] > 0.5f) << j;      // d2d_ppo.py:166
-        } else {
-          for (int blk = 0; blk * 4 < a.A; ++blk) {
-            const uint4 r = philox4x32_10(a.env_offset + (uint32_t)b, (uint32_t)(t + a.t_abs_off),
-                                          (uint32_t)g | (kPurposePolicy << 16), (uint32_t)blk, a.k0, a.k1);
-            const uint32_t u[4] = {r.x, r.y, r.z, r.w};
-            for (int l = 0; l < 4 && blk * 4 + l < a.A; ++l) {
-              const int j = blk * 4 + l;
-              const double thr = (double)p[j] * 4294967296.0;          // P(u32 < thr) = p at 2^-32 resolution
-              act |= (uint32_t)((double)u[l] < thr) << j;
-            }
-          }
-        }
-      } else {
-        if (a.act_mode == kActGreedy) {
-          float best = p[0];
-          for (int j = 1; j < a.A; ++j)
-            if (p[j] > best) best = p[j], act = (uint32_t)j;            // argmax, first maximum (d2d_ppo.py:176)
-        } else {
-          const uint4 r = philox4x32_10(a.env_offset + (uint32_t)b, (uint32_t)(t + a.t_abs_off),
-                                        (uint32_t)g | (kPurposePolicy << 16), 0u, a.k0, a.k1);
-          double s = 0.0;
-          for (int j = 0; j < a.A; ++j) s += (double)p[j];
-          const double uu = ((double)r.x + 0.5) * (1.0 / 4294967296.0) * s;
-          double c = 0.0;
-          act = (uint32_t)(a.A - 1);
-          for (int j = 0; j < a.A; ++j) {
-            c += (double)p[j];
-            if (uu < c) {
-              act = (uint32_t)j;
-              break;
-            }
-          }
-        }
-      }
-      store_action(a, idx, act);
-    }
-    float logp, ent;
-    dist_logp_entropy(a, p, act, logp, ent);
-    if (a.logp) a.logp[idx] = logp;
-    if (a.entropy) a.entropy[idx] = ent;
+    policy_select(a, g, t, b, p);
   }
 }
 

@@ -283,6 +283,17 @@ int d2d_get_kernel_switch(int which);
 int d2d_net_rollout_step(d2d_net* net, const float* params, const float* x, int x_lead, int t, float* out,
                          void* stream);
 
+/* PPO.select_action for all N agents at time t (d2d_ppo.py:159-181 called at :298-309): network forward on the
+ * unpadded window, then the action (sampled from the Philox policy stream, greedy, or given) and its log-prob.
+ * When the tensor-core GRU window kernel takes the net, window + head + selection + log-prob are ONE launch and the
+ * outputs never leave the SM; otherwise d2d_net_rollout_step + d2d_policy_head.
+ *   actions     [N][B] of time t (channel bitmask u8 / i16 / i32 for Bernoulli, u8 index for Categorical); read when
+ *               act_mode = D2D_ACT_GIVEN, written otherwise;   logp f32 [N][B] of time t
+ *   logits_out  f32 [1][N][O][B] or NULL (pre-activation outputs, for callers that want them)                    */
+int d2d_net_rollout_act(d2d_net* net, const float* params, const float* x, int x_lead, int t, int dist_kind,
+                        int act_mode, void* actions, float* logp, uint64_t seed, uint64_t env_offset, int t_abs0,
+                        float* logits_out, void* stream);
+
 /* Distribution head on pre-activation outputs (PPO.select_action / PPO.evaluate, d2d_ppo.py:159-196).
  *   logits   f32 [n_t][N][O][B]
  *   actions  Bernoulli: channel bitmask [n_t][N][B] (1/2/4 bytes for O <= 8/16/32); Categorical: u8 index.
