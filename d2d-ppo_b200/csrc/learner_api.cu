@@ -60,8 +60,9 @@ static View make_view(float* p, long long t_stride, int t_off, int N, int feat_p
 // kernel.  Not thread-safe; set before the first launch.
 enum { kSwGruTc = D2D_SWITCH_GRU_WINDOW_TC, kSwBwdTc = D2D_SWITCH_GRU_BPTT_TC, kSwDenseTc = D2D_SWITCH_DENSE_TC,
        kSwWgradTc = D2D_SWITCH_WGRAD_TC, kSwFusedHead = D2D_SWITCH_FUSED_HEAD, kSwAllTc = D2D_SWITCH_ALL_TC,
-       kSwBpttRecompute = D2D_SWITCH_BPTT_RECOMPUTE, kSwWindowHead = D2D_SWITCH_WINDOW_HEAD, kSwCount };
-static int g_switch_off[kSwCount] = {0, 0, 0, 0, 0, 0, 0, 0};
+       kSwBpttRecompute = D2D_SWITCH_BPTT_RECOMPUTE, kSwWindowHead = D2D_SWITCH_WINDOW_HEAD,
+       kSwWindowWide = D2D_SWITCH_WINDOW_WIDE, kSwCount };
+static int g_switch_off[kSwCount] = {0, 0, 0, 0, 0, 0, 0, 0, 1};   // the 32-warp window variant is opt-in (measured slower)
 static bool switched_off(int which) { return g_switch_off[which] != 0; }
 static bool tc_enabled() { return g_switch_off[kSwAllTc] == 0; }
 
@@ -273,21 +274,34 @@ static bool gru_tc_eligible(const d2d_net* n) {
          (n->H == 16 || n->H == 32 || n->H == 48 || n->H == 64);
 }
 
-template <int H, bool STORE, int OMAX>
-static int launch_gru_tc_hs(const d2d_net* n, const GruTcArgs& a, cudaStream_t s) {
-  const size_t smem = OMAX > 0 ? ((tc::Smem<H>::bytes + 15) & ~(size_t)15) + tc::Smem<H>::head_bytes(OMAX) : tc::Smem<H>::bytes;
+template <int H, bool STORE, int OMAX, int Q>
+static int launch_gru_tc_q(const d2d_net* n, const GruTcArgs& a, cudaStream_t s) {
+  const size_t smem =
+      OMAX > 0 ? ((tc::Smem<H>::bytes + 15) & ~(size_t)15) + tc::Smem<H>::head_bytes(OMAX, Q) : tc::Smem<H>::bytes;
   static bool attr = false;
   if (!attr) {
-    D2D_CUDA(cudaFuncSetAttribute(gru_window_tc_kernel<H, STORE, OMAX>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    D2D_CUDA(cudaFuncSetAttribute(gru_window_tc_kernel<H, STORE, OMAX, Q>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   (int)smem));
     attr = true;
   }
   const int pairs = (a.t1 - a.t0) * ((n->B + 2 * tc::kM - 1) / (2 * tc::kM));
   if (pairs <= 0) return D2D_OK;
   const int gx = std::max(1, std::min(pairs, 148 / n->N));   // one CTA per SM (all of its shared memory and TMEM)
-  gru_window_tc_kernel<H, STORE, OMAX><<<dim3(gx, n->N), tc::kThreads, smem, s>>>(a);
+  gru_window_tc_kernel<H, STORE, OMAX, Q><<<dim3(gx, n->N), 256 * Q, smem, s>>>(a);
   D2D_LAUNCHED();
   return D2D_OK;
+}
+
+template <int H, bool STORE, int OMAX>
+static int launch_gru_tc_hs(const d2d_net* n, const GruTcArgs& a, cudaStream_t s) {
+  // two threads per row (16 warps of 128 registers).  The four-threads-per-row variant (32 warps of 64 registers, more
+  // warps per scheduler in the latency-bound gate phase) is kept behind D2D_SWITCH_WINDOW_WIDE: measured SLOWER on
+  // B200 (rollout 3.81e8 vs 4.52e8 agent-steps/s, epoch 61 vs 55 ms): at 64 registers ptxas spills 100-500 bytes per
+  // thread and the extra tcgen05.ld / staging instructions outweigh the added warps
+  if constexpr ((H == 32 || H == 64) && OMAX <= 8) {
+    if (!switched_off(kSwWindowWide)) return launch_gru_tc_q<H, STORE, OMAX, 4>(n, a, s);
+  }
+  return launch_gru_tc_q<H, STORE, OMAX, 2>(n, a, s);
 }
 
 template <int H>
