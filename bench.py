@@ -230,12 +230,20 @@ def measured_peaks():
 BF16_SUSTAINED = FALLBACK_BF16
 
 
-def gru_tc_issued_flops(I_pad, H, L):
-    """bf16 tensor-pipe flops the fused GRU-window kernel ISSUES per row (csrc/gru_tc.cuh): every fp32 operand is
-    three bf16 planes.  Per step: h (3 planes) x W_hh (3 planes) keeps the 6 plane pairs with i + j <= 2 as N = 3H
-    MMAs of K = H; x (exact in one plane) x W_ih: plane 0 as N = 3H ([r; z; 0]), planes 1, 2 as N = 2H, and the n rows of
-    the three planes as N = H, all of K = I_pad."""
-    return 2 * L * (6 * H * 3 * H + I_pad * (3 * H + 2 * 2 * H + 3 * H))
+def gru_tc_issued_flops(I_pad, H, L, head=True):
+    """fp16 tensor-pipe flops the fused GRU-window kernel ISSUES per row (csrc/gru_tc.cuh): every fp32 operand is two
+    fp16 planes and a product keeps 3 plane pairs.  Per step: h (2 planes) x W_hh (2 planes) as 3 N = 3H MMA groups of
+    K = H; x (exact in one plane) x W_ih (2 planes) as 2 N = 4H groups of K = I_pad ([r; z; 0; n] rows).  The fused head
+    adds 3 N = H groups of K = H once per row."""
+    return 2 * L * (3 * H * 3 * H + 2 * 4 * H * I_pad) + (3 * 2 * H * H if head else 0)
+
+
+def gru_bptt_issued_flops(I_pad, H, L):
+    """fp16 MMA flops of the recomputing BPTT kernel per row (csrc/gru_bptt_tc.cuh): per step the gate recompute
+    (as a forward step), D = G W_hh (3 plane pairs, K = 3H, N = H) and dW += G^T P (pairs g0 p0, g1 p0 with N = H + 16,
+    g0 p1 with N = H; K = rows, M = 3H counted as the flops of the useful 3H rows)."""
+    fwd = 2 * (3 * H * 3 * H + 2 * 4 * H * I_pad)
+    return L * (fwd + 2 * 3 * 3 * H * H + 2 * 3 * H * (2 * (H + 16) + H))
 
 
 def gru_flops_per_agent_step(I, H, L, O):
@@ -289,10 +297,11 @@ def bench_learner(args, dev, world, rank, barrier, max_over_ranks):
         "roofline": {"bound": "tensor",
                      "note": "primary figure: ALGORITHMIC forward flops (SURVEY.md 8d: 2 L 3H (I + H) + 2 H^2 + 2 H O per "
                              "net, counted once) over the WHOLE rollout time (env step, heads, sampling, returns "
-                             "included) against the SUSTAINED bf16 peak (a kernel inside a 0.2 s step).  The GRU windows "
-                             "run on tcgen05 with fp32 operands split into 3 bf16 planes (fp32 parity at 1e-5), i.e. "
-                             "the tensor pipe ISSUES issued_bf16_flops_per_agent_step (6 plane pairs for h W_hh, 3 "
-                             "planes of W_ih, K padded 30 -> 32): issued_frac_of_sustained is that rate",
+                             "included) against the SUSTAINED bf16 / fp16 peak (a kernel inside a 0.2 s step).  The GRU "
+                             "windows run on tcgen05 with fp32 operands split into 2 fp16 planes (fp32 parity at 1e-5), "
+                             "i.e. the tensor pipe ISSUES issued_bf16_flops_per_agent_step (3 plane pairs for h W_hh, 2 "
+                             "planes of W_ih as N = 4H groups, K padded 30 -> 32, plus the fused head): "
+                             "issued_frac_of_sustained is that rate",
                      "achieved": steps / world * flops / dt / 1e12, "peak": BF16_SUSTAINED, "unit": "TFLOP/s",
                      "frac": steps / world * flops / dt / 1e12 / BF16_SUSTAINED, "traffic": None,
                      "flops_per_agent_step": flops, "issued_bf16_flops_per_agent_step": issued,
@@ -356,8 +365,8 @@ def bench_learner(args, dev, world, rank, barrier, max_over_ranks):
         for O in O_list:
             fwd = gru_flops_per_agent_step(30, H, L, O)
             alg += 3 * fwd                                               # backward = data + weight gradients = 2 x forward
-            issued += gru_tc_issued_flops(I_pad, H, L)                   # forward window (training direction)
-            issued += 2 * L * (5 * 3 * H * H + 5 * 3 * H * (H + 16))     # BPTT: D = G W_hh and dW += G^T P, 5 plane pairs
+            issued += gru_tc_issued_flops(I_pad, H, L)                   # forward window + head (training direction)
+            issued += gru_bptt_issued_flops(I_pad, H, L)                 # recompute + D = G W_hh + dW += G^T P
         return alg, issued
 
     def train_sps(make_env, make_agent, B, n_agents, label, n_epoch=5, iters=2, nets=None):
@@ -382,7 +391,7 @@ def bench_learner(args, dev, world, rank, barrier, max_over_ranks):
             if os.path.exists(tpath):
                 traffic = json.load(open(tpath))
             res["roofline"] = {
-                "bound": "tensor", "kernel": "gru_bwd_tc_kernel<64> (+ gru_window_tc_kernel<64,1>): ~75 % of an epoch",
+                "bound": "tensor", "kernel": "gru_bptt_tc_kernel<64> (+ gru_window_tc_kernel<64,1,*>): ~75 % of an epoch",
                 "achieved": rows * alg / ep_dt / 1e12, "peak": BF16_SUSTAINED, "unit": "TFLOP/s",
                 "frac": rows * alg / ep_dt / 1e12 / BF16_SUSTAINED,
                 "flops_per_agent_step_epoch": alg, "issued_bf16_flops_per_agent_step_epoch": issued,
@@ -390,9 +399,10 @@ def bench_learner(args, dev, world, rank, barrier, max_over_ranks):
                 "issued_frac_of_sustained": rows * issued / ep_dt / 1e12 / BF16_SUSTAINED,
                 "traffic": traffic,
                 "note": "one update epoch timed alone with CUDA events; `achieved` = algorithmic fp32-equivalent flops "
-                        "of forward + backward of every GRU net (3 x forward), `issued` = bf16 MMA flops of the GRU "
-                        "window and BPTT kernels (3-plane operands); `traffic` = DRAM bytes per 4,096-env epoch of the "
-                        "two dominant kernels from the ncu launch list in profiles/ (null if absent)",
+                        "of forward + backward of every GRU net (3 x forward), `issued` = fp16 MMA flops of the GRU "
+                        "window and BPTT kernels (two fp16 planes per fp32 operand, 3 plane pairs per product, gates "
+                        "recomputed in the backward kernel); `traffic` = DRAM bytes per 4,096-env epoch of the two "
+                        "dominant kernels from the ncu launch list in profiles/ (null if absent)",
                 "peak_source": peak_src + " bf16_tflops_sustained"}
         del ag, env
         torch.cuda.empty_cache()
