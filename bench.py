@@ -527,10 +527,10 @@ def bench_env_configs(dev, hbm_peak, steps=200):
                               period=None, arrival_probs=None, offsets=None, episode_length=200,
                               traffic_model="aperiodic", periodic_devices=[], channel_switch=np.array([0.2] * (C + 1)),
                               n_envs=B, device=dev, seed=4)
-    acts = torch.randint(0, C + 1, (N, B), dtype=torch.uint8, device=dev)
-    # global channel state u32 per env (read + written), ack f32 [C+1] per env in the observation only
-    alg = (7 + 1 + 8) + (7 + 8 + 4 * (7 + C + 1)) + (8 + 5 + 4 * (C + 1)) / N
-    run("ChannelSelectionEnv xp_gamma.py (N=5, C=16), device actions u8 [N,B]", sel, alg, actions=acts)
+    # global channel state u32 per env (read + written), ack f32 [C+1] per env in the observation only; the fused
+    # RandomAccess policy (baselines.py:10-14) reads no action byte
+    alg = (7 + 8) + (7 + 8 + 4 * (7 + C + 1)) + (8 + 5 + 4 * (C + 1)) / N
+    run("ChannelSelectionEnv xp_gamma.py (N=5, C=16), fused RandomAccess policy", sel, alg, tp=0.0)
     return out
 
 

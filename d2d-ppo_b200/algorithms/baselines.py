@@ -69,13 +69,15 @@ class CombinatorialRandomAccess:
 
 class RandomAccess:
     """Uniform random channel pick for every device that has a packet (baselines.py:5-45), on ``ChannelSelectionEnv``.
-    ``act`` takes the flattened buffers [..., N * Dmax] the reference passes (``state[0]``); in batched mode the draws
-    come from torch's CUDA generator (seed with ``torch.manual_seed``), in single-env mode from ``np.random`` as in the
-    reference."""
+    ``act`` takes the flattened buffers [..., N * Dmax] the reference passes (``state[0]``) and draws from torch's CUDA
+    generator in batched mode (seed with ``torch.manual_seed``), from ``np.random`` in single-env mode as in the
+    reference.  ``run`` in batched mode uses the policy fused into ``sel_step_kernel`` (Philox policy stream, one
+    library call per episode) unless ``fused=False``."""
 
-    def __init__(self, env, verbose=False):
+    def __init__(self, env, verbose=False, fused=True):
         self.env = env
         self.verbose = verbose
+        self.fused = fused        # batched mode: draw the actions inside the step kernel (Philox) instead of torch.randint
 
     def act(self, buffers):
         env = self.env
@@ -105,6 +107,13 @@ class RandomAccess:
             buffers = state[0] if env.compat else state[:, :sd]
             rew = torch.zeros(B, dtype=torch.float64, device=env.device)
             done = False
+            if self.fused and not env.compat:
+                # the policy is drawn inside the step kernel and the whole episode is one library call
+                acc = torch.zeros(B, dtype=torch.int32, device=env.device)
+                steps = env.run_random_access(0.0, env.episode_length, out_reward=acc, accumulate=True)
+                assert steps == env.episode_length
+                rew = acc.to(torch.float64) * env.n_agents        # np.sum(rewards_episode): every agent's copy counts
+                done = True
             while not done:
                 _, state, r, done, _ = env.step(self.act(buffers))
                 buffers = state[0] if env.compat else state[:, :sd]

@@ -301,9 +301,14 @@ __global__ void __launch_bounds__(256, 4) sel_step_kernel(const StepArgs a) {
   const uint32_t Bu = (uint32_t)a.B;
   uint32_t* chan = reinterpret_cast<uint32_t*>(a.chan);
   const uint8_t* act = reinterpret_cast<const uint8_t*>(a.actions);
+  uint8_t* act_out = reinterpret_cast<uint8_t*>(a.actions_out);
   const uint32_t* rp_sw = reinterpret_cast<const uint32_t*>(a.rp_sw);
   const uint32_t cmask = C1 >= 32 ? 0xFFFFFFFFu : ((1u << C1) - 1u);
   const int n_planes = 32 - __clz(N);     // a channel is picked by at most N devices: bits(N) counter planes suffice
+  // act_mode 1: fused RandomAccess policy (algorithms/baselines.py:10-14): every device draws a channel id uniformly
+  // from 0..C (0 = stay idle) -- floor(u32 (C + 1) / 2^32) of the Philox policy stream, one call per four devices --
+  // and devices without a packet are set to 0.  The drawn ids are kept in a local array for the second pass.
+  const bool fused_policy = a.act_mode != 0;
 
   for (int b = blockIdx.x * blockDim.x + threadIdx.x; b < a.B; b += gridDim.x * blockDim.x) {
     ArrivalWords arr_words;
@@ -314,10 +319,20 @@ __global__ void __launch_bounds__(256, 4) sel_step_kernel(const StepArgs a) {
 #pragma unroll
     for (int j = 0; j < kCountPlanes; ++j) plane[j] = 0;
 #pragma unroll 4
+    uint8_t drawn[D2D_MAX_AGENTS];
+    uint4 pol4 = make_uint4(0u, 0u, 0u, 0u);
     for (int k = 0; k < N; ++k) {
       const size_t idx = (size_t)k * B + b;
       const Rec<W> r = rec_load<W>(a.buf, idx);
-      const uint32_t sel = act[idx];
+      uint32_t sel;
+      if (fused_policy) {
+        if ((k & 3) == 0) pol4 = philox4x32_10(env, a.t, (uint32_t)(k >> 2) | (kPurposePolicy << 16), 0u, a.k0, a.k1);
+        sel = rec_any<W>(r) ? __umulhi(pick_word(pol4, k & 3), (uint32_t)C1) : 0u;
+        drawn[k] = (uint8_t)sel;
+        if (act_out) act_out[idx] = (uint8_t)sel;
+      } else {
+        sel = act[idx];
+      }
       uint32_t carry = (sel != 0 && rec_any<W>(r)) ? (1u << sel) : 0u;
 #pragma unroll
       for (int j = 0; j < kCountPlanes; ++j) {
@@ -344,7 +359,7 @@ __global__ void __launch_bounds__(256, 4) sel_step_kernel(const StepArgs a) {
     // ---- pass 2: device k + 1's record and counters are fetched while device k is processed ----
     int n_success = 0;
     Rec<W> r_nx = rec_load<W>(a.buf, (size_t)b);                 // second touch of the record: L1 hit
-    uint32_t sel_nx = act[b];
+    uint32_t sel_nx = fused_policy ? drawn[0] : act[b];
     uint32_t disc_nx = (r_nx.w[0] & 0xFFu) ? a.disc[b] : 0u;
     uint32_t recv_nx = (a.active & 1ull) ? a.recv[b] : 0u;
 #pragma unroll 1
@@ -355,7 +370,7 @@ __global__ void __launch_bounds__(256, 4) sel_step_kernel(const StepArgs a) {
       if (k + 1 < N) {
         const size_t nx = idx + B;
         r_nx = rec_load<W>(a.buf, nx);
-        sel_nx = act[nx];
+        sel_nx = fused_policy ? drawn[k + 1] : act[nx];
         disc_nx = (r_nx.w[0] & 0xFFu) ? a.disc[nx] : 0u;
         if ((a.active >> (k + 1)) & 1ull) recv_nx = a.recv[nx];
       }
@@ -846,8 +861,6 @@ extern "C" int d2d_env_step(d2d_env* e, const void* actions, float* obs, float* 
 extern "C" int d2d_env_step_random_access(d2d_env* e, double tp, void* actions_out, float* obs, float* state,
                                           int32_t* reward, uint8_t* done, void* ack, void* stream) {
   D2D_REQUIRE(e && reward, "d2d_env_step_random_access: null env or reward");
-  D2D_REQUIRE(e->kind != D2D_ENV_CHANNEL_SELECTION,
-              "d2d_env_step_random_access: the reference defines no random-access policy for the selection env");
   D2D_REQUIRE(tp >= 0.0 && tp <= 1.0, "d2d_env_step_random_access: transmission_prob must be in [0, 1]");
   if (!e->is_reset) {
     set_error("d2d_env_step_random_access: reset() has not been called");
@@ -873,8 +886,6 @@ extern "C" int d2d_env_run_random_access(d2d_env* e, double tp, int n_steps, int
                                          int32_t* reward, int64_t reward_step_stride, int reward_accumulate,
                                          uint8_t* done, void* stream, int* steps_done) {
   D2D_REQUIRE(e && reward && n_steps >= 0, "d2d_env_run_random_access: null env / reward or negative n_steps");
-  D2D_REQUIRE(e->kind != D2D_ENV_CHANNEL_SELECTION,
-              "d2d_env_run_random_access: the reference defines no random-access policy for the selection env");
   D2D_REQUIRE(tp >= 0.0 && tp <= 1.0, "d2d_env_run_random_access: transmission_prob must be in [0, 1]");
   D2D_REQUIRE(!(reward_accumulate && reward_step_stride != 0),
               "d2d_env_run_random_access: reward_accumulate sums into ONE i32 [B] buffer (reward_step_stride 0)");

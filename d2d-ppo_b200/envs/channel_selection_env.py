@@ -72,6 +72,23 @@ class ChannelSelectionEnv(LockstepEnv):
         return (self._obs_views(obs) if obs is not None else None,
                 state.t() if state is not None else None, rewards, done, {})
 
+    def step_random_access(self, *, with_obs=True, with_state=True, out_obs=None, out_state=None, return_actions=False):
+        """One step with the fused ``RandomAccess`` policy (algorithms/baselines.py:10-14): every device with a packet
+        picks a channel id uniformly from 0..C inside the step kernel (Philox policy stream)."""
+        if self.compat:
+            with_obs = with_state = True
+        acts = torch.empty((self.n_agents, self.n_envs), dtype=torch.uint8, device=self.device) if return_actions else None
+        obs, state, reward, done = self._step_device(None, with_obs, with_state, out_obs, out_state,
+                                                     random_access_tp=0.0, actions_out=acts)
+        if self.compat:
+            rewards = np.array([int(reward[0].item()) for _ in range(self.n_agents)])
+            out = (self._compat_obs(obs), self._split_state(state), rewards, done, {})
+        else:
+            rewards = reward.unsqueeze(1).expand(self.n_envs, self.n_agents)
+            out = (self._obs_views(obs) if obs is not None else None, state.t() if state is not None else None,
+                   rewards, done, {})
+        return out + (acts,) if return_actions else out
+
     @property
     def channel_state(self):
         chan = self._export()[1]

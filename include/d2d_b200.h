@@ -130,9 +130,12 @@ int d2d_env_reset(d2d_env* env, float* obs, float* state, void* stream);
 int d2d_env_step(d2d_env* env, const void* actions, float* obs, float* state, int32_t* reward,
                  uint8_t* done, void* ack, void* stream);
 
-/* step with the fused random-access policy: algorithms/baselines.py:181-183
- * (CombinatorialRandomAccess.act = Bernoulli(tp) per (device, channel)); the action bits come from
- * the Philox policy stream inside the step kernel.  actions_out (same layout as `actions`) may be NULL. */
+/* step with the fused random-access policy: the actions come from the Philox policy stream inside the step kernel.
+ *   combinatorial / single-channel: algorithms/baselines.py:181-183 (CombinatorialRandomAccess.act = Bernoulli(tp)
+ *                     per (device, channel) resp. per device)
+ *   selection:        algorithms/baselines.py:10-14 (RandomAccess.act: every device with a packet picks a channel id
+ *                     uniformly from 0..C, 0 = stay idle); transmission_prob is ignored
+ * actions_out (same layout as `actions`) may be NULL. */
 int d2d_env_step_random_access(d2d_env* env, double transmission_prob, void* actions_out, float* obs,
                                float* state, int32_t* reward, uint8_t* done, void* ack, void* stream);
 

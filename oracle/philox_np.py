@@ -119,3 +119,10 @@ def poisson_cdf_thresholds(lam):
 def poisson_from_u32(u, thr):
     u = np.asarray(u, dtype=np.uint32)
     return (u[..., None] >= thr[None, :]).sum(-1).astype(np.int64)
+
+
+def uniform_choice(seed, env, t, device, n_choices):
+    """The fused RandomAccess policy of the selection env: floor(u32 * n_choices / 2^32) with the 32-bit word of
+    ``device`` from the policy stream (word ``device % 4`` of the call whose device field is ``device // 4``)."""
+    u = word32(seed, env, t, device, PURPOSE_POLICY).astype(np.uint64)
+    return ((u * np.uint64(n_choices)) >> np.uint64(32)).astype(np.int64)

@@ -432,3 +432,35 @@ def test_grouped_device_mapping_matches_oracle(n_agents, B, cuda_device):
         assert np.array_equal(cat_obs(obs), cat_obs(o_obs)), t
         assert np.array_equal(to_np(state), o_state) and np.array_equal(to_np(rew), o_rew), t
     _check_state(env, orc, "combinatorial", "fused policy")
+
+
+def test_selection_env_fused_random_access_matches_oracle(cuda_device):
+    """RandomAccess (algorithms/baselines.py:10-14) fused into sel_step_kernel: the channel ids the kernel draws from
+    the Philox policy stream equal the numpy restatement (uniform over 0..C, 0 for devices without a packet), and the
+    env driven by them matches the oracle bit for bit; ids are uniform over the channels."""
+    from oracle import philox_np as px
+    from oracle.envs_np import PhiloxSource
+    g = load_env_case("sel_xp_gamma")
+    kw = dict(g["config"])
+    kw["episode_length"] = T = 25
+    B, N, C1 = 192, kw["n_agents"], kw["n_channels"] + 1
+    env = make_cuda_env("channel_selection", kw, B, rng="philox", seed=31, env_offset=4, device=cuda_device)
+    orc = make_oracle("channel_selection", kw, B, PhiloxSource(B, 31, env_offset=4, env_level_switch=True))
+    envs = np.arange(B) + 4
+    counts = np.zeros(C1, dtype=np.int64)
+    for episode in range(2):
+        env.reset()
+        orc.reset()
+        for t in range(1, T + 1):
+            has = orc.buffers.sum(2) > 0
+            obs, state, rew, done, _, acts = env.step_random_access(return_actions=True)
+            tc = orc.source.ctr_t(t)
+            want = np.stack([px.uniform_choice(31, envs, tc, k, C1) for k in range(N)], axis=1) * has
+            assert np.array_equal(to_np(acts).T.astype(np.int64), want), (episode, t)
+            counts += np.bincount(want[has], minlength=C1)
+            o_obs, o_state, o_rew, o_done, _ = orc.step(want)
+            assert np.array_equal(cat_obs(obs), cat_obs(o_obs)) and np.array_equal(to_np(state), o_state), (episode, t)
+            assert np.array_equal(to_np(rew), o_rew) and done == o_done
+        _check_state(env, orc, "channel_selection", episode)
+    freq = counts / counts.sum()
+    assert np.all(np.abs(freq - 1.0 / C1) < 0.01), freq
