@@ -78,9 +78,9 @@ def xp_load(out_dir="combinatorial_load", learner="d2dppo", n_seeds=1, loads=Non
     return result
 
 
-def xp_n_agents(out_dir="xp_n_agents", learner="random_access", n_seeds=1, n_agents_list=(4, 8, 12, 16), load=1 / 14,
-                n_envs=500, cv_episodes=50, test_episodes=500, num_iter=2000, n_epoch=5, test_freq=100, device=None,
-                result_name="results/gf.p"):
+def xp_n_agents(out_dir="xp_3gpp_homogeneous", learner="random_access", n_seeds=1, n_agents_list=(4, 8, 12, 16),
+                load=1 / 14, n_envs=500, cv_episodes=50, test_episodes=500, num_iter=2000, n_epoch=5, test_freq=100,
+                device=None, result_name="results/aloha.p"):
     """xp_n_agents.py: N-agent sweep on 4 channels; the active block of the script is the random-access baseline
     with its transmission probability picked by ``get_best_transmission_probs`` (:137-140)."""
     from .algorithms.baselines import CombinatorialRandomAccess
@@ -116,7 +116,7 @@ def xp_n_agents(out_dir="xp_n_agents", learner="random_access", n_seeds=1, n_age
 
 
 def run_ma_baselines(out_dir="combinatorial_load", n_seeds=1, n_envs=1000, cv_episodes=100, test_episodes=1000,
-                     setup="setup", device=None, result_name="results/ma_baselines.p"):
+                     setup="setup", device=None, result_name="results/aloha_16_channels.p"):
     """run_ma_baselines.py: writes setup.p, then the random-access baseline over ``loads_list`` (16 channels, ragged
     observations: ``homogeneous_size`` keeps its default False, :58-69)."""
     from .algorithms.baselines import CombinatorialRandomAccess
@@ -143,9 +143,9 @@ def run_ma_baselines(out_dir="combinatorial_load", n_seeds=1, n_envs=1000, cv_ep
     return result
 
 
-def xp_gamma(out_dir="xp_gamma", gammas=(0.1, 0.3, 0.5, 0.7, 0.9, 0.99), n_agents=5, n_channels=16, load=1 / 14,
+def xp_gamma(out_dir=".", gammas=(0.2, 0.4, 0.6, 0.8, 0.99), n_agents=5, n_channels=16, load=1 / 3.5,
              num_iter=1000, n_epoch=4, n_envs=10, test_freq=100, test_episodes=500, device=None,
-             result_name="results/ippo.p"):
+             result_name="results/xp_gamma_ippo.p"):
     """xp_gamma.py: iPPO (Categorical channel pick, GRU, history 10) on ChannelSelectionEnv for several discounts.
     Note: in the reference snapshot this script stops in ``env.step`` (actions arrive as (N, 1), SURVEY.md section
     8c); here the action vector is (N,) per env and the sweep runs."""
@@ -182,11 +182,52 @@ def run_ippo_combinatorial(out_dir="combinatorial_load", load=1 / 3, num_iter=20
     ippo = _learner("ippo", env, folder, 0, hidden_size=64, gamma=0.99, policy_lr=3e-4, value_lr=1e-2, useRNN=True,
                     combinatorial=True, history_len=6, early_stopping=True)
     res = ippo.train(num_iter=num_iter, n_epoch=n_epoch, num_episodes=n_envs, test_freq=test_freq)
+    if os.path.exists(os.path.join(folder, "agent_0.pth")):
+        ippo.load(folder)                                             # run_ippo_combinatorial.py:93 reloads the best model
     out = ippo.test(test_episodes)
     result = _result([out[0]], [out[1]], [out[2]], [out[3]], [res])
     with open(os.path.join(out_dir, result_name), "wb") as f:
         pickle.dump(result, f)
     return result
+
+
+# Literal settings of the reference scripts that the drivers above reproduce as their defaults; checked against the
+# values parsed from the reference scripts themselves (tests/golden/experiment_constants.json, written by
+# oracle/gen_experiment_constants.py; tests/test_presets.py).
+DRIVER_CONSTANTS = {
+    "xp_load": dict(output_path="combinatorial_load/results/mcappo_8_channels.p", n_seeds=1, hidden_size=64, gamma=0.6,
+                    policy_lr=3e-4, value_lr=1e-3, train=dict(num_iter=2000, n_epoch=5, num_episodes=10, test_freq=100),
+                    test_episodes=1000),
+    "xp_n_agents": dict(output_path="xp_3gpp_homogeneous/results/aloha.p", n_seeds=1, n_channels=4, load=1 / 14,
+                        n_agents_list=[4, 8, 12, 16], cv_episodes=50, test_episodes=500),
+    "run_ma_baselines": dict(output_path="combinatorial_load/results/aloha_16_channels.p", n_seeds=1, cv_episodes=100,
+                             test_episodes=1000),
+    "xp_gamma": dict(output_path="results/xp_gamma_ippo.p", n_seeds=1, n_agents=5, n_channels=16, load=1 / 3.5,
+                     gammas=[0.2, 0.4, 0.6, 0.8, 0.99], hidden_size=64, policy_lr=3e-4, value_lr=1e-2, history_len=10,
+                     train=dict(num_iter=1000, n_epoch=4, num_episodes=10, test_freq=100), test_episodes=500),
+    "run_ippo_combinatorial": dict(output_path="combinatorial_load/results/ippo_16_channels.p", n_seeds=1, n_channels=16,
+                                   hidden_size=64, gamma=0.99, policy_lr=3e-4, value_lr=1e-2, history_len=6,
+                                   train=dict(num_iter=2000, n_epoch=5, num_episodes=10, test_freq=100),
+                                   test_episodes=500),
+}
+
+
+def driver_defaults(name):
+    """The same settings read back from the driver's signature / body defaults (what a call without arguments runs)."""
+    import inspect
+    sig = {k: v.default for k, v in inspect.signature(globals()[name]).parameters.items()}
+    out = {"output_path": os.path.normpath(os.path.join(sig["out_dir"], sig["result_name"])), "n_seeds": sig.get("n_seeds", 1)}
+    for k in ("load", "n_agents", "n_channels", "cv_episodes", "test_episodes"):
+        if k in sig:
+            out[k] = sig[k]
+    if "gammas" in sig:
+        out["gammas"] = list(sig["gammas"])
+    if "n_agents_list" in sig:
+        out["n_agents_list"] = list(sig["n_agents_list"])
+    if "num_iter" in sig and name not in ("xp_n_agents",):
+        out["train"] = dict(num_iter=sig["num_iter"], n_epoch=sig["n_epoch"], num_episodes=sig["n_envs"],
+                            test_freq=sig["test_freq"])
+    return out
 
 
 def main(argv=None):
