@@ -55,3 +55,38 @@ def test_ippo_sweeps_smoke(tmp_path, cuda_device):
     res = X.run_ippo_combinatorial(out_dir=str(tmp_path / "c16"), num_iter=1, n_epoch=1, n_envs=8, test_freq=1,
                                    test_episodes=8, device=cuda_device)
     _check_metrics(res["scores"], res["jains"])
+
+
+def test_random_access_baseline_matches_reference_results(cuda_device):
+    """The baseline experiments of run_ma_baselines.py:58-74 and xp_n_agents.py:62-140, statistically: URLLC score of
+    CombinatorialRandomAccess for every transmission probability of the cross-validation sweep and at the reference's
+    picked probability, against results of the UNMODIFIED reference (tests/golden/exp_baselines.json, written by
+    oracle/gen_golden_experiments.py).  Different random streams, same distributions: the tolerance is 4 standard errors
+    of the reference's own estimate (from its per-episode spread) plus 0.01."""
+    import json
+    from d2d_ppo_b200 import presets
+    from d2d_ppo_b200.algorithms.baselines import CombinatorialRandomAccess
+    from d2d_ppo_b200.envs import CombinatorialEnv
+    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "exp_baselines.json")
+    ref = json.load(open(path))
+    B = 2048
+
+    def check(kw, r, what):
+        env = CombinatorialEnv(n_envs=B, device=cuda_device, seed=123, **kw)
+        gf = CombinatorialRandomAccess(env)
+        cv = gf.get_best_transmission_probs(B)
+        se_cv = r["score_episode_std"] / np.sqrt(r["cv_episodes"])
+        for tp, mine, theirs in zip(gf.transmission_prob_list, cv, r["cv_scores"]):
+            assert abs(mine - theirs) <= 4 * se_cv + 0.01, (what, "cv", float(tp), mine, theirs)
+        # the reference's pick is (near-)optimal here too
+        assert cv[r["best_index"]] >= max(cv) - (4 * se_cv + 0.01), (what, cv, r["best_index"])
+        gf.transmission_prob = r["best_tp"]
+        score = gf.run(B)[0]
+        se = r["score_episode_std"] / np.sqrt(r["episodes"])
+        assert abs(score - r["score"]) <= 4 * se + 0.01, (what, score, r["score"])
+
+    for n, r in ref["n_agents_sweep"].items():
+        check(presets.n_agents_sweep_kwargs(int(n), load=1 / 14), r, f"xp_n_agents N={n}")
+    for load, r in ref["ma_baselines"].items():
+        check(presets.combinatorial_kwargs("setup", load=float(load), homogeneous_size=False), r,
+              f"run_ma_baselines load={load}")
