@@ -515,6 +515,30 @@ def bench_env_configs(dev, hbm_peak, steps=200):
     for B in (4096, 1 << 22):
         run(f"c2 D2DEnv N=4 deadlines 7, {B} envs, fused random access", D2DEnv(n_envs=B, device=dev, seed=2, **c2),
             env_alg_bytes(7, 1, 4, 9, 5, 0), tp=TP)
+    # c2 through RandomAccess.run's call (rewards accumulated, no observation rows): the steps of an episode run in ONE
+    # register-resident kernel (sc_run_kernel); the same call with one launch per step is timed beside it
+    from d2d_ppo_b200 import _lib
+    for B in (4096, 1 << 22):
+        env = D2DEnv(n_envs=B, device=dev, seed=2, **c2)
+        acc = torch.zeros(B, dtype=torch.int32, device=dev)
+        rates = {}
+        for multi in (1, 0):
+            _lib.set_kernel_switch(_lib.SWITCH_ENV_MULTISTEP, multi)
+            n = 5 * env.episode_length                       # 5 episodes: 5 resets + 5 (or 1000) step launches
+            env.run_random_access(TP, env.episode_length, auto_reset=True, out_reward=acc, accumulate=True)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            env.run_random_access(TP, n, auto_reset=True, out_reward=acc, accumulate=True)
+            e1.record()
+            torch.cuda.synchronize()
+            rates[multi] = (B * env.n_agents * n / (e0.elapsed_time(e1) * 1e-3), e0.elapsed_time(e1) / n)
+        _lib.set_kernel_switch(_lib.SWITCH_ENV_MULTISTEP, 1)
+        out.append({"config": f"c2 D2DEnv N=4 deadlines 7, {B} envs, RandomAccess.run (rewards only), multi-step kernel",
+                    "envs": B, "n_agents": env.n_agents, "agent_steps_per_s": rates[1][0], "ms_per_step": rates[1][1],
+                    "one_launch_per_step_agent_steps_per_s": rates[0][0], "one_launch_per_step_ms": rates[0][1],
+                    "bound": "issue (3 Philox calls + update logic per env-step, state in registers)"})
+        del env, acc
+        torch.cuda.empty_cache()
     # c4: xp_n_agents sweep, C=4, deadlines 7, B x N = 4M
     for N in (4, 16, 64):
         kw = presets.n_agents_sweep_kwargs(N, load=1 / 3)

@@ -50,7 +50,7 @@ DIST_BERNOULLI, DIST_CATEGORICAL = 0, 1
 ACT_SAMPLE, ACT_GREEDY, ACT_GIVEN = 0, 1, 2
 ACT_HOST_REFERENCE, ACT_HOST_DEVICE_LAYOUT = 0, 1
 SWITCH_GRU_WINDOW_TC, SWITCH_GRU_BPTT_TC, SWITCH_DENSE_TC, SWITCH_WGRAD_TC, SWITCH_FUSED_HEAD, SWITCH_ALL_TC, \
-    SWITCH_BPTT_RECOMPUTE, SWITCH_WINDOW_HEAD, SWITCH_WINDOW_WIDE = range(9)
+    SWITCH_BPTT_RECOMPUTE, SWITCH_WINDOW_HEAD, SWITCH_WINDOW_WIDE, SWITCH_ENV_MULTISTEP = range(10)
 
 _lib = None
 

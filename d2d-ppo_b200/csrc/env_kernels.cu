@@ -235,6 +235,103 @@ __global__ void __launch_bounds__(256, NK ? 5 : 4) sc_step_kernel(const StepArgs
   }
 }
 
+// n_inner consecutive random-access steps of ONE episode in one launch (d2d_env_run_random_access without per-step
+// outputs): the env's records, channel bits and counters are loaded once, live in registers for every step and are
+// stored once; each step is the three Philox calls of sc_step_kernel (policy lanes, switch lanes, arrival words: one
+// call each serves all N <= 4 devices) plus the serve / age / switch / arrive logic.  A thread only ever touches its own
+// env, so no step needs a grid-wide barrier.  The per-step kernel at the named c2 size (4,096 envs) is launch-latency
+// bound (8.2 us a step for ~0.5 MB of state); this one is bound by the dependent-issue chain of a single warp.
+// Same Philox counters and the same update order as sc_step_kernel: trajectories are bit-identical.
+struct RunArgs {
+  const uint64_t* active;      // device copy of the per-timestep arrival masks, indexed by the episode timestep
+  int t_plain;                 // episode timestep of the first step produced (a.t is its Philox counter)
+  int n_inner;
+  long long reward_stride;     // elements between the reward rows of consecutive steps (0 with reward_accum)
+};
+
+template <int W, int NK>
+__global__ void __launch_bounds__(256) sc_run_kernel(const StepArgs a, const RunArgs ra) {
+  extern __shared__ __align__(16) uint8_t smem[];
+  const EnvParamsHdr* P = stage_params(a, smem);
+  const uint32_t* cdf = reinterpret_cast<const uint32_t*>(smem + P->off_cdf);
+  const uint32_t* swthr = reinterpret_cast<const uint32_t*>(smem + P->off_sw);
+  const int N = P->N;
+  const size_t B = (size_t)a.B;
+  uint8_t* chan = reinterpret_cast<uint8_t*>(a.chan);
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= a.B) return;
+  const uint32_t env = a.env_offset + (uint32_t)b;
+  Rec<W> rec[NK];
+  uint32_t chv[NK], discv[NK], recvv[NK], thr_sw[NK];
+  int dl[NK];
+#pragma unroll
+  for (int k = 0; k < NK; ++k) {
+    const int kk = min(k, N - 1);
+    const size_t idx = (size_t)kk * B + b;
+    rec[k] = rec_load<W>(a.buf, idx);
+    chv[k] = chan[idx] & 1u, discv[k] = a.disc[idx], recvv[k] = a.recv[idx];
+    thr_sw[k] = swthr[kk], dl[k] = P->deadline[kk];
+  }
+  uint32_t st0 = a.stats[b], st1 = a.stats[B + b];
+  int32_t rew = a.reward_accum ? a.reward[b] : 0;
+  auto lane16 = [](const uint4& r, int k) {
+    const uint32_t w = pick_word(r, k >> 1);
+    return (k & 1) ? (w >> 16) : (w & 0xFFFFu);
+  };
+#pragma unroll 1
+  for (int i = 0; i < ra.n_inner; ++i) {
+    const uint32_t t = a.t + (uint32_t)i;
+    const uint64_t active = ra.active[ra.t_plain + i];
+    // the three draws are independent of the state: their Philox rounds interleave
+    const uint4 pol = philox_rk(a, env, t, kPurposePolicy << 16, 0u);
+    const uint4 sw4 = philox_rk(a, env, t, kPurposeSwitch << 16, 0u);
+    uint4 ar4 = make_uint4(0u, 0u, 0u, 0u);
+    if (active) ar4 = philox_rk(a, env, t, kPurposeArrival << 16, 0u);
+    uint32_t att = 0, good = 0;                                 // env.py:125-127
+#pragma unroll
+    for (int k = 0; k < NK; ++k) {
+      if (k < N) {
+        const uint32_t at = (lane16(pol, k) < a.tp_thr && rec_any<W>(rec[k])) ? 1u : 0u;
+        att |= at << k;
+        good |= (at & chv[k]) << k;
+      }
+    }
+    const int n_att = __popc(att);                              // :130-152
+    const bool lone = n_att == 1;
+    const bool decoded = lone && good != 0;
+    const int ack = n_att > 1 ? -1 : (decoded ? 1 : 0);
+    st0 += (lone && !decoded) ? 1u : 0u;
+    st1 += n_att > 1 ? 1u : 0u;
+#pragma unroll
+    for (int k = 0; k < NK; ++k) {
+      if (k < N) {
+        rec_pop_earliest<W>(rec[k], decoded && ((att >> k) & 1u));   // :137-144
+        discv[k] += rec_age<W>(rec[k]);                              // :157-158
+        chv[k] ^= lane16(sw4, k) < thr_sw[k] ? 1u : 0u;              // :107-109
+        if ((active >> k) & 1ull) {                                  // :162-180
+          const uint32_t arrived = arrival_from_u(P, cdf, k, pick_word(ar4, k));
+          rec_set_byte<W>(rec[k], dl[k] - 1, arrived);
+          recvv[k] += arrived;
+        }
+      }
+    }
+    if (a.reward_accum) rew += ack;                             // :191
+    else a.reward[(size_t)i * ra.reward_stride + b] = ack;
+  }
+#pragma unroll
+  for (int k = 0; k < NK; ++k) {
+    if (k < N) {
+      const size_t idx = (size_t)k * B + b;
+      rec_store<W>(a.buf, idx, rec[k]);
+      chan[idx] = (uint8_t)chv[k];
+      a.disc[idx] = discv[k], a.recv[idx] = recvv[k];
+    }
+  }
+  a.stats[b] = st0, a.stats[B + b] = st1;
+  if (a.reward_accum) a.reward[b] = rew;
+  if (a.done) a.done[b] = (uint8_t)a.done_flag;
+}
+
 template <int W>
 __global__ void __launch_bounds__(256) sc_reset_kernel(const StepArgs a) {
   extern __shared__ __align__(16) uint8_t smem[];
@@ -542,6 +639,7 @@ struct d2d_env {
   bool is_reset;
   std::vector<int> deadlines, obs_off, obs_dim;
   std::vector<uint64_t> active;
+  uint64_t* active_dev = nullptr;   // device copy of `active` (multi-step kernels index it by the episode timestep)
   int obs_rows, state_rows, sum_dl;
   uint32_t* buf = nullptr;
   void* chan = nullptr;
@@ -589,6 +687,7 @@ static int env_free(d2d_env* e) {
   if (!e) return D2D_OK;
   pipe_free(e->pipe);
   cudaFree(e->buf), cudaFree(e->chan), cudaFree(e->disc), cudaFree(e->recv), cudaFree(e->stats), cudaFree(e->params);
+  cudaFree(e->active_dev);
   delete e;
   return D2D_OK;
 }
@@ -715,6 +814,9 @@ extern "C" int d2d_env_create(const d2d_env_config* cfg, d2d_env** out) {
   alloc((void**)&e->stats, (size_t)2 * e->B * 4);
   alloc((void**)&e->params, blob.size());
   if (err == cudaSuccess) err = cudaMemcpy(e->params, blob.data(), blob.size(), cudaMemcpyHostToDevice);
+  alloc((void**)&e->active_dev, e->active.size() * 8);
+  if (err == cudaSuccess)
+    err = cudaMemcpy(e->active_dev, e->active.data(), e->active.size() * 8, cudaMemcpyHostToDevice);
   if (err != cudaSuccess) {
     set_error("d2d_env_create: CUDA allocation failed: %s", cudaGetErrorString(err));
     env_free(e);
@@ -897,6 +999,11 @@ extern "C" int d2d_env_run_random_access(d2d_env* e, double tp, int n_steps, int
     }
   }
   const uint32_t tp_thr = (uint32_t)std::min(65536.0, std::max(0.0, std::floor(tp * 65536.0 + 0.5)));
+  // single-channel env, N <= 4, no per-step observation / state rows wanted: the steps of one episode run inside ONE
+  // kernel with the env state in registers (sc_run_kernel)
+  const bool multi = e->kind == D2D_ENV_SINGLE_CHANNEL && e->N <= 4 && (e->W == 2 || e->W == 4) &&
+                     e->rng_mode == D2D_RNG_PHILOX && !obs && !state &&
+                     d2d_get_kernel_switch(D2D_SWITCH_ENV_MULTISTEP) == 1;
   for (int i = 0; i < n_steps; ++i) {
     float* obs_i = obs ? obs + (size_t)i * obs_step_stride : nullptr;
     float* state_i = state ? state + (size_t)i * state_step_stride : nullptr;
@@ -905,6 +1012,26 @@ extern "C" int d2d_env_run_random_access(d2d_env* e, double tp, int n_steps, int
       // the reset's observation goes to the slot of the step that follows and is overwritten by it
       int rc = d2d_env_reset(e, obs_i ? obs_i : nullptr, state_i, stream);
       if (rc) return rc;
+    }
+    if (multi) {
+      const int n_inner = std::min(n_steps - i, e->T - e->t);
+      StepArgs a;
+      int rc = fill_args(e, a, (uint32_t)(e->t + 1), "d2d_env_run_random_access");
+      if (rc) return rc;
+      a.reward = reward + (size_t)i * reward_step_stride, a.done = done;
+      a.act_mode = 1, a.tp_thr = tp_thr, a.reward_accum = reward_accumulate ? 1 : 0;
+      a.done_flag = e->t + n_inner >= e->T;
+      RunArgs ra;
+      ra.active = e->active_dev, ra.t_plain = e->t + 1, ra.n_inner = n_inner, ra.reward_stride = reward_step_stride;
+      // few envs: 64-thread blocks spread the warps over the SMs (each warp is one dependent-issue chain)
+      const int block = e->B >= 148 * 256 ? 256 : 64, grid = (e->B + block - 1) / block;
+      if (e->W == 2) sc_run_kernel<2, 4><<<grid, block, e->params_bytes, as_stream(stream)>>>(a, ra);
+      else sc_run_kernel<4, 4><<<grid, block, e->params_bytes, as_stream(stream)>>>(a, ra);
+      D2D_LAUNCHED();
+      e->t += n_inner;
+      i += n_inner - 1;
+      if (steps_done) *steps_done = i + 1;
+      continue;
     }
     StepArgs a;
     int rc = fill_args(e, a, (uint32_t)(e->t + 1), "d2d_env_run_random_access");

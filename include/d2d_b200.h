@@ -278,6 +278,8 @@ int d2d_net_check_inputs(const d2d_net* net, const float* x, int x_lead, int t0,
                                          (default 0: measured slower, kept for A/B runs) */
 #define D2D_SWITCH_WINDOW_HEAD 7      /* 0: the network head runs as its own kernel behind the GRU window kernel */
 #define D2D_SWITCH_BPTT_RECOMPUTE 6   /* 0: the BPTT kernel reads stored activations instead of recomputing the gates */
+#define D2D_SWITCH_ENV_MULTISTEP 9    /* 0: d2d_env_run_random_access launches one step kernel per step even where the
+                                         register-resident multi-step kernel applies (single-channel env, N <= 4) */
 int d2d_set_kernel_switch(int which, int enabled);
 int d2d_get_kernel_switch(int which);
 

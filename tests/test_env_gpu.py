@@ -464,3 +464,50 @@ def test_selection_env_fused_random_access_matches_oracle(cuda_device):
         _check_state(env, orc, "channel_selection", episode)
     freq = counts / counts.sum()
     assert np.all(np.abs(freq - 1.0 / C1) < 0.01), freq
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("deadline,traffic", [(7, "aperiodic"), (14, "aperiodic"), (5, "periodic"), (7, "mixed")])
+def test_multistep_kernel_equals_step_kernels(deadline, traffic, cuda_device):
+    """D2DEnv, N <= 4, no per-step observation rows: d2d_env_run_random_access runs the steps of an episode inside ONE
+    kernel with the env state in registers (sc_run_kernel).  Bit-identical to the same call with the multi-step kernel
+    switched off (one sc_step_kernel launch per step): per-step rewards, done flags, buffers, channel bits, packet
+    counters, error / collision counters, across two automatic resets, and for the accumulating reward form."""
+    import torch
+    from d2d_ppo_b200 import _lib as L
+    from d2d_ppo_b200.envs import D2DEnv
+    N, T, B, tp = (3 if traffic == "periodic" else 4), 11, 333, 0.35
+    kw = dict(n_agents=N, deadlines=np.array([deadline] * N), lbdas=np.array([1 / 4] * N), episode_length=T,
+              traffic_model="aperiodic" if traffic == "aperiodic" else "heterogeneous" if traffic == "mixed" else "periodic",
+              channel_switch=0.2)
+    if traffic == "periodic":
+        kw.update(period=3, arrival_probs=np.array([0.7] * N), offsets=np.array([0, 1, 2]))
+    if traffic == "mixed":
+        kw.update(period=np.array([4] * N), arrival_probs=np.array([0.6] * N), offsets=np.array([0, 1, 2, 3]),
+                  periodic_devices=[1, 3])
+    n = 2 * T + 5
+    outs = []
+    for multi in (1, 0):
+        L.set_kernel_switch(L.SWITCH_ENV_MULTISTEP, multi)
+        try:
+            e = D2DEnv(n_envs=B, device=cuda_device, seed=21, env_offset=1000, **kw)
+            rew = torch.full((n, B), -7, dtype=torch.int32, device=cuda_device)
+            before = L.launch_count()
+            assert e.run_random_access(tp, n, auto_reset=True, out_reward=rew, reward_stride=B) == n
+            launches = L.launch_count() - before
+            acc = torch.zeros(B, dtype=torch.int32, device=cuda_device)
+            e.reset()
+            assert e.run_random_access(tp, T + 3, out_reward=acc, accumulate=True) == T
+            bufs = [to_np(t) for t in e._export()]
+            outs.append((to_np(rew), to_np(acc), bufs, to_np(e.channel_errors), to_np(e.n_collisions), e.timestep,
+                         e.episode, launches))
+        finally:
+            L.set_kernel_switch(L.SWITCH_ENV_MULTISTEP, 1)
+    a, b = outs
+    assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1])
+    assert a[0].min() >= -1 and a[0].max() <= 1 and (a[0] != 0).any()
+    for x, y in zip(a[2], b[2]):
+        assert np.array_equal(x, y)
+    assert np.array_equal(a[3], b[3]) and np.array_equal(a[4], b[4]) and a[5:7] == b[5:7]
+    # 3 episodes -> 3 resets + 3 multi-step launches instead of one launch per step
+    assert a[7] == 6 and b[7] == 3 + n
