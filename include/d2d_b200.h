@@ -150,7 +150,10 @@ int d2d_env_step_random_access(d2d_env* env, double transmission_prob, void* act
  *   reward            i32: step i writes reward + i * reward_step_stride ([B] each); with reward_accumulate = 1
  *                     (stride 0) every step ADDS its reward into the one [B] buffer (zero it first): the
  *                     per-episode reward sum of baselines.py:211
- *   done              u8 [B] of the last step (may be NULL);  *steps_done (may be NULL): steps actually run     */
+ *   done              u8 [B] of the last step (may be NULL);  *steps_done (may be NULL): steps actually run
+ * Single-channel env with N <= 4 and obs == state == NULL (rewards only, RandomAccess.run): the steps of an episode
+ * run in ONE launch with the env state in registers (sc_run_kernel), bit-identical to the per-step launches
+ * (D2D_SWITCH_ENV_MULTISTEP = 0 restores them). */
 int d2d_env_run_random_access(d2d_env* env, double transmission_prob, int n_steps, int auto_reset, float* obs,
                               int64_t obs_step_stride, float* state, int64_t state_step_stride, int32_t* reward,
                               int64_t reward_step_stride, int reward_accumulate, uint8_t* done, void* stream,
