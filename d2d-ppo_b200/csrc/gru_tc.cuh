@@ -194,6 +194,8 @@ struct Smem {
 }  // namespace tc
 
 // STORE: the training direction (a.store); compile time so that the rollout kernel carries none of the store code.
+// 1: h and the gates (r, z, n, gh_n) of every step are kept (BPTT kernels that read them: recompute switched off);
+// 2: only h is kept (the recomputing BPTT kernel) and the gate maths takes the rollout's shared-reciprocal form.
 // OMAX > 0: the network head is fused behind the last step -- Linear(H, H) as one more
 // two-plane GEMM on the h planes the step already staged (12 MMAs), ReLU and Linear(H, O <= OMAX) on the CUDA cores from
 // TMEM, the two unit halves of a row combined through shared memory -- and the kernel writes the O pre-activation
@@ -201,7 +203,7 @@ struct Smem {
 // Q: threads per row (each owns H / Q hidden units).  Q = 2: 16 warps of 128 registers.  Q = 4: 32 warps of 64
 // registers -- four instead of two warps per scheduler are in a slot's gate phase, which is latency bound (dependent
 // MUFU / FMA chains at an IPC of ~0.5 per scheduler with two warps).
-template <int H, bool STORE, int OMAX = 0, int Q = 2>
+template <int H, int STORE, int OMAX = 0, int Q = 2>
 __global__ void __launch_bounds__(256 * Q, 1) gru_window_tc_kernel(const GruTcArgs a) {
   using namespace tc;
   using S = Smem<H>;
@@ -411,7 +413,7 @@ __global__ void __launch_bounds__(256 * Q, 1) gru_window_tc_kernel(const GruTcAr
         float* acts_row = nullptr;
         float* hs_row = nullptr;
         if (STORE && b < a.B) {   // acts.p == nullptr: only h is kept (the recomputing BPTT kernel, gru_bptt_tc.cuh)
-          if (a.acts.p) acts_row = view_ptr(a.acts, g, t, a.B, b) + (long long)s * a.acts_step;
+          if constexpr (STORE == 1) acts_row = view_ptr(a.acts, g, t, a.B, b) + (long long)s * a.acts_step;
           hs_row = view_ptr(a.hs, g, t, a.B, b) + (long long)s * a.hs_step;
         }
 #pragma unroll
@@ -441,7 +443,7 @@ __global__ void __launch_bounds__(256 * Q, 1) gru_window_tc_kernel(const GruTcAr
             const float ghn = fmaf(phn[j], kInvWScale, b_h[j]);
             const float pre = fmaf(r, ghn, fmaf(pin[j], kInvWScale, b_i[j]));
             float hv, z = 0.f, nn = 0.f;
-            if constexpr (STORE) {
+            if constexpr (STORE == 1) {
               z = rcp_approx(1.0f + ex2_approx(fmaf(pz[j], kSig, b_z[j])));
               // tanh(v) = 1 - 2 / (1 + 2^(2 v log2 e))
               nn = fmaf(-2.0f, rcp_approx(1.0f + ex2_approx(2.8853900817779268f * pre)), 1.0f);
@@ -461,7 +463,7 @@ __global__ void __launch_bounds__(256 * Q, 1) gru_window_tc_kernel(const GruTcAr
             if (STORE && b < a.B) {   // rows of a warp are consecutive envs: every store below is one 128-byte line
               const long long f = (long long)(u0 + c * 8 + j) * a.B;
               const long long hb = (long long)H * a.B;
-              if (acts_row) acts_row[f] = r, acts_row[f + hb] = z, acts_row[f + 2 * hb] = nn, acts_row[f + 3 * hb] = ghn;
+              if constexpr (STORE == 1) acts_row[f] = r, acts_row[f + hb] = z, acts_row[f + 2 * hb] = nn, acts_row[f + 3 * hb] = ghn;
               hs_row[f] = hv;
             }
           }

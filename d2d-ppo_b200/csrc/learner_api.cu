@@ -274,7 +274,7 @@ static bool gru_tc_eligible(const d2d_net* n) {
          (n->H == 16 || n->H == 32 || n->H == 48 || n->H == 64);
 }
 
-template <int H, bool STORE, int OMAX, int Q>
+template <int H, int STORE, int OMAX, int Q>
 static int launch_gru_tc_q(const d2d_net* n, const GruTcArgs& a, cudaStream_t s) {
   const size_t smem =
       OMAX > 0 ? ((tc::Smem<H>::bytes + 15) & ~(size_t)15) + tc::Smem<H>::head_bytes(OMAX, Q) : tc::Smem<H>::bytes;
@@ -292,7 +292,7 @@ static int launch_gru_tc_q(const d2d_net* n, const GruTcArgs& a, cudaStream_t s)
   return D2D_OK;
 }
 
-template <int H, bool STORE, int OMAX>
+template <int H, int STORE, int OMAX>
 static int launch_gru_tc_hs(const d2d_net* n, const GruTcArgs& a, cudaStream_t s) {
   // two threads per row (16 warps of 128 registers).  The four-threads-per-row variant (32 warps of 64 registers, more
   // warps per scheduler in the latency-bound gate phase) is kept behind D2D_SWITCH_WINDOW_WIDE: measured SLOWER on
@@ -307,19 +307,25 @@ static int launch_gru_tc_hs(const d2d_net* n, const GruTcArgs& a, cudaStream_t s
 template <int H>
 static int launch_gru_tc_h(const d2d_net* n, const GruTcArgs& a, cudaStream_t s, bool head) {
   if constexpr (H == 32 || H == 64) {
-    if (head && a.store) {
-      if (a.O <= 1) return launch_gru_tc_hs<H, true, 1>(n, a, s);
-      if (a.O <= 8) return launch_gru_tc_hs<H, true, 8>(n, a, s);
-      return launch_gru_tc_hs<H, true, 16>(n, a, s);
+    if (head && a.store && a.acts.p) {   // gates kept for a BPTT kernel that reads them
+      if (a.O <= 1) return launch_gru_tc_hs<H, 1, 1>(n, a, s);
+      if (a.O <= 8) return launch_gru_tc_hs<H, 1, 8>(n, a, s);
+      return launch_gru_tc_hs<H, 1, 16>(n, a, s);
+    }
+    if (head && a.store) {               // only h kept (recomputing BPTT kernel)
+      if (a.O <= 1) return launch_gru_tc_hs<H, 2, 1>(n, a, s);
+      if (a.O <= 8) return launch_gru_tc_hs<H, 2, 8>(n, a, s);
+      return launch_gru_tc_hs<H, 2, 16>(n, a, s);
     }
     if (head) {
-      if (a.O <= 1) return launch_gru_tc_hs<H, false, 1>(n, a, s);
-      if (a.O <= 8) return launch_gru_tc_hs<H, false, 8>(n, a, s);
-      return launch_gru_tc_hs<H, false, 16>(n, a, s);
+      if (a.O <= 1) return launch_gru_tc_hs<H, 0, 1>(n, a, s);
+      if (a.O <= 8) return launch_gru_tc_hs<H, 0, 8>(n, a, s);
+      return launch_gru_tc_hs<H, 0, 16>(n, a, s);
     }
   }
-  if (a.store) return launch_gru_tc_hs<H, true, 0>(n, a, s);
-  return launch_gru_tc_hs<H, false, 0>(n, a, s);
+  if (a.store && a.acts.p) return launch_gru_tc_hs<H, 1, 0>(n, a, s);
+  if (a.store) return launch_gru_tc_hs<H, 2, 0>(n, a, s);
+  return launch_gru_tc_hs<H, 0, 0>(n, a, s);
 }
 
 static bool head_fused_eligible(const d2d_net* n);
