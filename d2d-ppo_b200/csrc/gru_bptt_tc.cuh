@@ -56,8 +56,15 @@ struct GruBpttArgs {
   int L, B, t0, t1;
 };
 
+#ifdef D2D_BPTT_TRACE
+__device__ long long g_bptt_trace[16 * 512];
+#define D2D_TR(i) do { if (tid == 0 && blockIdx.x == 0 && blockIdx.y == 0 && tr_n < 512) g_bptt_trace[tr_n * 16 + (i)] = clock64(); } while (0)
+#else
+#define D2D_TR(i) do { } while (0)
+#endif
 namespace tcr {
-constexpr int kThreads = 512;
+constexpr int kGate = 512;              // 16 gate warps
+constexpr int kThreads = kGate + 32;    // + one warp whose lane 0 issues every MMA
 template <int H>
 struct Smem {
   static constexpr int kG = tc::kM * 3 * H;       // fp16 elements per d(gh) plane
@@ -68,6 +75,51 @@ struct Smem {
   static constexpr int kX = tc::kM * tc::kKx;
   static constexpr size_t bytes = (size_t)(2 * kG + 2 * kW + kP0 + kP1 + 2 * kWih + kX) * 2 + 4 * H * 4 + 64;
 };
+// D[tmem] (+)= A[tmem] B[smem]: the A tile sits in tensor memory, lane = row, one 32-bit column = two consecutive K
+// elements (K = 16 per instruction = 8 columns)
+__device__ __forceinline__ void mma_f16_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t bdesc, uint32_t idesc, bool accum) {
+  const uint32_t acc = accum ? 1u : 0u;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "r"(a_tmem), "l"(bdesc), "r"(idesc), "r"(acc)
+      : "memory");
+}
+// Warp-uniform issue: EVERY lane of the issuing warp executes these (uniform control flow, identical operands), the
+// instruction itself is predicated on elect.sync.  With uniform operands ptxas keeps the descriptors in uniform
+// registers and emits back-to-back UTCHMMA (3 instructions per MMA); issued from one lane of a divergent branch, each
+// MMA costs two R2UR and an ELECT / BRA.U.ANY loop (~14 instructions, 80-100 cycles per MMA measured).
+__device__ __forceinline__ void mma_f16_e(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n\t.reg .pred p, q;\n\telect.sync _|q, 0xffffffff;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "@q tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
+      : "memory");
+}
+__device__ __forceinline__ void mma_f16_ts_e(uint32_t d_tmem, uint32_t a_tmem, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n\t.reg .pred p, q;\n\telect.sync _|q, 0xffffffff;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "@q tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "r"(a_tmem), "l"(bdesc), "r"(idesc), "r"(acc)
+      : "memory");
+}
+__device__ __forceinline__ void commit_e(uint64_t* bar) {
+  asm volatile(
+      "{\n\t.reg .pred q;\n\telect.sync _|q, 0xffffffff;\n\t"
+      "@q tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}"
+      ::"r"(tc::smem_u32(bar))
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st8u(uint32_t taddr, const uint32_t* v) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
+               ::"r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7])
+               : "memory");
+}
+__device__ __forceinline__ void tmem_st4u(uint32_t taddr, const uint32_t* v) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1, %2, %3, %4};"
+               ::"r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3])
+               : "memory");
+}
 // D = F32, A = B = FP16, M = 128; bit 15 / 16: A / B are MN-major
 __device__ __forceinline__ uint32_t idesc_f16_major(int n, bool a_mn, bool b_mn) {
   return tc::idesc_f16(n) | (a_mn ? (1u << 15) : 0u) | (b_mn ? (1u << 16) : 0u);
@@ -134,12 +186,13 @@ __global__ void __launch_bounds__(tcr::kThreads, 1) gru_bptt_tc_kernel(const Gru
     bias[i] = v;
   }
   if (tid == 0) {
-    mbar_init(a_ready, tcr::kThreads), mbar_init(r_ready, 1), mbar_init(g_ready, tcr::kThreads);
-    mbar_init(d_ready, tcr::kThreads / 32), mbar_init(w_done, tcr::kThreads / 32);
+    mbar_init(a_ready, tcr::kGate), mbar_init(r_ready, 1), mbar_init(g_ready, tcr::kGate);
+    mbar_init(d_ready, 1), mbar_init(w_done, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   constexpr uint32_t kColsUsed = 4 * H + H + NBLK * NP0;
-  constexpr uint32_t kCols = kColsUsed <= 128 ? 128 : (kColsUsed <= 256 ? 256 : 512);
+  constexpr uint32_t kColsAll = kColsUsed + (H == 64 ? 0 : 32);    // H = 32: h_{s-1} operand planes behind the accumulators
+  constexpr uint32_t kCols = kColsAll <= 128 ? 128 : (kColsAll <= 256 ? 256 : 512);
   if (warp == 0) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
                  "r"(kCols));
@@ -173,21 +226,101 @@ __global__ void __launch_bounds__(tcr::kThreads, 1) gru_bptt_tc_kernel(const Gru
   const long long HB = (long long)H * a.B;
   const float gs = exp2f(10.0f - ceilf(log2f(fmaxf(*a.dh_absmax, 1e-30f))));
   const float d_scale = kWScale * gs, d_unscale = 1.0f / d_scale;
-  uint32_t ph_a = 0, ph_r = 0, ph_g = 0, ph_d = 0, ph_w = 0;
-  bool staged_before = false;           // a weight-gradient batch is (or was) in flight on the operand tiles
   const uint32_t id_x = idesc_f16(4 * H);                                  // x W_ih^T: both K-major, N = 4H
   const uint32_t id_h = tcr::idesc_f16_major(K3, false, true);             // h W_hh^T: B = W_hh^T tiles read MN-major
   const uint32_t id_d = idesc_f16(H);                                      // G W_hh: both K-major, N = H
   const uint32_t id_w0 = tcr::idesc_f16_major(NP0, true, true), id_w = tcr::idesc_f16_major(H, true, true);
-  // base descriptors, built once (desc_adv moves the start address only)
   constexpr uint32_t ks_g = (K3 / 8) * 128, ks_p0 = (NP0 / 8) * 128, ks_p = (H / 8) * 128;   // 8-row group strides
-  const uint64_t dg_k = desc16(smem_u32(sg), K3), dw_k = desc16(smem_u32(sw), K3);
-  const uint64_t dw_mn = tcb::desc_mn(smem_u32(sw), ks_g, 128);            // [H rows = K][3H = N]
-  const uint64_t dg_mn = tcb::desc_mn(smem_u32(sg), ks_g, 128);
-  const uint64_t dp0_k = desc16(smem_u32(sp0), NP0), dp1_k = desc16(smem_u32(sp1), H);
-  const uint64_t dp0_mn = tcb::desc_mn(smem_u32(sp0), ks_p0, 128), dp1_mn = tcb::desc_mn(smem_u32(sp1), ks_p, 128);
-  const uint64_t dx_k = desc16(smem_u32(sx), kKx), dwih_k = desc16(smem_u32(swih), kKx);
+  // h_{s-1} as the A operand of the recompute, in TENSOR memory (the shared-memory copy P is written later, in phase B,
+  // for the weight-gradient GEMM only, so that GEMM can run behind the next step's recompute).  Plane i of hidden-unit
+  // group j (16 units = one K step = 8 packed columns):
+  //   H = 64: inside D's columns, at tmem_d + 16 j + 8 i -- the 16 columns of D that belong to the thread quarter j
+  //           which also owns those units, so a thread only overwrites D columns it has read itself;
+  //   H = 32: its own 32 columns behind the accumulators, at tmem_p + 16 i + 8 j (thread quarter q: 4 columns at + 4 q).
+  const uint32_t tmem_p = H == 64 ? tmem_d : tmem + kColsUsed;
+  int n_steps = 0;                      // window steps this CTA has staged so far
+  int tr_n = 0;
+  (void)tr_n;
 
+  if (__shfl_sync(0xffffffffu, warp, 0) == tcr::kGate / 32) {
+    // =================== MMA warp: issues every MMA, in the order  D(s), recompute(s - 1), dW(s)  ==================
+    // so that the weight-gradient GEMM of a step runs on the tensor pipe while the CUDA cores are in the NEXT step's
+    // gate phase (the pipe would idle there), and no gate warp ever blocks on a full MMA queue.  The whole warp runs
+    // this code uniformly; the MMA / commit instructions are predicated on elect.sync (mma_f16_e).
+    const uint32_t tm = __shfl_sync(0xffffffffu, tmem, 0);
+    const uint32_t tm_d = tm + 4 * H, tm_dw = tm + 5 * H, tm_p = H == 64 ? tm_d : tm + kColsUsed;
+    const uint64_t dg_k = desc16(smem_u32(sg), K3), dw_k = desc16(smem_u32(sw), K3);
+    const uint64_t dw_mn = tcb::desc_mn(smem_u32(sw), ks_g, 128);            // [H rows = K][3H = N]
+    const uint64_t dg_mn = tcb::desc_mn(smem_u32(sg), ks_g, 128);
+    const uint64_t dp0_mn = tcb::desc_mn(smem_u32(sp0), ks_p0, 128), dp1_mn = tcb::desc_mn(smem_u32(sp1), ks_p, 128);
+    const uint64_t dx_k = desc16(smem_u32(sx), kKx), dwih_k = desc16(smem_u32(swih), kKx);
+    auto a_col = [&](int plane, int k16) { return H == 64 ? tm_p + 16 * k16 + 8 * plane : tm_p + 16 * plane + 8 * k16; };
+    // dW += G^T P of the step whose G / P tiles are staged: both tiles read along their contiguous dimension,
+    // reduction over the 128 rows; plane pairs g0 p0, g1 p0, g0 p1
+    auto issue_dw = [&]() {
+#pragma unroll
+      for (int pr = 0; pr < 3; ++pr) {
+        const int gi_ = pr == 1 ? 1 : 0;
+#pragma unroll
+        for (int k16 = 0; k16 < kM / 16; ++k16) {
+          const uint64_t pd = pr < 2 ? desc_adv(dp0_mn, k16 * 2 * ks_p0) : desc_adv(dp1_mn, k16 * 2 * ks_p);
+#pragma unroll
+          for (int blk = 0; blk < NBLK; ++blk)
+            tcr::mma_f16_e(tm_dw + (uint32_t)(blk * NP0), desc_adv(dg_mn, gi_ * S::kG * 2 + blk * 16 * 128 + k16 * 2 * ks_g),
+                           pd, pr < 2 ? id_w0 : id_w, 1u);
+        }
+      }
+      tcr::commit_e(w_done);
+    };
+    uint32_t ph_a = 0, ph_g = 0;
+    bool dw_pending = false;
+    for (int p = blockIdx.x; p < n_tiles; p += gridDim.x) {
+#pragma unroll 1
+      for (int s = L - 1; s >= 0; --s) {
+        mbar_wait(a_ready, ph_a);
+        ph_a ^= 1u;
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        // recompute: x W_ih^T initialises all 4H columns (zero block -> gh_n), h_{s-1} W_hh^T accumulates onto [0, 3H)
+#pragma unroll
+        for (int j = 0; j < 2; ++j)
+#pragma unroll
+          for (int k16 = 0; k16 < kKx / 16; ++k16)
+            tcr::mma_f16_e(tm, desc_adv(dx_k, k16 * 256), desc_adv(dwih_k, j * S::kWih * 2 + k16 * 256), id_x,
+                           j + k16 > 0 ? 1u : 0u);
+        if (s > 0) {
+#pragma unroll
+          for (int pr = 0; pr < 3; ++pr) {          // h0 w0, h0 w1, h1 w0
+            const int wi = pr == 1 ? 1 : 0;
+#pragma unroll
+            for (int k16 = 0; k16 < H / 16; ++k16)
+              tcr::mma_f16_ts_e(tm, a_col(pr == 2 ? 1 : 0, k16), desc_adv(dw_mn, wi * S::kW * 2 + k16 * 2 * ks_g), id_h, 1u);
+          }
+        }
+        tcr::commit_e(r_ready);
+        if (dw_pending) issue_dw();             // the previous step's G / P tiles: behind this step's recompute
+        mbar_wait(g_ready, ph_g);
+        ph_g ^= 1u;
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        if (s > 0) {
+          // D += d(gh) W_hh : G K-major x W_hh^T K-major, plane pairs g0 w0, g0 w1, g1 w0 over 3H / 16 reduction steps
+#pragma unroll
+          for (int pr = 0; pr < 3; ++pr) {
+            const int gi_ = pr == 2 ? 1 : 0, wi = pr == 1 ? 1 : 0;
+#pragma unroll
+            for (int k16 = 0; k16 < K3 / 16; ++k16)
+              tcr::mma_f16_e(tm_d, desc_adv(dg_k, gi_ * S::kG * 2 + k16 * 256), desc_adv(dw_k, wi * S::kW * 2 + k16 * 256),
+                             id_d, 1u);
+          }
+          tcr::commit_e(d_ready);
+        }
+        dw_pending = true;
+      }
+    }
+    if (dw_pending) issue_dw();                 // flush: the last step staged
+    __syncwarp();
+  } else {
+  // =================== gate warps ==================================================================================
+  uint32_t ph_r = 0, ph_d = 0, ph_w = 0;
   for (int p = blockIdx.x; p < n_tiles; p += gridDim.x) {
     const int t = a.t0 + p % n_t;
     const int b = (p / n_t) * kM + row;
@@ -218,20 +351,21 @@ __global__ void __launch_bounds__(tcr::kThreads, 1) gru_bptt_tc_kernel(const Gru
     load_step(L - 1);
     for (int s = L - 1; s >= 0; --s) {
       float* gp = view_ptr(a.dgi, g, t - (L - 1 - s), a.B, bb) + (long long)u0 * a.B;
-      // the operand tiles are free once the weight-gradient MMAs of the previous staging have completed
-      if (staged_before) {
-        mbar_wait(w_done, ph_w);
-        ph_w ^= 1u;
-      }
-      staged_before = true;
-      // ---- A. stage P = h_{s-1} (2 planes) and X = x_s ----
+      D2D_TR(0);
+      // ---- A. h_{s-1} (2 planes) -> tensor memory, X = x_s -> shared memory ----
+      // (D's columns are free: this thread read its own in phase C, the MMAs that wrote them completed before that;
+      //  X was last read by the previous recompute, which completed before the previous phase B)
+      if (s > 0) {
+        uint32_t q0[UT / 2], q1[UT / 2];
 #pragma unroll
-      for (int c = 0; c < UT / 8; ++c) {
-        uint32_t q0[4], q1[4];
-#pragma unroll
-        for (int j = 0; j < 4; ++j) split2h(hp[c * 8 + 2 * j], hp[c * 8 + 2 * j + 1], q0[j], q1[j]);
-        *reinterpret_cast<uint4*>(sp0 + canon16(row, u0 + c * 8, NP0)) = make_uint4(q0[0], q0[1], q0[2], q0[3]);
-        *reinterpret_cast<uint4*>(sp1 + canon16(row, u0 + c * 8, H)) = make_uint4(q1[0], q1[1], q1[2], q1[3]);
+        for (int j = 0; j < UT / 2; ++j) split2h(hp[2 * j], hp[2 * j + 1], q0[j], q1[j]);
+        if constexpr (H == 64) {
+          tcr::tmem_st8u(tmem_p + lane_addr + (uint32_t)(16 * quarter), q0);
+          tcr::tmem_st8u(tmem_p + lane_addr + (uint32_t)(16 * quarter + 8), q1);
+        } else {
+          tcr::tmem_st4u(tmem_p + lane_addr + (uint32_t)(4 * quarter), q0);
+          tcr::tmem_st4u(tmem_p + lane_addr + (uint32_t)(16 + 4 * quarter), q1);
+        }
       }
       {
         const __half2 a0 = __floats2half2_rn(xq[0], xq[1]), a1 = __floats2half2_rn(xq[2], xq[3]);
@@ -241,38 +375,15 @@ __global__ void __launch_bounds__(tcr::kThreads, 1) gru_bptt_tc_kernel(const Gru
         v.z = *reinterpret_cast<const uint32_t*>(&a2), v.w = *reinterpret_cast<const uint32_t*>(&a3);
         *reinterpret_cast<uint4*>(sx + canon16(row, quarter * XQ, kKx)) = v;
       }
+      if (s > 0) asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
       mbar_arrive(a_ready);
-      if (tid == 0) {
-        mbar_wait(a_ready, ph_a);
-        ph_a ^= 1u;
-        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        // recompute: x W_ih^T initialises all 4H columns (zero block -> gh_n), h_{s-1} W_hh^T accumulates onto [0, 3H)
-#pragma unroll
-        for (int j = 0; j < 2; ++j)
-#pragma unroll
-          for (int k16 = 0; k16 < kKx / 16; ++k16)
-            mma_bf16(tmem, desc_adv(dx_k, k16 * 256), desc_adv(dwih_k, j * S::kWih * 2 + k16 * 256), id_x, j + k16 > 0);
-        if (s > 0) {
-#pragma unroll
-          for (int pr = 0; pr < 3; ++pr) {          // h0 w0, h0 w1, h1 w0
-            const int wi = pr == 1 ? 1 : 0;
-#pragma unroll
-            for (int k16 = 0; k16 < H / 16; ++k16) {
-              const uint64_t ad = pr == 2 ? desc_adv(dp1_k, k16 * 256) : desc_adv(dp0_k, k16 * 256);
-              mma_bf16(tmem, ad, desc_adv(dw_mn, wi * S::kW * 2 + k16 * 2 * ks_g), id_h, true);
-            }
-          }
-        }
-        asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];"
-                     ::"r"(smem_u32(r_ready))
-                     : "memory");
-      }
-      __syncwarp();
+      D2D_TR(1);
       mbar_wait(r_ready, ph_r);
       ph_r ^= 1u;
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      D2D_TR(2);
       // ---- B. gates from the recomputed pre-activations, derivatives, G = d(gh), d(gi), direct path into D ----
 #pragma unroll
       for (int c = 0; c < UT / 8; ++c) {
@@ -308,11 +419,19 @@ __global__ void __launch_bounds__(tcr::kThreads, 1) gru_bptt_tc_kernel(const Gru
           const float dr = dn * ghn * r * (1.0f - r);
           dg[0][j] = dr * gs, dg[1][j] = dz * gs, dg[2][j] = dn * r * gs;
           dd[j] = dv * z * d_scale;          // direct path: pre-loaded into D, d(gh) W_hh accumulates on top
+#ifndef D2D_BPTT_NO_ATOMICS   // (timing experiment only)
           if (ok) {
             const long long f = (long long)u * a.B;
             atomicAdd(gp + f, dr), atomicAdd(gp + f + HB, dz), atomicAdd(gp + f + 2 * HB, dn);
           }
+#endif
         }
+        if (c == 0) D2D_TR(3);
+        if (c == 0 && n_steps > 0) {         // G and P are free once the previous step's weight-gradient MMAs are done
+          mbar_wait(w_done, ph_w);
+          ph_w ^= 1u;
+        }
+        if (c == 0) D2D_TR(4);
         if (s > 0) tcb::tmem_st8(tmem_d + lane_addr + (uint32_t)(u0 + c * 8), dd);
 #pragma unroll
         for (int gate = 0; gate < 3; ++gate) {
@@ -323,51 +442,28 @@ __global__ void __launch_bounds__(tcr::kThreads, 1) gru_bptt_tc_kernel(const Gru
           *reinterpret_cast<uint4*>(dst) = make_uint4(w0[0], w0[1], w0[2], w0[3]);
           *reinterpret_cast<uint4*>(dst + S::kG) = make_uint4(w1[0], w1[1], w1[2], w1[3]);
         }
+        {                                    // P = h_{s-1} (2 planes) for the weight-gradient GEMM
+          uint32_t q0[4], q1[4];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) split2h(hp[c * 8 + 2 * j], hp[c * 8 + 2 * j + 1], q0[j], q1[j]);
+          *reinterpret_cast<uint4*>(sp0 + canon16(row, u0 + c * 8, NP0)) = make_uint4(q0[0], q0[1], q0[2], q0[3]);
+          *reinterpret_cast<uint4*>(sp1 + canon16(row, u0 + c * 8, H)) = make_uint4(q1[0], q1[1], q1[2], q1[3]);
+        }
       }
       if (s > 0) asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
       mbar_arrive(g_ready);
-      if (lane == 0) {
-        mbar_wait(g_ready, ph_g);
-        ph_g ^= 1u;
-        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        constexpr int kWarps = tcr::kThreads / 32;
-        if (s > 0) {
-          // D += d(gh) W_hh : G K-major x W_hh^T K-major, plane pairs g0 w0, g0 w1, g1 w0 over 3H / 16 reduction steps,
-          // dealt round robin to the warps' issuing lanes
-          constexpr int kPer = K3 / 16;
-          for (int m = warp; m < 3 * kPer; m += kWarps) {
-            const int pr = m / kPer, k16 = m % kPer;
-            const int gi_ = pr == 2 ? 1 : 0, wi = pr == 1 ? 1 : 0;
-            mma_bf16(tmem_d, desc_adv(dg_k, gi_ * S::kG * 2 + k16 * 256), desc_adv(dw_k, wi * S::kW * 2 + k16 * 256), id_d,
-                     true);
-          }
-          asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];"
-                       ::"r"(smem_u32(d_ready))
-                       : "memory");
-        }
-        // dW += G^T P : both tiles read along their contiguous dimension, reduction over the 128 rows;
-        // plane pairs g0 p0, g1 p0, g0 p1
-        constexpr int kPerW = (kM / 16) * NBLK;
-        for (int m = warp; m < 3 * kPerW; m += kWarps) {
-          const int pr = m / kPerW, k16 = (m % kPerW) / NBLK, blk = m % NBLK;
-          const int gi_ = pr == 1 ? 1 : 0;
-          const uint64_t pd = pr < 2 ? desc_adv(dp0_mn, k16 * 2 * ks_p0) : desc_adv(dp1_mn, k16 * 2 * ks_p);
-          mma_bf16(tmem_dw + (uint32_t)(blk * NP0), desc_adv(dg_mn, gi_ * S::kG * 2 + blk * 16 * 128 + k16 * 2 * ks_g),
-                   pd, pr < 2 ? id_w0 : id_w, true);
-        }
-        asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];"
-                     ::"r"(smem_u32(w_done))
-                     : "memory");
-      }
-      __syncwarp();
-      if (s == 0) break;                     // dh of the zero initial state is not needed
+      D2D_TR(5);
+      ++n_steps;
+      if (s == 0) { ++tr_n; break; }         // dh of the zero initial state is not needed
       load_step(s - 1);                      // in flight while the tensor pipe works (h_{s-1}'s registers are free now)
+      D2D_TR(6);
       // ---- C. dh_prev = (dh z + d(gh) W_hh) from D ----
       mbar_wait(d_ready, ph_d);
       ph_d ^= 1u;
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      D2D_TR(7);
 #pragma unroll
       for (int c = 0; c < UT / 8; ++c) {
         float v[8];
@@ -376,13 +472,19 @@ __global__ void __launch_bounds__(tcr::kThreads, 1) gru_bptt_tc_kernel(const Gru
 #pragma unroll
         for (int j = 0; j < 8; ++j) dh[c * 8 + j] = v[j] * d_unscale;
       }
+      D2D_TR(8);
+      ++tr_n;
     }
   }
-  // ---- partial dW_hh / db_hh of this CTA: accumulator row = gate row (TMEM lane), column = unit, column H = bias ----
-  if (staged_before) {
+  // the flush's weight-gradient MMAs (the accumulators are read below)
+  if (n_steps > 0) {
     mbar_wait(w_done, ph_w);
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   }
+  }   // gate warps
+  const bool any_tile = (int)blockIdx.x < n_tiles;
+  const bool staged_before = any_tile;
+  // ---- partial dW_hh / db_hh of this CTA: accumulator row = gate row (TMEM lane), column = unit, column H = bias ----
   if (warp < 4) {
     float* out = a.partial + ((long long)g * gridDim.x + blockIdx.x) * a.part_stride;
     const float unscale = 1.0f / gs;

@@ -1188,3 +1188,9 @@ extern "C" int d2d_normalize(const double* raw, float* out, const double* mean, 
   D2D_LAUNCHED();
   return D2D_OK;
 }
+
+#ifdef D2D_BPTT_TRACE
+extern "C" int d2d_debug_bptt_trace(long long* out) {
+  return cudaMemcpyFromSymbol(out, d2d::g_bptt_trace, sizeof(long long) * 16 * 512) == cudaSuccess ? 0 : -1;
+}
+#endif
