@@ -40,7 +40,7 @@ class NetConfig(C.Structure):
         ("arch", C.c_int32), ("out_kind", C.c_int32), ("n_agents", C.c_int32), ("n_envs", C.c_int32),
         ("hidden", C.c_int32), ("n_out", C.c_int32), ("history_len", C.c_int32), ("in_rows", C.c_int32),
         ("in_dim", C.POINTER(C.c_int32)), ("in_off", C.POINTER(C.c_int32)), ("scratch_bytes", C.c_int64),
-        ("inputs_bf16_exact", C.c_int32), ("reserved0", C.c_int32),
+        ("inputs_bf16_exact", C.c_int32), ("head_layers", C.c_int32),
     ]
 
 
@@ -49,6 +49,7 @@ OUT_SOFTMAX, OUT_SIGMOID, OUT_IDENTITY = 0, 1, 2
 DIST_BERNOULLI, DIST_CATEGORICAL = 0, 1
 ACT_SAMPLE, ACT_GREEDY, ACT_GIVEN = 0, 1, 2
 ACT_HOST_REFERENCE, ACT_HOST_DEVICE_LAYOUT = 0, 1
+QLOSS_HUBER, QLOSS_MSE = 0, 1
 SWITCH_GRU_WINDOW_TC, SWITCH_GRU_BPTT_TC, SWITCH_DENSE_TC, SWITCH_WGRAD_TC, SWITCH_FUSED_HEAD, SWITCH_ALL_TC, \
     SWITCH_BPTT_RECOMPUTE, SWITCH_WINDOW_HEAD, SWITCH_WINDOW_WIDE, SWITCH_ENV_MULTISTEP = range(10)
 
@@ -111,6 +112,14 @@ _SIGNATURES = {
     "d2d_returns_emit": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, C.c_int, C.c_int, C.c_int, C.c_double,
                                    C.c_double, C.c_int, _P]),
     "d2d_normalize": (C.c_int, [_P, _P, _P, _P, _P, C.c_int, C.c_int, C.c_int, C.c_int, _P]),
+    "d2d_adam_step_eps": (C.c_int, [_P, _P, _P, _P, C.c_int, C.c_int64, C.c_float, C.c_float, C.c_int, C.c_float, _P,
+                                    _P]),
+    "d2d_q_select": (C.c_int, [C.c_int, C.c_int, C.c_int, _P, C.c_int, C.c_float, C.c_int, C.c_int, _P, _P, C.c_int,
+                               C.c_uint64, C.c_uint64, C.c_int, _P]),
+    "d2d_q_td_target": (C.c_int, [C.c_int, C.c_int, C.c_int, _P, _P, _P, C.c_float, _P, _P]),
+    "d2d_q_grad": (C.c_int, [_P, _P, _P, C.c_int, C.c_int, C.c_int, _P, _P, C.c_int, C.c_float, _P, _P, _P, _P]),
+    "d2d_replay_gather": (C.c_int, [_P, _P, _P, _P, _P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
+                                    C.c_int, _P, _P, _P, _P, _P, _P]),
 }
 
 

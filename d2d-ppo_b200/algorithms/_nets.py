@@ -17,6 +17,8 @@ from .. import _lib as L
 GRU_KEYS = ["lstm.weight_ih_l0", "lstm.weight_hh_l0", "lstm.bias_ih_l0", "lstm.bias_hh_l0",
             "layers.0.weight", "layers.0.bias", "layers.2.weight", "layers.2.bias"]
 MLP_KEYS = ["linear1.weight", "linear1.bias", "linear2.weight", "linear2.bias"]
+# the Q-network of algorithms/irdqn.py:58-72: one more hidden Linear + ReLU behind the GRU
+GRU_Q_KEYS = GRU_KEYS[:6] + ["layers.2.weight", "layers.2.bias", "layers.4.weight", "layers.4.bias"]
 
 
 def _orthogonal(rows, cols, gain, generator):
@@ -30,8 +32,14 @@ class NetSet:
     """N independent networks of one architecture evaluated in one launch (grid.y = agent)."""
 
     def __init__(self, arch, out_kind, n_agents, n_envs, in_dim, in_off, in_rows, hidden, n_out, history_len, device,
-                 lr, scratch_bytes=0, generator=None, inputs_bf16_exact=False):
+                 lr, scratch_bytes=0, generator=None, inputs_bf16_exact=False, head_layers=1, adam_eps=1e-8,
+                 share_with=None):
+        """head_layers = 2: the GRU Q-network of irdqn.py.  share_with: another NetSet of the same architecture
+        (any n_envs) whose parameter / gradient / optimiser buffers this handle aliases -- the kernels of a handle are
+        sized for its n_envs, so a learner that evaluates the same networks on B rollout envs and on a minibatch of
+        other size holds two handles over one set of parameters."""
         self.arch, self.out_kind = arch, out_kind
+        self.head_layers, self.adam_eps = int(head_layers), float(adam_eps)
         self.N, self.B, self.H, self.O = int(n_agents), int(n_envs), int(hidden), int(n_out)
         self.L = int(history_len) if arch == L.NET_GRU else 1
         self.in_dim = [int(i) for i in in_dim]
@@ -46,13 +54,13 @@ class NetSet:
                           history_len=self.L, in_rows=self.in_rows,
                           in_dim=a_dim.ctypes.data_as(C.POINTER(C.c_int32)),
                           in_off=a_off.ctypes.data_as(C.POINTER(C.c_int32)), scratch_bytes=int(scratch_bytes),
-                          inputs_bf16_exact=int(bool(inputs_bf16_exact)), reserved0=0)
+                          inputs_bf16_exact=int(bool(inputs_bf16_exact)), head_layers=self.head_layers)
         h = C.c_void_p()
         with torch.cuda.device(self.device):
             L.check(self._lib.d2d_net_create(C.byref(cfg), C.byref(h)))
         self._h = h
         self.stride = int(self._lib.d2d_net_param_stride(h))
-        self.keys = GRU_KEYS if arch == L.NET_GRU else MLP_KEYS
+        self.keys = (GRU_Q_KEYS if self.head_layers == 2 else GRU_KEYS) if arch == L.NET_GRU else MLP_KEYS
         self._layout = []
         for g in range(self.N):
             per = []
@@ -61,12 +69,20 @@ class NetSet:
                 L.check(self._lib.d2d_net_tensor(h, g, i, C.byref(off), C.byref(rows), C.byref(cols)))
                 per.append((off.value, rows.value, cols.value))
             self._layout.append(per)
+        self._sqnorm = torch.zeros(self.N, dtype=torch.float64, device=self.device)
+        self._owner = share_with
+        if share_with is not None:
+            if (share_with.arch, share_with.N, share_with.stride, share_with.keys) != \
+                    (self.arch, self.N, self.stride, self.keys):
+                raise ValueError("share_with: the two net sets differ in architecture")
+            self.params, self.grads = share_with.params, share_with.grads
+            self.adam_m, self.adam_v = share_with.adam_m, share_with.adam_v
+            return
         self.params = torch.zeros((self.N, self.stride), dtype=torch.float32, device=self.device)
         self.grads = torch.zeros_like(self.params)
         self.adam_m = torch.zeros_like(self.params)
         self.adam_v = torch.zeros_like(self.params)
         self.adam_step = 0
-        self._sqnorm = torch.zeros(self.N, dtype=torch.float64, device=self.device)
         self.reset_parameters(generator)
 
     def __del__(self):
@@ -92,8 +108,13 @@ class NetSet:
                     sd[name] = (torch.rand(*shape, generator=generator) * 2 - 1) * k
                 sd["layers.0.weight"] = _orthogonal(self.H, self.H, 3, generator)
                 sd["layers.0.bias"] = torch.zeros(self.H)
-                sd["layers.2.weight"] = _orthogonal(self.O, self.H, 3, generator)
-                sd["layers.2.bias"] = torch.zeros(self.O)
+                last = "layers.2"
+                if self.head_layers == 2:          # irdqn.py:66-72: same init law on every Linear
+                    sd["layers.2.weight"] = _orthogonal(self.H, self.H, 3, generator)
+                    sd["layers.2.bias"] = torch.zeros(self.H)
+                    last = "layers.4"
+                sd[last + ".weight"] = _orthogonal(self.O, self.H, 3, generator)
+                sd[last + ".bias"] = torch.zeros(self.O)
             else:
                 sd["linear1.weight"] = _orthogonal(self.H, self.in_dim[g], 2, generator)
                 sd["linear1.bias"] = torch.zeros(self.H)
@@ -125,13 +146,15 @@ class NetSet:
         return v.reshape(rows, cols) if "weight" in name else v
 
     # ---------------------------------------------------------------- kernels
-    def forward(self, x, x_lead, t0, t1, padded, out=None):
-        """Pre-activation outputs [t1 - t0, N, O, B] of time blocks [t0, t1) of the env-minor input matrix x."""
+    def forward(self, x, x_lead, t0, t1, padded, out=None, params=None):
+        """Pre-activation outputs [t1 - t0, N, O, B] of time blocks [t0, t1) of the env-minor input matrix x.
+        params: another [N, stride] parameter buffer of the same layout (a target network)."""
         if out is None:
             out = torch.empty((t1 - t0, self.N, self.O, self.B), dtype=torch.float32, device=self.device)
         with torch.cuda.device(self.device):
-            L.check(self._lib.d2d_net_forward(self._h, L.ptr(self.params), L.ptr(x), int(x_lead), int(t0), int(t1),
-                                              int(padded), L.ptr(out), L.current_stream()))
+            L.check(self._lib.d2d_net_forward(self._h, L.ptr(self.params if params is None else params), L.ptr(x),
+                                              int(x_lead), int(t0), int(t1), int(padded), L.ptr(out),
+                                              L.current_stream()))
         return out
 
     def rollout_step(self, x, x_lead, t, out=None):
@@ -183,13 +206,24 @@ class NetSet:
                 int(per_agent), float(inv_rows), L.ptr(self.grads), L.ptr(loss_sum), L.ptr(value_out),
                 L.current_stream()))
 
+    def q_grad(self, x, x_lead, t0, t1, actions, target, loss_kind, inv_rows, loss_sum, q_out=None):
+        """DQN.train_step up to the optimiser (d2d_q_grad): gradients of loss(Q[action], target) accumulated into
+        ``grads``, the loss terms summed into ``loss_sum`` (f64 [N])."""
+        with torch.cuda.device(self.device):
+            L.check(self._lib.d2d_q_grad(self._h, L.ptr(self.params), L.ptr(x), int(x_lead), int(t0), int(t1),
+                                         L.ptr(actions), L.ptr(target), int(loss_kind), float(inv_rows),
+                                         L.ptr(self.grads), L.ptr(loss_sum), L.ptr(q_out), L.current_stream()))
+
     def adam(self, max_norm=0.0):
         """clip_grad_norm_(max_norm) per agent (if > 0) followed by one torch.optim.Adam step."""
+        if self._owner is not None:
+            raise RuntimeError("this handle aliases another net set's parameters: step the owner")
         self.adam_step += 1
         with torch.cuda.device(self.device):
-            L.check(self._lib.d2d_adam_step(L.ptr(self.params), L.ptr(self.adam_m), L.ptr(self.adam_v),
-                                            L.ptr(self.grads), self.N, self.stride, self.lr, self.adam_step,
-                                            float(max_norm), L.ptr(self._sqnorm), L.current_stream()))
+            L.check(self._lib.d2d_adam_step_eps(L.ptr(self.params), L.ptr(self.adam_m), L.ptr(self.adam_v),
+                                                L.ptr(self.grads), self.N, self.stride, self.lr, self.adam_eps,
+                                                self.adam_step, float(max_norm), L.ptr(self._sqnorm),
+                                                L.current_stream()))
 
 
 def policy_head(logits, n_agents, n_envs, n_out, out_kind, dist_kind, act_mode, actions, logp, entropy=None,
@@ -201,6 +235,28 @@ def policy_head(logits, n_agents, n_envs, n_out, out_kind, dist_kind, act_mode, 
                                         L.ptr(actions), L.ptr(logp), L.ptr(entropy), L.ptr(probs),
                                         int(seed) & 0xFFFFFFFFFFFFFFFF, int(env_offset), int(t_abs0),
                                         L.current_stream()))
+
+
+def q_select(q, n_agents, n_envs, n_out, act_mode, epsilon, ready, n_random, action_idx, action_mask, seed=0,
+             env_offset=0, t_abs=0):
+    """DQN.act / DQN.predict for all agents and envs (d2d_q_select): Q-values [1, N, O, B] -> channel index u8 [N, B]
+    and the one-hot channel bitmask the env kernels take."""
+    mask_bytes = 0 if action_mask is None else action_mask.element_size()
+    with torch.cuda.device(action_idx.device):
+        L.check(L.lib().d2d_q_select(n_agents, n_envs, n_out, L.ptr(q), int(act_mode), float(epsilon), int(bool(ready)),
+                                     int(n_random), L.ptr(action_idx), L.ptr(action_mask), mask_bytes,
+                                     int(seed) & 0xFFFFFFFFFFFFFFFF, int(env_offset), int(t_abs), L.current_stream()))
+
+
+def q_td_target(q_next, reward, done, gamma, out=None):
+    """rewards + (1 - dones) * gamma * max_a Q_target(s') (irdqn.py:137-139): [1, N, O, B] -> f32 [N, B]."""
+    _, N, O, B = q_next.shape
+    if out is None:
+        out = torch.empty((N, B), dtype=torch.float32, device=q_next.device)
+    with torch.cuda.device(q_next.device):
+        L.check(L.lib().d2d_q_td_target(N, B, O, L.ptr(q_next), L.ptr(reward), L.ptr(done), float(gamma), L.ptr(out),
+                                        L.current_stream()))
+    return out
 
 
 def action_dtype(dist_kind, n_out):

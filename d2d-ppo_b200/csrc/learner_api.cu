@@ -7,6 +7,8 @@
 //   critic MSE step                         d2d_ppo.py:440-446, ippo.py:208-215                    -> d2d_value_grad
 //   compute_gae / discount_rewards          d2d_ppo.py:100-124                                     -> d2d_returns_scan
 //   clip_grad_norm_ + Adam                  d2d_ppo.py:211-212,445-446                             -> d2d_adam_step
+//   DQN.act / predict, train_step, replay   algorithms/irdqn.py:24-42,133-166                      -> d2d_q_select,
+//                                                                    d2d_q_td_target, d2d_q_grad, d2d_replay_gather
 //
 // A net set evaluates N independent per-agent networks with grid.y = agent.  Time blocks are processed in
 // chunks sized to the activation-scratch budget; the GRU window is unrolled step by step over the chunk with
@@ -23,6 +25,7 @@
 #include "dense_tc.cuh"
 #include "head_fused.cuh"
 #include "learner_pointwise.cuh"
+#include "dqn_pointwise.cuh"
 
 using namespace d2d;
 
@@ -34,6 +37,8 @@ struct d2d_net {
   long long stride;  // floats per agent block
   // per-agent tensor offsets inside the block
   std::vector<int> o_wih, o_whh, o_bih, o_bhh, o_w1, o_b1, o_w2, o_b2;
+  int head2 = 0;              // 1: the Q-network head of algorithms/irdqn.py:63-69 (Linear-ReLU-Linear-ReLU-Linear)
+  std::vector<int> o_w1b, o_b1b;   // its second hidden layer, layers.2 [H, H]; the output layer is then layers.4
   long long scratch_bytes;
   float* scratch = nullptr;
   long long scratch_cap = 0;  // floats
@@ -367,7 +372,7 @@ static void launch_head_fused_t(const HeadFusedArgs& a, int N, int tiles, cudaSt
 }
 
 static bool head_fused_eligible(const d2d_net* n) {
-  return !switched_off(kSwFusedHead) && n->arch == D2D_NET_GRU && (n->H == 32 || n->H == 64) && n->O <= 16;
+  return !switched_off(kSwFusedHead) && n->arch == D2D_NET_GRU && (n->H == 32 || n->H == 64) && n->O <= 16 && !n->head2;
 }
 
 static int launch_head_fused(const d2d_net* n, const float* params, const View& h, float* y1, const View& out, int t0,
@@ -450,13 +455,14 @@ static int launch_gate(const GateArgs& a, int N, bool bwd, cudaStream_t s) {
 // ------------------------------------------------------------------------------------------------
 struct Chunk {
   int Tc, halo;
-  float *gi, *gh, *acts, *hs, *y1, *logits, *dl, *dy1, *dh0, *dh1, *dgi;
+  float *gi, *gh, *acts, *hs, *y1, *y2, *logits, *dl, *dy1, *dy2, *dh0, *dh1, *dgi;
 };
 
 static long long floats_per_t(const d2d_net* n, bool train) {
   const long long NB = (long long)n->N * n->B;
   const long long H = n->H, O = n->O, L = n->arch == D2D_NET_GRU ? n->L : 0;
   long long f = H + O;                                // y1, logits
+  if (n->head2) f += train ? 2 * H : H;               // y2 (+ dy2)
   if (n->arch == D2D_NET_GRU) f += 3 * H + 3 * H;     // gi, gh
   // hs of every step; the 4H activations per step only for the BPTT kernels that do not recompute them
   if (n->arch == D2D_NET_GRU) f += train ? L * H + (gru_bptt_recompute_eligible(n) ? 0 : 4 * L * H) : 2 * H;
@@ -495,10 +501,13 @@ static int plan_chunk(d2d_net* n, bool train, int n_t, Chunk& c) {
     }
   }
   c.y1 = take((long long)Tc * H * NB);
+  c.y2 = c.dy2 = nullptr;
+  if (n->head2) c.y2 = take((long long)Tc * H * NB);
   c.logits = take((long long)Tc * O * NB);
   if (train) {
     c.dl = take((long long)Tc * O * NB);
     c.dy1 = take((long long)Tc * H * NB);
+    if (n->head2) c.dy2 = take((long long)Tc * H * NB);
     if (n->arch == D2D_NET_GRU) {
       c.dh0 = take((long long)Tc * H * NB);
       c.dh1 = take((long long)Tc * H * NB);
@@ -512,6 +521,39 @@ static int plan_chunk(d2d_net* n, bool train, int n_t, Chunk& c) {
 static float* hs_ptr(const d2d_net* n, const Chunk& c, bool train, int s) {
   const long long per = (long long)c.Tc * n->H * n->N * n->B;
   return c.hs + per * (train ? s : (s & 1));
+}
+
+// network head on the CUDA-core dense kernels: y1 = relu(W1 last + b1) [, y2 = relu(W1b y1 + b1b)], out = W2 y + b2
+static int head_dense(const d2d_net* n, const float* params, const View& last, const View& y1, float* y2p,
+                      const View& lg, int t0, int t1, cudaStream_t s) {
+  const int H = n->H, O = n->O;
+  const long long NB = (long long)n->N * n->B;
+  Wt w1{&n->o_w1, &n->o_b1, nullptr, H, H};
+  Wt w2{&n->o_w2, &n->o_b2, nullptr, H, O};
+  if (n->arch == D2D_NET_MLP) w1.in_dim = &n->in_dim;
+  int rc;
+  {
+    DenseArgs a;
+    memset(&a, 0, sizeof(a));
+    fill_dense_w(n, a, params, w1, 0);
+    a.x = last, a.y = y1, a.epilogue = kEpiRelu, a.t0 = t0, a.t1 = t1;
+    if ((rc = launch_dense(n, a, n->arch == D2D_NET_MLP ? n->max_in : H, s))) return rc;
+  }
+  View top = y1;
+  if (n->head2) {
+    Wt w1b{&n->o_w1b, &n->o_b1b, nullptr, H, H};
+    top = make_view(y2p, H * NB, -t0, n->N, H, n->B);
+    DenseArgs a;
+    memset(&a, 0, sizeof(a));
+    fill_dense_w(n, a, params, w1b, 0);
+    a.x = y1, a.y = top, a.epilogue = kEpiRelu, a.t0 = t0, a.t1 = t1;
+    if ((rc = launch_dense(n, a, H, s))) return rc;
+  }
+  DenseArgs a;
+  memset(&a, 0, sizeof(a));
+  fill_dense_w(n, a, params, w2, 0);
+  a.x = top, a.y = lg, a.epilogue = kEpiNone, a.t0 = t0, a.t1 = t1;
+  return launch_dense(n, a, H, s);
 }
 
 // forward of chunk [c0, c1) (c1 - c0 <= Tc): fills c.logits (local time index t - c0)
@@ -599,21 +641,7 @@ static int forward_chunk(d2d_net* n, const float* params, const float* x, int x_
     last = make_view(hs_ptr(n, c, train, L - 1), H * NB, -c0, N, H, B);
   }
   if (head_fused_eligible(n)) return launch_head_fused(n, params, last, train ? c.y1 : nullptr, lg, c0, c1, s);
-  {
-    DenseArgs a;
-    memset(&a, 0, sizeof(a));
-    fill_dense_w(n, a, params, w1, 0);
-    a.x = last, a.y = y1, a.epilogue = kEpiRelu, a.t0 = c0, a.t1 = c1;
-    if ((rc = launch_dense(n, a, n->arch == D2D_NET_MLP ? n->max_in : H, s))) return rc;
-  }
-  {
-    DenseArgs a;
-    memset(&a, 0, sizeof(a));
-    fill_dense_w(n, a, params, w2, 0);
-    a.x = y1, a.y = lg, a.epilogue = kEpiNone, a.t0 = c0, a.t1 = c1;
-    if ((rc = launch_dense(n, a, H, s))) return rc;
-  }
-  return D2D_OK;
+  return head_dense(n, params, last, y1, c.y2, lg, c0, c1, s);
 }
 
 // backward of chunk [c0, c1) given c.dl = d(loss)/d(pre-activation outputs); accumulates into grads
@@ -631,9 +659,30 @@ static int backward_chunk(d2d_net* n, const float* params, const float* x, int x
   Wt w1{&n->o_w1, &n->o_b1, nullptr, H, H};
   Wt w2{&n->o_w2, &n->o_b2, nullptr, H, O};
   int rc;
-  // head: dW2 = dl^T y1 ; dy1 = (dl W2) * relu'(y1)
-  if ((rc = launch_wgrad(n, dl, y1, w2, false, grads, c0, c1, s))) return rc;
-  {
+  if (n->head2) {
+    // Q-network head: dW2 = dl^T y2 ; dy2 = (dl W2) * relu'(y2) ; dW1b = dy2^T y1 ; dy1 = (dy2 W1b) * relu'(y1)
+    const View y2 = make_view(c.y2, H * NB, -c0, N, H, B);
+    const View dy2 = make_view(c.dy2, H * NB, -c0, N, H, B);
+    Wt w1b{&n->o_w1b, &n->o_b1b, nullptr, H, H};
+    if ((rc = launch_wgrad(n, dl, y2, w2, false, grads, c0, c1, s))) return rc;
+    {
+      DenseArgs a;
+      memset(&a, 0, sizeof(a));
+      fill_dense_w(n, a, params, w2, 1);
+      a.out_dim = H;
+      a.x = dl, a.y = dy2, a.aux = y2, a.epilogue = kEpiReluBwd, a.t0 = c0, a.t1 = c1;
+      if ((rc = launch_dense(n, a, O, s))) return rc;
+    }
+    if ((rc = launch_wgrad(n, dy2, y1, w1b, false, grads, c0, c1, s))) return rc;
+    DenseArgs a;
+    memset(&a, 0, sizeof(a));
+    fill_dense_w(n, a, params, w1b, 1);
+    a.out_dim = H;
+    a.x = dy2, a.y = dy1, a.aux = y1, a.epilogue = kEpiReluBwd, a.t0 = c0, a.t1 = c1;
+    if ((rc = launch_dense(n, a, H, s))) return rc;
+  } else {
+    // head: dW2 = dl^T y1 ; dy1 = (dl W2) * relu'(y1)
+    if ((rc = launch_wgrad(n, dl, y1, w2, false, grads, c0, c1, s))) return rc;
     DenseArgs a;
     memset(&a, 0, sizeof(a));
     fill_dense_w(n, a, params, w2, 1);
@@ -776,12 +825,15 @@ extern "C" int d2d_net_create(const d2d_net_config* cfg, d2d_net** out) {
   D2D_REQUIRE(cfg->arch == D2D_NET_MLP || (cfg->history_len >= 1 && cfg->history_len <= 64),
               "d2d_net_create: history_len out of range");
   D2D_REQUIRE(cfg->in_dim && cfg->in_off, "d2d_net_create: null in_dim / in_off");
+  D2D_REQUIRE(cfg->head_layers >= 0 && cfg->head_layers <= 2 && (cfg->head_layers != 2 || cfg->arch == D2D_NET_GRU),
+              "d2d_net_create: head_layers must be 0 / 1 (PPO nets) or 2 (GRU Q-network)");
   d2d_net* n = new (std::nothrow) d2d_net();
   D2D_REQUIRE(n, "d2d_net_create: out of host memory");
   n->arch = cfg->arch, n->out_kind = cfg->out_kind, n->N = cfg->n_agents, n->B = cfg->n_envs, n->H = cfg->hidden;
   n->O = cfg->n_out, n->L = cfg->arch == D2D_NET_GRU ? cfg->history_len : 1, n->in_rows = cfg->in_rows;
   n->scratch_bytes = cfg->scratch_bytes > 0 ? cfg->scratch_bytes : (2ll << 30);
   n->x_exact = cfg->inputs_bf16_exact != 0;
+  n->head2 = cfg->head_layers == 2;
   n->max_in = 0, n->stride = 0;
   const int H = n->H, O = n->O;
   for (int g = 0; g < n->N; ++g) {
@@ -805,6 +857,10 @@ extern "C" int d2d_net_create(const d2d_net_config* cfg, d2d_net** out) {
       n->o_w1.push_back(o), o += H * I;
     }
     n->o_b1.push_back(o), o += H;
+    if (n->head2) {
+      n->o_w1b.push_back(o), o += H * H;
+      n->o_b1b.push_back(o), o += H;
+    }
     n->o_w2.push_back(o), o += O * H;
     n->o_b2.push_back(o), o += O;
     n->stride = std::max<long long>(n->stride, o);
@@ -828,11 +884,21 @@ extern "C" int d2d_net_destroy(d2d_net* n) {
   return D2D_OK;
 }
 extern "C" int64_t d2d_net_param_stride(const d2d_net* n) { return n ? n->stride : D2D_ERR_INVALID; }
-extern "C" int d2d_net_num_tensors(const d2d_net* n) { return n ? (n->arch == D2D_NET_GRU ? 8 : 4) : D2D_ERR_INVALID; }
+extern "C" int d2d_net_num_tensors(const d2d_net* n) {
+  return n ? (n->arch == D2D_NET_GRU ? (n->head2 ? 10 : 8) : 4) : D2D_ERR_INVALID;
+}
 extern "C" int d2d_net_tensor(const d2d_net* n, int g, int index, int64_t* offset, int32_t* rows, int32_t* cols) {
   D2D_REQUIRE(n && offset && rows && cols && g >= 0 && g < n->N, "d2d_net_tensor: bad argument");
   const int H = n->H, O = n->O, I = n->in_dim[g];
-  if (n->arch == D2D_NET_GRU) {
+  if (n->arch == D2D_NET_GRU && n->head2) {
+    // irdqn.py:58-72 state_dict order: the four GRU tensors, layers.0, layers.2 (hidden), layers.4 (output)
+    const int off[10] = {n->o_wih[g], n->o_whh[g], n->o_bih[g], n->o_bhh[g], n->o_w1[g],
+                         n->o_b1[g],  n->o_w1b[g], n->o_b1b[g], n->o_w2[g],  n->o_b2[g]};
+    const int r[10] = {3 * H, 3 * H, 3 * H, 3 * H, H, H, H, H, O, O};
+    const int c[10] = {I, H, 1, 1, H, 1, H, 1, H, 1};
+    D2D_REQUIRE(index >= 0 && index < 10, "d2d_net_tensor: index out of range");
+    *offset = off[index], *rows = r[index], *cols = c[index];
+  } else if (n->arch == D2D_NET_GRU) {
     // state_dict order: weight_ih, weight_hh, bias_ih, bias_hh, layers.0.weight, layers.0.bias, layers.2.weight, .bias
     const int off[8] = {n->o_wih[g], n->o_whh[g], n->o_bih[g], n->o_bhh[g], n->o_w1[g], n->o_b1[g], n->o_w2[g], n->o_b2[g]};
     const int r[8] = {3 * H, 3 * H, 3 * H, 3 * H, H, H, O, O};
@@ -947,24 +1013,7 @@ extern "C" int d2d_net_rollout_step(d2d_net* n, const float* params, const float
   if (head_fused_eligible(n))
     return launch_head_fused(n, params, make_view(hs_ptr(n, c, false, L - 1), H * NB, -t, N, H, B), nullptr, lg, t,
                              t + 1, s);
-  Wt w1{&n->o_w1, &n->o_b1, nullptr, H, H};
-  Wt w2{&n->o_w2, &n->o_b2, nullptr, H, O};
-  {
-    DenseArgs a;
-    memset(&a, 0, sizeof(a));
-    fill_dense_w(n, a, params, w1, 0);
-    a.x = make_view(hs_ptr(n, c, false, L - 1), H * NB, -t, N, H, B), a.y = y1, a.epilogue = kEpiRelu;
-    a.t0 = t, a.t1 = t + 1;
-    if ((rc = launch_dense(n, a, H, s))) return rc;
-  }
-  {
-    DenseArgs a;
-    memset(&a, 0, sizeof(a));
-    fill_dense_w(n, a, params, w2, 0);
-    a.x = y1, a.y = lg, a.epilogue = kEpiNone, a.t0 = t, a.t1 = t + 1;
-    if ((rc = launch_dense(n, a, H, s))) return rc;
-  }
-  return D2D_OK;
+  return head_dense(n, params, make_view(hs_ptr(n, c, false, L - 1), H * NB, -t, N, H, B), y1, c.y2, lg, t, t + 1, s);
 }
 
 static void fill_head(HeadArgs& h, int N, int B, int O, int out_kind, int dist_kind) {
@@ -1097,6 +1146,11 @@ extern "C" int d2d_value_grad(d2d_net* n, const float* params, const float* x, i
 
 extern "C" int d2d_adam_step(float* params, float* m, float* v, const float* grads, int N, int64_t per_agent,
                              float lr, int step, float max_norm, double* sqnorm, void* stream) {
+  return d2d_adam_step_eps(params, m, v, grads, N, per_agent, lr, 1e-8f, step, max_norm, sqnorm, stream);
+}
+
+extern "C" int d2d_adam_step_eps(float* params, float* m, float* v, const float* grads, int N, int64_t per_agent,
+                                 float lr, float eps, int step, float max_norm, double* sqnorm, void* stream) {
   D2D_REQUIRE(params && m && v && grads && N >= 1 && per_agent >= 1 && step >= 1, "d2d_adam_step: bad argument");
   D2D_REQUIRE(max_norm <= 0.f || sqnorm, "d2d_adam_step: clipping needs the sqnorm scratch buffer");
   cudaStream_t s = as_stream(stream);
@@ -1108,10 +1162,91 @@ extern "C" int d2d_adam_step(float* params, float* m, float* v, const float* gra
   }
   AdamArgs a;
   a.p = params, a.m = m, a.v = v, a.g = grads, a.sqnorm = max_norm > 0.f ? sqnorm : nullptr;
-  a.per_agent = per_agent, a.lr = lr, a.beta1 = 0.9f, a.beta2 = 0.999f, a.eps = 1e-8f, a.max_norm = max_norm;
+  a.per_agent = per_agent, a.lr = lr, a.beta1 = 0.9f, a.beta2 = 0.999f, a.eps = eps, a.max_norm = max_norm;
   a.bc1 = (float)(1.0 - pow(0.9, (double)step));
   a.bc2 = (float)(1.0 - pow(0.999, (double)step));
   adam_kernel<<<dim3(gx, N), 256, 0, s>>>(a);
+  D2D_LAUNCHED();
+  return D2D_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// independent recurrent DQN (algorithms/irdqn.py)
+// ------------------------------------------------------------------------------------------------
+extern "C" int d2d_q_select(int N, int B, int O, const float* q, int act_mode, float epsilon, int training_ready,
+                            int n_random, uint8_t* action_idx, void* action_mask, int mask_bytes, uint64_t seed,
+                            uint64_t env_offset, int t_abs, void* stream) {
+  D2D_REQUIRE(action_idx && (q || act_mode == D2D_ACT_GIVEN), "d2d_q_select: null argument");
+  D2D_REQUIRE(N >= 1 && N <= D2D_MAX_AGENTS && B >= 1 && O >= 1 && O <= kMaxOut, "d2d_q_select: bad shape");
+  D2D_REQUIRE(act_mode >= 0 && act_mode <= 2, "d2d_q_select: bad act_mode");
+  D2D_REQUIRE(n_random >= 1 && n_random <= O, "d2d_q_select: n_random %d not in 1..n_out", n_random);
+  D2D_REQUIRE(!action_mask || ((mask_bytes == 1 || mask_bytes == 2 || mask_bytes == 4) && O <= 8 * mask_bytes),
+              "d2d_q_select: mask_bytes %d cannot hold %d channels", mask_bytes, O);
+  QSelectArgs a;
+  memset(&a, 0, sizeof(a));
+  a.q = q, a.action = action_idx, a.mask = action_mask, a.mask_bytes = mask_bytes, a.N = N, a.B = B, a.O = O;
+  a.act_mode = act_mode, a.epsilon = epsilon, a.ready = training_ready != 0, a.n_random = n_random;
+  a.k0 = (uint32_t)(seed & 0xFFFFFFFFull), a.k1 = (uint32_t)(seed >> 32), a.env_offset = (uint32_t)env_offset;
+  a.t_abs = t_abs;
+  q_select_kernel<<<grid_for((long long)N * B, 128), 128, 0, as_stream(stream)>>>(a);
+  D2D_LAUNCHED();
+  return D2D_OK;
+}
+
+extern "C" int d2d_q_td_target(int N, int B, int O, const float* q_next, const int32_t* reward, const uint8_t* done,
+                               float gamma, float* target, void* stream) {
+  D2D_REQUIRE(q_next && reward && done && target, "d2d_q_td_target: null argument");
+  D2D_REQUIRE(N >= 1 && N <= D2D_MAX_AGENTS && B >= 1 && O >= 1 && O <= kMaxOut, "d2d_q_td_target: bad shape");
+  q_td_target_kernel<<<grid_for((long long)N * B, 128), 128, 0, as_stream(stream)>>>(q_next, reward, done, gamma,
+                                                                                       target, N, B, O);
+  D2D_LAUNCHED();
+  return D2D_OK;
+}
+
+extern "C" int d2d_q_grad(d2d_net* n, const float* params, const float* x, int x_lead, int t0, int t1,
+                          const uint8_t* actions, const float* target, int loss_kind, float inv_rows, float* grads,
+                          double* loss_sum, float* q_out, void* stream) {
+  D2D_REQUIRE(n && params && x && actions && target && grads && loss_sum, "d2d_q_grad: null argument");
+  D2D_REQUIRE(n->out_kind == D2D_OUT_IDENTITY, "d2d_q_grad: a Q-network has identity outputs");
+  D2D_REQUIRE(loss_kind == D2D_QLOSS_HUBER || loss_kind == D2D_QLOSS_MSE, "d2d_q_grad: unknown loss_kind");
+  int rc = check_range(n, x_lead, t0, t1, "d2d_q_grad");
+  if (rc) return rc;
+  cudaStream_t s = as_stream(stream);
+  Chunk c;
+  if ((rc = plan_chunk(n, true, t1 - t0, c))) return rc;
+  const long long NB = (long long)n->N * n->B;
+  for (int c0 = t0; c0 < t1; c0 += c.Tc) {
+    const int c1 = std::min(t1, c0 + c.Tc);
+    if ((rc = forward_chunk(n, params, x, x_lead, c0, c1, 1, true, c, s))) return rc;
+    QLossArgs q;
+    memset(&q, 0, sizeof(q));
+    q.q = make_view(c.logits, n->O * NB, -c0, n->N, n->O, n->B);
+    q.dq = make_view(c.dl, n->O * NB, -c0, n->N, n->O, n->B);
+    q.actions = actions, q.target = target, q.q_out = q_out, q.O = n->O, q.B = n->B, q.t0 = c0, q.t1 = c1;
+    q.loss_kind = loss_kind, q.inv_rows = inv_rows, q.loss_sum = loss_sum;
+    const long long rows = (long long)(c1 - c0) * n->B;
+    q_loss_grad_kernel<<<dim3(grid_for(rows, 128), n->N), 128, 0, s>>>(q);
+    D2D_LAUNCHED();
+    if ((rc = backward_chunk(n, params, x, x_lead, c0, c1, c, grads, inv_rows, s))) return rc;
+  }
+  return D2D_OK;
+}
+
+extern "C" int d2d_replay_gather(const float* obs_ring, const uint8_t* act_ring, const int32_t* rew_ring,
+                                 const int32_t* start, const int32_t* env_col, int ep0, int n_ep_slots, int T,
+                                 int chunk, int rows, int N, int B, int mb, float* xs, float* xn, uint8_t* act,
+                                 int32_t* rew, uint8_t* done, void* stream) {
+  D2D_REQUIRE(obs_ring && act_ring && rew_ring && start && env_col && xs && xn && act && rew && done,
+              "d2d_replay_gather: null argument");
+  D2D_REQUIRE(n_ep_slots >= 1 && ep0 >= 0 && ep0 < n_ep_slots && T >= 1 && chunk >= 1 && rows >= 1 && N >= 1 &&
+                  N <= D2D_MAX_AGENTS && B >= 1 && mb >= 1,
+              "d2d_replay_gather: bad shape");
+  GatherArgs a;
+  memset(&a, 0, sizeof(a));
+  a.obs_ring = obs_ring, a.act_ring = act_ring, a.rew_ring = rew_ring, a.start = start, a.env_col = env_col;
+  a.ep0 = ep0, a.slots = n_ep_slots, a.T = T, a.chunk = chunk, a.rows = rows, a.N = N, a.B = B, a.mb = mb;
+  a.xs = xs, a.xn = xn, a.act = act, a.rew = rew, a.done = done;
+  replay_gather_kernel<<<grid_for((long long)chunk * rows * mb, 256), 256, 0, as_stream(stream)>>>(a);
   D2D_LAUNCHED();
   return D2D_OK;
 }

@@ -213,6 +213,8 @@ int d2d_env_scores(const d2d_env* env, double* urllc, double* jains, double* cha
  *   GRU ("RNN", d2d_ppo.py:24-59):  lstm.weight_ih_l0 [3H, I], lstm.weight_hh_l0 [3H, H], lstm.bias_ih_l0 [3H],
  *                                   lstm.bias_hh_l0 [3H], layers.0.weight [H, H], layers.0.bias [H],
  *                                   layers.2.weight [O, H], layers.2.bias [O]
+ *   GRU Q-network (irdqn.py:58-72, head_layers = 2): the same with layers.2 [H, H] and layers.4.weight [O, H],
+ *                                   layers.4.bias [O]
  *   MLP ("Policy"/"Value", :62-98): linear1.weight [H, I], linear1.bias [H], linear2.weight [O, H], linear2.bias [O]
  * ------------------------------------------------------------------------------------------ */
 #define D2D_NET_MLP 0
@@ -241,14 +243,15 @@ typedef struct d2d_net_config {
   int32_t inputs_bf16_exact; /* 1: every input value is exactly representable in bf16 (the integer-valued
                                 observations of CombinatorialEnv / D2DEnv): allows the tcgen05 GRU-window
                                 kernel, whose input projection uses a single bf16 plane for x            */
-  int32_t reserved0;
+  int32_t head_layers;     /* hidden Linear+ReLU layers behind the GRU: 0 or 1 = the PPO nets (layers.0, layers.2);
+                              2 = the Q-network of algorithms/irdqn.py:58-72 (layers.0, layers.2, layers.4; GRU only) */
 } d2d_net_config;
 
 typedef struct d2d_net d2d_net;
 int d2d_net_create(const d2d_net_config* cfg, d2d_net** out);
 int d2d_net_destroy(d2d_net* net);
 int64_t d2d_net_param_stride(const d2d_net* net);       /* floats per agent block                        */
-int d2d_net_num_tensors(const d2d_net* net);            /* 8 (GRU) or 4 (MLP)                            */
+int d2d_net_num_tensors(const d2d_net* net);            /* 8 (GRU), 10 (GRU Q-network) or 4 (MLP)        */
 /* state_dict tensor `index` of agent `agent`: offset inside the agent's block, rows, cols (cols = 1: vector) */
 int d2d_net_tensor(const d2d_net* net, int agent, int index, int64_t* offset, int32_t* rows, int32_t* cols);
 
@@ -373,6 +376,57 @@ int d2d_returns_emit(const int32_t* reward, const float* value, float* adv_out, 
  * discount_rewards (cast to f32 first, normalise in f32).  mean/std f64 device [n_cols], do_norm i32 device. */
 int d2d_normalize(const double* raw, float* out, const double* mean, const double* std, const int32_t* do_norm,
                   int fp32_math, int T, int n_envs, int n_cols, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Independent recurrent DQN (algorithms/irdqn.py), SURVEY.md section 8(f)4.  The Q-networks are net sets with
+ * head_layers = 2 and D2D_OUT_IDENTITY; forward / rollout go through d2d_net_forward / d2d_net_rollout_step.
+ * ------------------------------------------------------------------------------------------ */
+#define D2D_QLOSS_HUBER 0   /* F.smooth_l1_loss (beta 1), irdqn.py:120 */
+#define D2D_QLOSS_MSE 1     /* F.mse_loss                             */
+
+/* torch.optim.Adam with a caller-chosen eps (irdqn.py:130 passes adam_epsilon); otherwise d2d_adam_step. */
+int d2d_adam_step_eps(float* params, float* m, float* v, const float* grads, int n_agents, int64_t per_agent,
+                      float lr, float eps, int step, float max_norm, double* sqnorm, void* stream);
+
+/* DQN.act / DQN.predict for all N agents and B envs (irdqn.py:150-166, called at :244-253 and :323-328).
+ *   q          f32 [N][O][B] Q-values of the current windows
+ *   act_mode   D2D_ACT_SAMPLE: greedy iff training_ready and uniform >= epsilon, else a uniform draw from
+ *              {0, .., n_random - 1} (the reference draws np.random.randint(0, 2): n_random = 2, whatever O is);
+ *              D2D_ACT_GREEDY: argmax, first maximum (predict); D2D_ACT_GIVEN: action_idx is read, not written
+ *   action_idx u8 [N][B];  action_mask: one-hot channel bitmask 1 << idx, [N][B] of mask_bytes (1/2/4) bytes each,
+ *              the action_binary rows of irdqn.py:249-250 in the device action layout (may be NULL)
+ *   draws: Philox4x32-10 keyed (seed; env_offset + b, t_abs, agent, purpose = policy)                        */
+int d2d_q_select(int n_agents, int n_envs, int n_out, const float* q, int act_mode, float epsilon,
+                 int training_ready, int n_random, uint8_t* action_idx, void* action_mask, int mask_bytes,
+                 uint64_t seed, uint64_t env_offset, int t_abs, void* stream);
+
+/* td_target = rewards + (1 - dones) * gamma * max_a Q_target(s')  (irdqn.py:136-139), fp32 in torch's op order.
+ *   q_next f32 [N][O][B];  reward i32 [B] (all agents of an env share it);  done u8 [B];  target f32 [N][B]  */
+int d2d_q_td_target(int n_agents, int n_envs, int n_out, const float* q_next, const int32_t* reward,
+                    const uint8_t* done, float gamma, float* target, void* stream);
+
+/* DQN.train_step up to the optimiser (irdqn.py:140-145) for all N agents over time blocks [t0, t1): forward on
+ * padded windows, loss(Q[action], target) with reduction 'mean' over the rows, backward.
+ *   actions u8 [T][N][B], target f32 [T][N][B] (absolute time);  inv_rows = 1 / rows of the whole batch
+ *   grads f32 [N][param_stride] ACCUMULATED;  loss_sum f64 device [N] ACCUMULATED (sum over rows of the loss
+ *   terms: the loss is loss_sum * inv_rows);  q_out f32 [T][N][B] or NULL: Q of the taken action             */
+int d2d_q_grad(d2d_net* net, const float* params, const float* x, int x_lead, int t0, int t1,
+               const uint8_t* actions, const float* target, int loss_kind, float inv_rows, float* grads,
+               double* loss_sum, float* q_out, void* stream);
+
+/* ReplayBuffer.sample_chunk (irdqn.py:24-42) on a device-resident ring.  Every env column b holds its own deque
+ * of transitions, episode-major: the ring keeps the last n_ep_slots episodes as
+ *   obs_ring f32 [n_ep_slots][T + 1][rows][B]  (state of transition t = block t, state_next = block t + 1)
+ *   act_ring u8  [n_ep_slots][T][N][B],  rew_ring i32 [n_ep_slots][T][B]
+ * and ep0 is the slot of the OLDEST stored episode (deque index 0).  Minibatch element j is the chunk of `chunk`
+ * consecutive transitions start[j] .. start[j] + chunk - 1 (deque indices, may straddle an episode end as in the
+ * reference) of env column env_col[j].  Outputs are env-minor minibatch matrices with B = mb:
+ *   xs, xn f32 [chunk][rows][mb] (states / next states of the chunk);  act u8 [N][mb], rew i32 [mb], done u8 [mb]
+ *   of the LAST transition of the chunk (irdqn.py:293-296).                                                  */
+int d2d_replay_gather(const float* obs_ring, const uint8_t* act_ring, const int32_t* rew_ring,
+                      const int32_t* start, const int32_t* env_col, int ep0, int n_ep_slots, int T, int chunk,
+                      int rows, int n_agents, int n_envs, int mb, float* xs, float* xn, uint8_t* act, int32_t* rew,
+                      uint8_t* done, void* stream);
 
 #ifdef __cplusplus
 }

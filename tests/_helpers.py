@@ -66,6 +66,14 @@ def load_ppo_case(name):
     return d
 
 
+def load_dqn_case(name):
+    z = np.load(os.path.join(GOLDEN, f"dqn_{name}.npz"), allow_pickle=False)
+    d = {k: z[k] for k in z.files}
+    for key in ("meta", "config"):
+        d[key] = json.loads(str(d[key]))
+    return d
+
+
 def params_from(d, prefix):
     """{'lstm.weight_ih_l0': tensor, ...} for keys 'prefix/...' of a loaded fixture."""
     import torch
