@@ -51,7 +51,7 @@ def parse():
     ap.add_argument("--cpu-learner-envs", type=int, default=64, help="envs of the CPU iPPO iteration baseline")
     ap.add_argument("--no-configs", action="store_true", help="skip the c1 / c2 / c4 / selection env-step sections")
     ap.add_argument("--no-learner", action="store_true", help="skip the learned-policy rollout / train SPS sections")
-    ap.add_argument("--learner-sections", default="rollout,gae,train_c3,train_c3_small,train_c2",
+    ap.add_argument("--learner-sections", default="rollout,gae,train_c3,train_c3_small,train_c2,irdqn",
                     help="comma list of the learner sections to run (development runs time one section at a time)")
     ap.add_argument("--rollout-envs", type=int, default=65536, help="envs per GPU of the learned-policy rollout (c3)")
     ap.add_argument("--train-envs", type=int, default=65536,
@@ -439,6 +439,35 @@ def bench_learner(args, dev, world, rank, barrier, max_over_ranks):
         out["train_d2dppo_c3_small"] = train_sps(c3_env(9), c3_d2dppo, Bs, N_AGENTS,
                                                  f"xp_load.py shape at {Bs} envs/GPU (round-1 bench shape)",
                                                  nets=(1, 32, 64, 6, [8]))
+    if "irdqn" in sections:
+        # independent recurrent DQN with the settings of xp_load.py:112-126 (history_len = n_agents,
+        # gamma .4, minibatch 64, lr 1e-4, Huber) on the c3 env; training from iteration 1 on, so every timed iteration
+        # is B lockstep epsilon-greedy episodes + the replay-ring copy + one minibatch update of all N Q-networks
+        from d2d_ppo_b200.algorithms.irdqn import iRDQN
+
+        def irdqn_sps(B, hidden, iters=3):
+            env = CombinatorialEnv(n_envs=B, device=dev, seed=11, env_offset=rank * B, **kw)
+            ag = iRDQN(env, history_len=N_AGENTS, replay_start_size=1, replay_buffer_size=100000, gamma=0.4,
+                       update_target_frequency=100, minibatch_size=64, learning_rate=1e-4, update_frequency=1,
+                       loss="huber", early_stopping=False, hidden_size=hidden, seed=5)
+            ag.test = lambda *a, **k: (0.0, 0.0)                 # SPS excludes the periodic evaluation episodes
+            import contextlib
+            import io
+            with contextlib.redirect_stdout(io.StringIO()):      # train() prints a line at every 100th episode
+                ag.train(2, early_stopping=False)                 # warm-up: one random and one trained iteration
+                ag.replay_start_size = 0
+                dt, launches = timed(lambda: ag.train(iters, early_stopping=False))
+            return {"metric": "iRDQN train SPS (agent-steps consumed per second of train(): B lockstep "
+                              "epsilon-greedy episodes + one minibatch update per iteration)",
+                    "value": world * iters * B * N_AGENTS * T / dt, "unit": "agent-steps/s", "envs_per_gpu": B,
+                    "config": f"xp_load.py:112-126: iRDQN GRU Q-networks (hidden {hidden}, history_len 6, minibatch 64) "
+                              f"on CombinatorialEnv setup_8_channels.p",
+                    "seconds_per_iteration": dt / iters, "gpu_launches": int(launches),
+                    "kernels": "tcgen05 GRU window + dense head" if hidden in (32, 64) else
+                               "FP32 CUDA-core kernels (hidden 100 is the reference's fixed size; the tcgen05 kernels "
+                               "take 16 / 32 / 48 / 64)"}
+        out["irdqn_c3"] = irdqn_sps(args.train_envs_small, 100)
+        out["irdqn_c3_h64"] = irdqn_sps(args.train_envs_small, 64)
     if "train_c2" not in sections:
         return out
     c2 = presets.d2d_c2_kwargs()
@@ -811,6 +840,14 @@ def run_native(args):
                               f"n_epoch=5, num_episodes=2) of algorithms/ippo.py, GRU actor + critic per agent (H 64, "
                               f"L 6) on envs/combinatorial_env.py setup_8_channels.p, torch CPU with {rr['threads']} "
                               f"threads: rollout {rr['rollout_s']:.1f} s, train {rr['total_s']:.1f} s"}
+                rq = ref_timing.irdqn_episodes(presets.combinatorial_kwargs("setup_8_channels", load=LOAD),
+                                               n_episodes=3, threads=threads)
+                line["cpu_baseline_irdqn_reference"] = {
+                    "train_value": rq["agent_steps"] / rq["total_s"], "unit": "agent-steps/s", "cores": rq["threads"],
+                    "kind": "reference",
+                    "sample": f"UNMODIFIED reference (oracle/_ref): iRDQN.train(3) of algorithms/irdqn.py with the "
+                              f"settings of xp_load.py:112-126 (replay_start_size 1) on envs/combinatorial_env.py "
+                              f"setup_8_channels.p, torch CPU with {rq['threads']} threads: {rq['total_s']:.1f} s"}
             line["cpu_baseline_learner"] = {
                 "rollout_value": r["agent_steps"] / r["rollout_s"],
                 "train_value": r["agent_steps"] / (r["rollout_s"] + r["update_s"]), "unit": "agent-steps/s",

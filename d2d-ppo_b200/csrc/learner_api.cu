@@ -104,6 +104,26 @@ static int launch_dense_tile(const d2d_net* n, const DenseArgs& a, int max_in, c
 
 static int launch_dense(const d2d_net* n, DenseArgs& a, int max_in, cudaStream_t s, int x_exact = 0) {
   a.B = n->B;
+  // more than 192 outputs (3H of the hidden sizes above 64, e.g. the reference's iRDQN networks with H = 100): the
+  // register-tiled kernel takes at most 192, so the output rows are split into equal slices that each go through it
+  // (the generic kernel below is ~5x slower: profiles/r02_n_irdqn_launch_summary.txt)
+  if (a.out_dim > 192 && n->B % 4 == 0 && (size_t)std::max(max_in, 1) * 8 * 24 * 4 <= 150 * 1024) {
+    const int parts = (a.out_dim + 191) / 192;
+    const int slice = ((a.out_dim + parts - 1) / parts + 7) / 8 * 8;
+    for (int o0 = 0; o0 < a.out_dim; o0 += slice) {
+      DenseArgs p = a;
+      p.out_dim = std::min(slice, a.out_dim - o0);
+      for (int g = 0; g < n->N; ++g) {
+        p.w_off[g] = a.w_off[g] + (a.trans ? o0 : o0 * a.w_ld[g]);
+        if (a.b_off[g] >= 0) p.b_off[g] = a.b_off[g] + o0;
+        p.y.f_off[g] = a.y.f_off[g] + o0;
+        if (a.aux.p) p.aux.f_off[g] = a.aux.f_off[g] + o0;
+      }
+      const int rc = launch_dense(n, p, max_in, s, x_exact);
+      if (rc) return rc;
+    }
+    return D2D_OK;
+  }
   // tensor-core path (dense_tc.cuh) for single-chunk reductions (K <= 64); with K = 3H the three stage -> MMA round
   // trips per tile serialise inside a slot and the register-tiled FP32 kernel is faster (measured 212 vs 480 us)
   if (tc_enabled() && !switched_off(kSwDenseTc) && n->B >= 256 && a.out_dim <= 192 && max_in <= tcd::kKc &&

@@ -24,7 +24,7 @@ SRC = os.environ.get("D2D_REFERENCE_ROOT", "/root/reference")
 DST = os.path.join(HERE, "_ref", "reference")
 MANIFEST = os.path.join(HERE, "_ref", "MANIFEST.json")
 FILES = ["__init__.py", "envs/env.py", "envs/combinatorial_env.py", "envs/channel_selection_env.py",
-         "algorithms/baselines.py", "algorithms/ippo.py", "algorithms/d2d_ppo.py",
+         "algorithms/baselines.py", "algorithms/ippo.py", "algorithms/d2d_ppo.py", "algorithms/irdqn.py",
          "combinatorial_load/setup.p", "combinatorial_load/setup_8_channels.p", "combinatorial_load/channel_switch_8.p"]
 
 

@@ -8,6 +8,7 @@ a timing run, not a parity run); the only harness pieces are the ``gym.spaces`` 
 * ``random_access_worker``: ``CombinatorialRandomAccess(env, tp).run(n_episodes)`` (algorithms/baselines.py:193-222 on
   envs/combinatorial_env.py), the loop of run_ma_baselines.py:71-74 -- the reference arm of the headline metric.
 * ``ippo_iteration``: ``iPPO.create_rollouts`` + ``iPPO.train`` (ippo.py:277-343, 406-441), GRU actor and critic.
+* ``irdqn_episodes``: ``iRDQN.train(n_episodes)`` (irdqn.py:222-302) with the settings of xp_load.py:112-126.
 """
 from __future__ import annotations
 
@@ -91,3 +92,30 @@ def ippo_iteration(kw, num_episodes=1, n_epoch=5, hidden=64, history_len=6, gamm
     total_s = time.perf_counter() - t0
     return {"rollout_s": rollout_s, "total_s": total_s,
             "agent_steps": num_episodes * env.episode_length * env.n_agents, "threads": torch.get_num_threads()}
+
+
+def irdqn_episodes(kw, n_episodes=3, threads=None):
+    """Unmodified ``iRDQN.train(n_episodes)`` with the (commented-out) settings of xp_load.py:112-126, training from
+    episode 1 on so that every timed episode but the first includes a minibatch update; the periodic ``test(50)`` is
+    stubbed (SPS excludes evaluation).  dict(total_s, agent_steps, threads)."""
+    import contextlib
+    import io
+
+    import numpy as np
+    import torch
+    if threads:
+        torch.set_num_threads(threads)
+    np.random.seed(0)
+    torch.manual_seed(0)
+    env = _env(kw)
+    mod = _import("algorithms.irdqn")
+    agent = mod.iRDQN(env, history_len=env.n_agents, replay_start_size=1, replay_buffer_size=100000, gamma=0.4,
+                      update_target_frequency=100, minibatch_size=64, learning_rate=1e-4, update_frequency=1,
+                      initial_exploration_rate=1, final_exploration_rate=0.1, adam_epsilon=1e-8, loss='huber')
+    agent.test = lambda n, verbose=False: (0.0, 0.0)
+    t0 = time.perf_counter()
+    with contextlib.redirect_stdout(io.StringIO()):
+        agent.train(n_episodes, early_stopping=False)
+    total_s = time.perf_counter() - t0
+    return {"total_s": total_s, "agent_steps": n_episodes * env.episode_length * env.n_agents,
+            "threads": torch.get_num_threads()}
