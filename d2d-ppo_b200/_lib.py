@@ -84,6 +84,7 @@ _SIGNATURES = {
     "d2d_env_export_state": (C.c_int, [_P, _P, _P, _P, _P, _P, _P]),
     "d2d_env_import_state": (C.c_int, [_P, _P, _P, _P, _P, _P, C.c_int, _P]),
     "d2d_env_scores": (C.c_int, [_P, _P, _P, _P, _P]),
+    "d2d_env_policy_edf": (C.c_int, [_P, C.c_int, _P, _P]),
     "d2d_net_create": (C.c_int, [C.POINTER(NetConfig), C.POINTER(_P)]),
     "d2d_net_destroy": (C.c_int, [_P]),
     "d2d_net_param_stride": (C.c_int64, [_P]),

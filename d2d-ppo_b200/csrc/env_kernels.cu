@@ -1170,6 +1170,44 @@ extern "C" int d2d_env_import_state(d2d_env* e, const uint8_t* buffers, const vo
   return D2D_OK;
 }
 
+// EarliestDeadlineFirstScheduler.act (algorithms/baselines.py:55-76) for every env: the one device whose oldest packet
+// is closest to its deadline transmits (ties: the first such device, as numpy's argmin); a uniformly drawn device when
+// no buffer holds a packet.  use_channel: devices whose channel is bad are skipped (:91-94).  One thread per env.
+__global__ void edf_policy_kernel(const uint32_t* __restrict__ buf, const uint8_t* __restrict__ chan, int N, int B,
+                                  int W, int use_channel, uint8_t* __restrict__ actions, uint32_t k0, uint32_t k1,
+                                  uint32_t env_offset, uint32_t t, uint32_t episode) {
+  for (int b = blockIdx.x * blockDim.x + threadIdx.x; b < B; b += gridDim.x * blockDim.x) {
+    int best = -1, best_d = 1 << 30;
+    for (int i = 0; i < N; ++i) {
+      if (use_channel && !(chan[(size_t)i * B + b] & 1)) continue;
+      const uint32_t* rec = buf + ((size_t)i * B + b) * W;
+      int d = -1;
+      for (int w = 0; w < W && d < 0; ++w) {
+        const uint32_t v = rec[w];
+        if (v) d = 4 * w + ((__ffs(v) - 1) >> 3);        // first non-zero byte = packets with the fewest slots left
+      }
+      if (d >= 0 && d < best_d) best_d = d, best = i;
+    }
+    if (best < 0) {
+      const uint4 r = philox4x32_10(env_offset + (uint32_t)b, t, kPurposePolicy << 16, episode, k0, k1);
+      best = (int)(((unsigned long long)r.x * (unsigned long long)N) >> 32);
+    }
+    for (int i = 0; i < N; ++i) actions[(size_t)i * B + b] = (uint8_t)(i == best);
+  }
+}
+
+extern "C" int d2d_env_policy_edf(const d2d_env* e, int use_channel, uint8_t* actions, void* stream) {
+  D2D_REQUIRE(e && actions, "d2d_env_policy_edf: null argument");
+  D2D_REQUIRE(e->kind == D2D_ENV_SINGLE_CHANNEL, "d2d_env_policy_edf: the scheduler grants the one shared channel of D2DEnv");
+  D2D_REQUIRE(e->is_reset, "d2d_env_policy_edf: call reset first");
+  edf_policy_kernel<<<grid_for(e->B, 128), 128, 0, as_stream(stream)>>>(
+      e->buf, reinterpret_cast<const uint8_t*>(e->chan), e->N, e->B, e->W, use_channel != 0, actions,
+      (uint32_t)(e->seed & 0xFFFFFFFFull), (uint32_t)(e->seed >> 32), (uint32_t)e->env_offset, (uint32_t)e->t,
+      (uint32_t)e->episode);
+  D2D_LAUNCHED();
+  return D2D_OK;
+}
+
 extern "C" int d2d_env_scores(const d2d_env* e, double* urllc, double* jains, double* channel_score, void* stream) {
   D2D_REQUIRE(e, "d2d_env_scores: null env");
   const int block = 256;

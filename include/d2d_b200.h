@@ -201,6 +201,12 @@ int d2d_env_import_state(d2d_env* env, const uint8_t* buffers, const void* chann
  * (combinatorial_env.py:245-264): f64 [B] each, any may be NULL. */
 int d2d_env_scores(const d2d_env* env, double* urllc, double* jains, double* channel_score, void* stream);
 
+/* EarliestDeadlineFirstScheduler.act (algorithms/baselines.py:55-76) on the env's current buffers, all B envs: actions
+ * u8 [N][B] one-hot over the devices -- the device whose oldest packet is closest to expiry (first one on ties), a
+ * uniformly drawn device (Philox policy stream) when no buffer holds a packet.  use_channel = 1 skips devices whose
+ * channel is bad (:91-94).  D2DEnv (D2D_ENV_SINGLE_CHANNEL) only: the scheduler grants its one shared channel. */
+int d2d_env_policy_edf(const d2d_env* env, int use_channel, uint8_t* actions, void* stream);
+
 
 /* ------------------------------------------------------------------------------------------
  * Learner: the per-agent actor / critic networks of algorithms/d2d_ppo.py and algorithms/ippo.py, evaluated
