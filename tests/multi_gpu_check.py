@@ -16,6 +16,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from d2d_ppo_b200 import presets  # noqa: E402
 from d2d_ppo_b200.algorithms.d2d_ppo import D2DPPO  # noqa: E402
 from d2d_ppo_b200.algorithms.ippo import iPPO  # noqa: E402
+from d2d_ppo_b200.algorithms.irdqn import iRDQN  # noqa: E402
 from d2d_ppo_b200.envs import CombinatorialEnv  # noqa: E402
 
 
@@ -30,6 +31,56 @@ def run(algo, B, offset, dev, epochs=2):
     for e in range(epochs):
         losses.append(ag.update_epoch() if algo == "ippo" else ag.update_epoch(cycle=np.roll(np.arange(6), e)))
     return ag, scores, losses
+
+
+def run_irdqn(B, offset, mb, pick, dev, K=4):
+    """K iterations of iRDQN on B envs starting at global env index `offset`; pick(ep) -> (start, global env column)
+    of the GLOBAL minibatch, of which this run takes the samples whose column it owns."""
+    kw = presets.combinatorial_kwargs("setup_8_channels", load=0.5, episode_length=20)
+    env = CombinatorialEnv(n_envs=B, device=dev, seed=23, env_offset=offset, **kw)
+    ag = iRDQN(env, history_len=4, replay_start_size=1, replay_buffer_size=10 ** 6, gamma=0.6, update_target_frequency=2,
+               minibatch_size=mb, learning_rate=1e-3, loss="huber", early_stopping=False, hidden_size=32, seed=6)
+    ag.test = lambda *a, **k: (0.0, 0.0)
+
+    def forced(ep):
+        start, col = pick(ep)
+        own = (col >= offset) & (col < offset + B)
+        assert own.sum() == mb
+        return start[own], col[own] - offset
+    scores, _, _ = ag.train(K, early_stopping=False, forced_samples=forced)
+    return ag, torch.tensor(scores, dtype=torch.float64, device=dev)
+
+
+def check_irdqn(rank, world, dev):
+    B, mb, T, L = 64, 32, 20, 4
+    Bw = B // world
+
+    def pick(ep):      # every rank draws the same global minibatch: mb / world samples per shard
+        rng = np.random.default_rng(100 + ep)
+        start = rng.integers(0, (ep + 1) * T - L, mb)
+        col = np.concatenate([r * Bw + rng.integers(0, Bw, mb // world) for r in range(world)])
+        return start, col
+    ag, scores = run_irdqn(Bw, rank * Bw, mb // world, pick, dev)
+    gathered = [torch.empty_like(scores) for _ in range(world)]
+    dist.all_gather(gathered, scores)
+    params = ag.network.params.clone()
+    dist.barrier()
+    if rank == 0:
+        from d2d_ppo_b200.algorithms import _dist
+        saved = _dist.active
+        _dist.active = lambda: False
+        ref, ref_scores = run_irdqn(B, 0, mb, pick, dev)
+        _dist.active = saved
+        K = ref_scores.numel() // B
+        mine = torch.stack([g.view(K, Bw) for g in gathered], dim=1).reshape(-1)     # iteration-major, shard, env
+        assert torch.equal(mine, ref_scores), "sharded iRDQN rollouts differ from the single-GPU run"
+        d = (params - ref.network.params).abs().max().item()
+        l0, l1 = torch.stack(ag.losses).cpu().numpy(), torch.stack(ref.losses).cpu().numpy()
+        assert np.allclose(l0, l1, rtol=1e-4, atol=1e-6), (l0, l1)
+        assert d < 5e-5, d
+        print(f"irdqn: {world} ranks x {Bw} envs == 1 rank x {B} envs (scores bit-equal, max |param diff| {d:.2e}, "
+              f"last losses {l0[-1][:2]} vs {l1[-1][:2]})")
+    dist.barrier()
 
 
 def main():
@@ -61,6 +112,7 @@ def main():
             print(f"{algo}: {world} ranks x {B // world} envs == 1 rank x {B} envs "
                   f"(scores bit-equal, max |param diff| {d:.2e}, losses {l0.reshape(-1)[:2]} vs {l1.reshape(-1)[:2]})")
         dist.barrier()
+    check_irdqn(rank, world, dev)
     dist.destroy_process_group()
 
 
