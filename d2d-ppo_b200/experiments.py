@@ -62,6 +62,19 @@ def xp_load(out_dir="combinatorial_load", learner="d2dppo", n_seeds=1, loads=Non
             folder = _mk(os.path.join(out_dir, f"models_mcappo{s['n_channels']}_seed_{seed}_load_{load}"))
             env = CombinatorialEnv(n_envs=n_envs, device=device, seed=42 + seed,
                                    **presets.combinatorial_kwargs(setup, load=load, homogeneous_size=True))
+            if learner == "irdqn":
+                # the run the script keeps commented out (xp_load.py:111-131): same settings, idqn.train(20000) and
+                # idqn.test(500) scaled by the caller through num_iter / test_episodes; channel errors / rewards are ""
+                from .algorithms.irdqn import iRDQN
+                idqn = iRDQN(env, history_len=s["n_agents"], replay_start_size=100, replay_buffer_size=100000,
+                             gamma=0.4, update_target_frequency=100, minibatch_size=64, learning_rate=1e-4,
+                             update_frequency=1, initial_exploration_rate=1, final_exploration_rate=0.1,
+                             adam_epsilon=1e-8, loss="huber", seed=seed)
+                res = idqn.train(num_iter)
+                score, jain = idqn.test(test_episodes)
+                for lst, v in zip(row, (score, jain, "", "", res)):
+                    lst.append(v)
+                continue
             ppo = _learner(learner, env, folder, seed, hidden_size=64, gamma=gamma, policy_lr=3e-4, value_lr=1e-3,
                            useRNN=True, combinatorial=True, history_len=s["n_agents"], early_stopping=True)
             res = ppo.train(num_iter=num_iter, n_epoch=n_epoch, num_episodes=n_envs, test_freq=test_freq)

@@ -27,6 +27,10 @@ def test_xp_load_smoke(tmp_path, cuda_device):
     res = X.xp_load(out_dir=out, learner="ippo", loads=[0.5], num_iter=1, n_epoch=1, n_envs=8, test_freq=1,
                     test_episodes=8, device=cuda_device)
     _check_metrics(res["scores"], res["jains"])
+    # the iRDQN block the script keeps commented out (xp_load.py:111-131)
+    res = X.xp_load(out_dir=out, learner="irdqn", loads=[0.5], num_iter=2, n_envs=8, test_episodes=8,
+                    device=cuda_device)
+    assert 0 <= res["scores"][0][0] <= 1 and res["channel_errors"][0][0] == "" and len(res["training"][0][0]) == 3
 
 
 def test_baseline_sweeps_smoke(tmp_path, cuda_device):

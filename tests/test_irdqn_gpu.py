@@ -184,3 +184,46 @@ def test_irdqn_checkpoint_roundtrip_and_reference_keys(tmp_path, cuda_device):
     a.save(str(tmp_path))
     b.load(str(tmp_path))
     assert torch.equal(a.network.params, b.network.params) and torch.equal(b.target_params, a.network.params)
+
+
+def test_replay_ring_wraps_like_a_deque(cuda_device):
+    """A ring of 3 episode slots fed 5 episodes: deque index 0 is the oldest SURVIVING transition, chunks straddle
+    episode ends and the physical end of the ring, done marks the last step of an episode."""
+    from d2d_ppo_b200.algorithms.irdqn import ReplayBuffer
+    B, N, T, rows, L, mb = 4, 3, 6, 5, 4, 64
+    rb = ReplayBuffer(3 * B * T, cuda_device, n_envs=B, n_agents=N, episode_length=T, obs_rows=rows, seed=1)
+    assert rb.n_slots == 3
+    rng = np.random.default_rng(0)
+    eps = []
+    for e in range(5):
+        obs = rng.standard_normal((T + 1, rows, B)).astype(np.float32)
+        act = rng.integers(0, 4, (T, N, B)).astype(np.uint8)
+        rew = rng.integers(0, 3, (T, B)).astype(np.int32)
+        eps.append((obs, act, rew))
+        rb.add_episode(torch.tensor(obs).to(cuda_device), torch.tensor(act).to(cuda_device),
+                       torch.tensor(rew).to(cuda_device))
+    assert len(rb) == 3 * T and rb.oldest_slot == 2          # episodes 2, 3, 4 survive; episode 2 sits in slot 2
+    kept = eps[2:]
+    s_flat = np.concatenate([o[:T] for o, _, _ in kept])     # [3T, rows, B] deque order
+    n_flat = np.concatenate([o[1:] for o, _, _ in kept])
+    a_flat = np.concatenate([a for _, a, _ in kept])
+    r_flat = np.concatenate([r for _, _, r in kept])
+    start = rng.integers(0, 3 * T - L, mb)
+    start[:4] = [T - 2, 2 * T - 1, 3 * T - L - 1, 0]         # straddle both episode ends; the last legal start; the first
+    col = rng.integers(0, B, mb)
+    xs, act, rew, xn, done = rb.sample_chunk(mb, L, start, col)
+    k = start[:, None] + np.arange(L)[None, :]
+    assert np.array_equal(xs.cpu().numpy(), s_flat[k, :, col[:, None]].transpose(1, 2, 0))
+    assert np.array_equal(xn.cpu().numpy(), n_flat[k, :, col[:, None]].transpose(1, 2, 0))
+    last = k[:, -1]
+    assert np.array_equal(act.cpu().numpy(), a_flat[last, :, col].T)
+    assert np.array_equal(rew.cpu().numpy(), r_flat[last, col])
+    assert np.array_equal(done.cpu().numpy(), (last % T == T - 1).astype(np.uint8))
+    xs2 = rb.sample_chunk(mb, L)[0]                          # default draws stay in range
+    assert xs2.shape == (L, rows, mb)
+    with pytest.raises(ValueError):
+        rb.sample_chunk(mb, L, start + 3 * T, col)
+    rb.reset()
+    assert len(rb) == 0
+    with pytest.raises(ValueError):
+        rb.sample_chunk(mb, L)
