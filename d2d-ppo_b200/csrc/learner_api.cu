@@ -288,8 +288,11 @@ static int launch_gru_step(const d2d_net* n, GruStepArgs& a, const float* params
   int per_sm = 1;
   D2D_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, gru_step_kernel, 256, smem));
   const int gx = std::max(1, std::min(tiles, (148 * std::max(per_sm, 1)) / n->N));
-  gru_step_kernel<<<dim3(gx, n->N), 256, smem, s>>>(a);
-  D2D_LAUNCHED();
+  for (int u0 = 0; u0 < n->H; u0 += 64) {      // H > 64: every slice reads all of h_prev and writes its own units
+    a.u0 = u0;
+    gru_step_kernel<<<dim3(gx, n->N), 256, smem, s>>>(a);
+    D2D_LAUNCHED();
+  }
   return D2D_OK;
 }
 
@@ -631,7 +634,7 @@ static int forward_chunk(d2d_net* n, const float* params, const float* x, int x_
     for (int st = 0; st < L && !use_tc; ++st) {
       const View hprev = make_view(hs_ptr(n, c, train, st - 1 < 0 ? 0 : st - 1), H * NB, -c0, N, H, B);
       const View hout = make_view(hs_ptr(n, c, train, st), H * NB, -c0, N, H, B);
-      if (B % 4 == 0 && H <= 64) {   // fused hidden projection + gates (its register tile covers 3H <= 192 outputs)
+      if (B % 4 == 0 && H <= 128) {   // fused hidden projection + gates (a register tile covers 64 units; H > 64: 2 launches)
         GruStepArgs fa;
         memset(&fa, 0, sizeof(fa));
         fa.h_prev = hprev, fa.h_out = hout, fa.gi = gi, fa.gi.t_off = gi.t_off - (L - 1 - st);
@@ -983,7 +986,7 @@ extern "C" int d2d_net_check_inputs(const d2d_net* n, const float* x, int x_lead
 extern "C" int d2d_net_rollout_step(d2d_net* n, const float* params, const float* x, int x_lead, int t, float* out,
                                     void* stream) {
   D2D_REQUIRE(n && params && x && out, "d2d_net_rollout_step: null argument");
-  if (n->arch == D2D_NET_MLP || n->B % 4 != 0 || n->H > 64)
+  if (n->arch == D2D_NET_MLP || n->B % 4 != 0 || n->H > 128)
     return d2d_net_forward(n, params, x, x_lead, t, t + 1, 0, out, stream);
   int rc = check_range(n, x_lead, t, t + 1, "d2d_net_rollout_step");
   if (rc) return rc;

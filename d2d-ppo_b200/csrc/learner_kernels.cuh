@@ -254,7 +254,8 @@ __global__ void __launch_bounds__(256) dense_tile_kernel(const DenseArgs a) {
 // ------------------------------------------------------------------------------------------------
 // Fused GRU step: gh = h_prev W_hh^T + b_hh (register-tiled as dense_tile_kernel<4, 24>) with the gate maths in
 // the epilogue, so the [rows x 3H] hidden projection never goes to HBM.  Warp w owns hidden units
-// [8 w, 8 w + 8); its 24 accumulator columns are (r, z, n) x 8 units.  H <= 64.
+// [u0 + 8 w, u0 + 8 w + 8); its 24 accumulator columns are (r, z, n) x 8 units.  One launch covers 64 units; hidden
+// sizes up to 128 (the reference's iRDQN networks: 100) take one launch per slice of 64 units (u0 = 0, 64).
 // ------------------------------------------------------------------------------------------------
 struct GruStepArgs {
   View h_prev, h_out, gi, acts;   // gi: input projections at time t - back (view.t_off carries the shift)
@@ -265,6 +266,7 @@ struct GruStepArgs {
   int bhh_off[D2D_MAX_AGENTS];
   int H, B, t0, t1;
   int back, padded, first, store, t_episode0;
+  int u0;                         // first hidden unit of this launch (H > 64: one launch per slice of 64 units)
 };
 
 __device__ __forceinline__ float4 sigmoid4(float4 v) {
@@ -284,11 +286,11 @@ __global__ void __launch_bounds__(256) gru_step_kernel(const GruStepArgs a) {
   const float* bias = a.w + g * a.w_agent_stride + a.bhh_off[g];
   for (int i = threadIdx.x; i < in_dim * OUT_PAD; i += 256) {
     const int k = i / OUT_PAD, col = i % OUT_PAD;
-    const int u = (col / OPT) * 8 + (col % 8), gate = (col % OPT) / 8;
+    const int u = a.u0 + (col / OPT) * 8 + (col % 8), gate = (col % OPT) / 8;
     Ms[i] = u < H ? W[(long long)(gate * H + u) * H + k] : 0.f;
   }
   for (int col = threadIdx.x; col < OUT_PAD; col += 256) {
-    const int u = (col / OPT) * 8 + (col % 8), gate = (col % OPT) / 8;
+    const int u = a.u0 + (col / OPT) * 8 + (col % 8), gate = (col % OPT) / 8;
     bs[col] = u < H ? bias[gate * H + u] : 0.f;
   }
   const int lane = threadIdx.x & 31, og = threadIdx.x >> 5;
@@ -366,7 +368,7 @@ __global__ void __launch_bounds__(256) gru_step_kernel(const GruStepArgs a) {
         float* ac = a.store ? view_ptr(a.acts, g, t, a.B, b) : nullptr;
 #pragma unroll
         for (int uu = 0; uu < 8; ++uu) {
-          const int u = og * 8 + uu;
+          const int u = a.u0 + og * 8 + uu;
           if (u < H) {
             const long long uB = (long long)u * a.B;
             const float4 hpv = hp ? *reinterpret_cast<const float4*>(hp + uB) : make_float4(0.f, 0.f, 0.f, 0.f);
