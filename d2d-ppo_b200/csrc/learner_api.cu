@@ -124,6 +124,27 @@ static int launch_dense(const d2d_net* n, DenseArgs& a, int max_in, cudaStream_t
     }
     return D2D_OK;
   }
+  // a reduction too long for the register-tiled kernel's resident weight tile (K = 3H of the hidden sizes above 64 in
+  // d(h) += d(gh) W_hh): split along K into accumulating launches instead of falling to the generic kernel, which
+  // re-stages the whole matrix per block (322 us for a 64-row minibatch: profiles/r02_n_irdqn_launch_summary.txt)
+  if ((a.epilogue == kEpiAccum || a.epilogue == kEpiNone) && n->B % 4 == 0 && a.out_dim <= 192 && max_in > 160 &&
+      (size_t)max_in * 8 * (a.out_dim > 64 ? 24 : (a.out_dim > 32 ? 8 : 4)) * 4 > 160 * 1024) {
+    const int parts = (max_in + 159) / 160;
+    const int slice = ((max_in + parts - 1) / parts + 3) / 4 * 4;
+    for (int k0 = 0; k0 < max_in; k0 += slice) {
+      DenseArgs p = a;
+      if (k0 > 0) p.epilogue = kEpiAccum;
+      for (int g = 0; g < n->N; ++g) {
+        p.in_dim[g] = std::max(0, std::min(slice, a.in_dim[g] - k0));
+        p.w_off[g] = a.w_off[g] + (a.trans ? k0 * a.w_ld[g] : k0);
+        if (k0 > 0) p.b_off[g] = -1;
+        p.x.f_off[g] = a.x.f_off[g] + k0;
+      }
+      const int rc = launch_dense(n, p, std::min(slice, max_in - k0), s, x_exact);
+      if (rc) return rc;
+    }
+    return D2D_OK;
+  }
   // tensor-core path (dense_tc.cuh) for single-chunk reductions (K <= 64); with K = 3H the three stage -> MMA round
   // trips per tile serialise inside a slot and the register-tiled FP32 kernel is faster (measured 212 vs 480 us)
   if (tc_enabled() && !switched_off(kSwDenseTc) && n->B >= 256 && a.out_dim <= 192 && max_in <= tcd::kKc &&
