@@ -89,3 +89,21 @@ def test_gfaccess_matches_reference_statistics(cuda_device):
         assert abs(errors / B - r["errors_per_episode"]) <= 4 * r["errors_se"] + 0.02, (tp, errors / B, r)
     with pytest.raises(ValueError):
         GFAccess(env, use_channel=True)
+
+
+def test_baselines_single_env_mode(cuda_device):
+    """Without n_envs the env is the reference's single host-facing env: the schedulers' run() keeps working and returns
+    the reference's tuple types."""
+    from d2d_ppo_b200.algorithms.baselines import EarliestDeadlineFirstScheduler, GFAccess
+    g = _load()
+    env = make_cuda_env("d2d", g["config"], None, device=cuda_device, seed=11)
+    for pol in (EarliestDeadlineFirstScheduler(env), EarliestDeadlineFirstScheduler(env, use_channel=True),
+                GFAccess(env, transmission_prob=0.3)):
+        score, jains, errors, rewards = pol.run(3)
+        assert 0.0 <= score <= 1.0 and 0.0 < jains <= 1.0 + 1e-12 and isinstance(errors, int) and errors >= 0
+        assert np.isfinite(rewards)
+    cv = GFAccess(env, transmission_prob_list=[0.1, 0.9]).get_best_transmission_probs(2)
+    assert len(cv) == 2 and all(0.0 <= c <= 1.0 for c in cv)
+    # EDF beats grant-free access on this load by a wide margin (it never collides)
+    envb = make_cuda_env("d2d", g["config"], 2048, device=cuda_device, seed=12)
+    assert EarliestDeadlineFirstScheduler(envb).run(2048)[0] > GFAccess(envb, transmission_prob=0.5).run(2048)[0] + 0.1

@@ -91,7 +91,7 @@ def test_irdqn_greedy_test_matches_reference(tag, cuda_device):
                        << agent.act_buf.to(torch.int64))
 
 
-@pytest.mark.parametrize("hidden,B", [(64, 256), (100, 8), (32, 12)])
+@pytest.mark.parametrize("hidden,B", [(64, 256), (100, 8), (32, 12), (100, 6), (128, 16)])
 def test_irdqn_lockstep_training_matches_restatement(hidden, B, cuda_device):
     """B lockstep envs on Philox streams, epsilon-greedy actions drawn by the kernel: every train_step (replay gather
     from several env columns and episodes, target network, TD target, loss, BPTT, Adam) against the torch
