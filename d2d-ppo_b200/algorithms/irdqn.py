@@ -159,9 +159,12 @@ class iRDQN:
     def _sample_seed(self):
         return (self.seed * 0x9E3779B97F4A7C15 + self._episode * 0xD1B54A32D192ED03 + 0x6A09E667F3BCC909) & (2 ** 64 - 1)
 
-    def _run_episode(self, mode, ready, forced_actions=None):
+    def _run_episode(self, mode, ready, forced_actions=None, episode=None):
         """One lockstep episode: Q-values of the unpadded history window (irdqn.py:242-247), epsilon-greedy / greedy /
-        given channel index per agent, env step with the one-hot channel vectors.  forced_actions: u8 [T, N, B]."""
+        given channel index per agent, env step with the one-hot channel vectors.  forced_actions: u8 [T, N, B].
+        episode: training episode index -- the reference updates every agent's epsilon right after its FIRST action of
+        the episode (a.update_epsilon(ep) inside the step loop, :253), so step 0 explores with the previous episode's
+        rate and the remaining steps with this episode's."""
         env, N, B = self.env, self.n_agents, self.B
         env.reset_into(self.obs_buf[self.lead])
         for t in range(self.T):
@@ -173,6 +176,8 @@ class iRDQN:
             q_select(q, N, B, self.n_actions, L.ACT_GIVEN if forced_actions is not None else mode, self.epsilon, ready,
                      self.n_random, self.act_buf[t], self.mask_buf[t], seed=self._sample_seed(),
                      env_offset=env.env_offset, t_abs=t)
+            if t == 0 and episode is not None:
+                self.update_epsilon(episode)
             done = env.step_into(self.mask_buf[t], self.obs_buf[self.lead + t + 1], None, self.reward_buf[t])
         assert done
         self._episode += 1
@@ -207,8 +212,7 @@ class iRDQN:
         test_list, reward_list, train_scores = [], [], []
         for ep in range(n_episodes):
             ready = ep >= self.replay_start_size
-            self._run_episode(L.ACT_SAMPLE, ready, None if forced_actions is None else forced_actions(ep))
-            self.update_epsilon(ep)                          # a.update_epsilon(ep) inside the step loop (:253)
+            self._run_episode(L.ACT_SAMPLE, ready, None if forced_actions is None else forced_actions(ep), episode=ep)
             self.replay_buffer.add_episode(self.obs_buf[self.lead:], self.act_buf, self.reward_buf)
             train_scores += self.env.compute_urllc().tolist()            # 1 - discarded / received per episode (:272)
             if ep % 100 == 0:
