@@ -182,6 +182,16 @@ class iRDQN:
         assert done
         self._episode += 1
 
+    def _guard_exact_inputs(self):
+        """The nets are created with ``inputs_bf16_exact`` (CombinatorialEnv observations are small integers), which lets
+        hidden sizes 16 / 32 / 48 / 64 run on the tensor-core GRU window with the observations as ONE bf16 plane.  As in
+        the PPO learners the promise is checked on every collected episode, before it enters the replay ring."""
+        if self.hidden_size in (16, 32, 48, 64):
+            bad = int(self.actor.count_inexact_inputs(self.obs_buf, self.lead, 0, self.T + 1).item())
+            if bad:
+                raise RuntimeError(f"{bad} observation values are not exactly representable in bf16: the tensor-core "
+                                   f"GRU path would truncate them")
+
     def _packet_sums(self, n=None):
         disc, recv = self.env.discarded_packets, self.env.received_packets        # [B, N]
         n = self.B if n is None else n
@@ -213,6 +223,7 @@ class iRDQN:
         for ep in range(n_episodes):
             ready = ep >= self.replay_start_size
             self._run_episode(L.ACT_SAMPLE, ready, None if forced_actions is None else forced_actions(ep), episode=ep)
+            self._guard_exact_inputs()
             self.replay_buffer.add_episode(self.obs_buf[self.lead:], self.act_buf, self.reward_buf)
             train_scores += self.env.compute_urllc().tolist()            # 1 - discarded / received per episode (:272)
             if ep % 100 == 0:
