@@ -733,9 +733,20 @@ def run_native(args):
         e2e_secs[layout] = max_over_ranks(time.perf_counter() - t0)
         return world * B * N_AGENTS * Ke / e2e_secs[layout]
 
+    # reference layout: with >= 12 host threads the library packs the [B,N,C] bytes to bitmasks on the host before the
+    # copy (csrc/host_pack.cpp); the same call with that switched off (device-side packing) is reported beside it
+    from d2d_ppo_b200 import _lib as _L
+    host_threads = int(_L.lib().d2d_get_host_threads())
+    host_packed = host_threads >= 12
     e2e_value = e2e_time(host_actions, "reference")
+    secs_default = e2e_secs["reference"]
+    _L.set_kernel_switch(_L.SWITCH_HOST_PACK, False)
+    e2e_unpacked = e2e_time(host_actions, "reference")
+    secs_unpacked = e2e_secs["reference"]
+    _L.set_kernel_switch(_L.SWITCH_HOST_PACK, True)
     e2e_masks = e2e_time(host_masks, "device")
-    h2d_gbs_rank = B * N_AGENTS * N_CHANNELS * Ke / e2e_secs["reference"] / 1e9
+    h2d_step = B * N_AGENTS * (1 if host_packed else N_CHANNELS)
+    h2d_gbs_rank = B * N_AGENTS * N_CHANNELS * Ke / secs_unpacked / 1e9
 
     # ---- roofline of the dominant kernel ---------------------------------------------------------
     peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
@@ -785,11 +796,20 @@ def run_native(args):
                                  "note": "write-only and copy bandwidth measured in this run (1 GiB torch fill_ / "
                                          "copy_); the step kernel's traffic is 83 % stores"}},
         "e2e": {"value": e2e_value, "unit": "agent-steps/s",
-                "h2d_bytes_per_step": B * N_AGENTS * N_CHANNELS, "d2h_bytes_per_step": B * 4, "steps": Ke,
+                "h2d_bytes_per_step": h2d_step, "d2h_bytes_per_step": B * 4, "steps": Ke,
                 "api": "CombinatorialEnv.step_host (C ABI d2d_env_step_host): actions u8 [B,N,C] 0/1, the reference's "
                        "(N,C) array per env, in pinned host memory -> i32 [B] rewards in pinned host memory, read by "
                        "the host every step; two calls in flight",
-                "bound": "PCIe: 48 B of actions per env-step",
+                "host_packed": host_packed, "host_threads": host_threads,
+                "host_bytes_read_per_step": B * N_AGENTS * N_CHANNELS,
+                "host_pack_gbs_per_rank": (B * N_AGENTS * N_CHANNELS * Ke / secs_default / 1e9) if host_packed else None,
+                "bound": ("host: the library packs the 48 B of actions per env-step into 6 B of channel bitmasks on "
+                          f"{host_threads} host threads (AVX2) before they cross PCIe") if host_packed else
+                         "PCIe: 48 B of actions per env-step",
+                "unpacked_copy": {"value": e2e_unpacked, "unit": "agent-steps/s",
+                                  "h2d_bytes_per_step": B * N_AGENTS * N_CHANNELS,
+                                  "api": "the same call with D2D_SWITCH_HOST_PACK = 0: the u8 [B,N,C] bytes cross PCIe "
+                                         "as they are and are packed on the device (PCIe bound)"},
                 "h2d_gbs_per_rank": h2d_gbs_rank, "h2d_gbs_all_ranks": h2d_gbs_rank * world,
                 "numa_binding": None if numa is None else {"node": numa[0], "cpus": numa[1]},
                 "limiter": "host -> device copy of the u8 [B,N,C] actions (50.3 MB per step and rank) over each GPU's "

@@ -20,7 +20,7 @@ FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-li
 
 
 def _sources():
-    return sorted(os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith(".cu"))
+    return sorted(os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cu", ".cpp")))   # .cpp: host only
 
 
 def _headers_mtime():
@@ -30,7 +30,7 @@ def _headers_mtime():
 
 
 def _compile(src, verbose):
-    obj = os.path.join(OBJ, os.path.basename(src)[:-3] + ".o")
+    obj = os.path.join(OBJ, os.path.splitext(os.path.basename(src))[0] + ".o")
     if os.path.exists(obj) and os.path.getmtime(obj) >= max(os.path.getmtime(src), _headers_mtime()):
         return obj
     cmd = [NVCC, *FLAGS, "-c", src, "-o", obj]

@@ -51,7 +51,7 @@ ACT_SAMPLE, ACT_GREEDY, ACT_GIVEN = 0, 1, 2
 ACT_HOST_REFERENCE, ACT_HOST_DEVICE_LAYOUT = 0, 1
 QLOSS_HUBER, QLOSS_MSE = 0, 1
 SWITCH_GRU_WINDOW_TC, SWITCH_GRU_BPTT_TC, SWITCH_DENSE_TC, SWITCH_WGRAD_TC, SWITCH_FUSED_HEAD, SWITCH_ALL_TC, \
-    SWITCH_BPTT_RECOMPUTE, SWITCH_WINDOW_HEAD, SWITCH_WINDOW_WIDE, SWITCH_ENV_MULTISTEP = range(10)
+    SWITCH_BPTT_RECOMPUTE, SWITCH_WINDOW_HEAD, SWITCH_WINDOW_WIDE, SWITCH_ENV_MULTISTEP, SWITCH_HOST_PACK = range(11)
 
 _lib = None
 
@@ -81,6 +81,9 @@ _SIGNATURES = {
     "d2d_env_step_host": (C.c_int, [_P, _P, C.c_int, _P, _P, _P, _P, _P, _P, C.POINTER(C.c_uint64)]),
     "d2d_env_host_wait": (C.c_int, [_P, C.c_uint64]),
     "d2d_pack_actions": (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_int, _P]),
+    "d2d_set_host_threads": (C.c_int, [C.c_int]),
+    "d2d_get_host_threads": (C.c_int, []),
+    "d2d_pack_actions_host": (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_int]),
     "d2d_env_export_state": (C.c_int, [_P, _P, _P, _P, _P, _P, _P]),
     "d2d_env_import_state": (C.c_int, [_P, _P, _P, _P, _P, _P, C.c_int, _P]),
     "d2d_env_scores": (C.c_int, [_P, _P, _P, _P, _P]),
@@ -143,6 +146,14 @@ def lib():
             fn.restype, fn.argtypes = res, args
         if handle.d2d_abi_version() != 1:
             raise ImportError("libd2d_b200.so ABI version mismatch; rebuild")
+        # host thread pool of the host-buffer step: this rank's share of the CPUs it may run on (torchrun exports
+        # LOCAL_WORLD_SIZE; the C library itself reads no environment variables)
+        try:
+            cpus = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+            share = max(1, cpus // max(1, int(os.environ.get("LOCAL_WORLD_SIZE", "1"))))
+            handle.d2d_set_host_threads(min(16, share))
+        except (ValueError, OSError):
+            pass
         _lib = handle
     return _lib
 

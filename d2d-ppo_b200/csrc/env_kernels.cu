@@ -661,6 +661,7 @@ struct HostPipe {
   static constexpr int kSlots = 2;
   cudaStream_t h2d = nullptr, d2h = nullptr;
   uint8_t* stage[kSlots] = {nullptr, nullptr};    // device copy of the host actions, as the host laid them out
+  uint8_t* hpacked[kSlots] = {nullptr, nullptr};  // pinned host buffers: the actions packed to bitmasks on the host
   void* masks[kSlots] = {nullptr, nullptr};       // device-layout actions [N][B] (packed from `stage` if needed)
   int32_t* reward[kSlots] = {nullptr, nullptr};
   uint8_t* done[kSlots] = {nullptr, nullptr};
@@ -670,12 +671,22 @@ struct HostPipe {
   size_t stage_bytes = 0;
 };
 
+// host_pack.cpp
+namespace d2d {
+void host_pack_actions(const uint8_t* src, void* dst, long long B, int N, int C, int mask_bytes);
+int host_threads();
+}  // namespace d2d
+// fewer threads than this pack no faster than PCIe moves the unpacked bytes (measured: 16 threads 82 GB/s of action
+// bytes, 8 threads about the 50 - 55 GB/s of the link)
+constexpr int kHostPackMinThreads = 12;
+
 static void pipe_free(HostPipe* p) {
   if (!p) return;
   if (p->h2d) cudaStreamSynchronize(p->h2d);
   if (p->d2h) cudaStreamSynchronize(p->d2h);
   for (int i = 0; i < HostPipe::kSlots; ++i) {
     cudaFree(p->stage[i]), cudaFree(p->masks[i]), cudaFree(p->reward[i]), cudaFree(p->done[i]);
+    if (p->hpacked[i]) cudaFreeHost(p->hpacked[i]);
     if (p->events) cudaEventDestroy(p->in_ready[i]), cudaEventDestroy(p->step_done[i]), cudaEventDestroy(p->out_done[i]);
   }
   if (p->h2d) cudaStreamDestroy(p->h2d);
@@ -1101,15 +1112,26 @@ extern "C" int d2d_env_step_host(d2d_env* e, const void* actions_host, int layou
   const bool comb = e->kind == D2D_ENV_COMBINATORIAL;
   D2D_REQUIRE(comb || layout == D2D_ACT_HOST_DEVICE_LAYOUT,
               "d2d_env_step_host: D2D_ACT_HOST_REFERENCE is defined for the combinatorial env only");
-  const bool need_pack = comb && layout == D2D_ACT_HOST_REFERENCE;
+  bool need_pack = comb && layout == D2D_ACT_HOST_REFERENCE;
   cudaStream_t s = as_stream(stream);
+  // 0. reference layout with enough host threads: pack u8 [B][N][C] to the [N][B] bitmasks ON THE HOST (host_pack.cpp),
+  //    so that 1/C of the bytes cross PCIe.  The call blocks for the packing; the copy and the step stay asynchronous,
+  //    so the host packs call k + 1 while the device runs call k.
+  const void* src_host = actions_host;
+  if (need_pack && d2d_get_kernel_switch(D2D_SWITCH_HOST_PACK) == 1 && d2d::host_threads() >= kHostPackMinThreads) {
+    if (!p->hpacked[slot]) D2D_CUDA(cudaHostAlloc((void**)&p->hpacked[slot], nb * e->CB, cudaHostAllocDefault));
+    if (reused) D2D_CUDA(cudaEventSynchronize(p->in_ready[slot]));   // the copy of call k - 2 has left this buffer
+    d2d::host_pack_actions(reinterpret_cast<const uint8_t*>(actions_host), p->hpacked[slot], e->B, e->N, e->C, e->CB);
+    src_host = p->hpacked[slot];
+    need_pack = false;
+  }
   // 1. host -> device on the copy-in stream, once the step of call k - 2 has consumed this slot.  The copy is NOT
   //    ordered after the caller's stream (that would serialise it behind the previous call's step and lose the
   //    copy / compute overlap): actions_host must be complete on the host when the call is made (d2d_b200.h)
   if (reused) D2D_CUDA(cudaStreamWaitEvent(p->h2d, p->step_done[slot], 0));
   void* dst = need_pack ? (void*)p->stage[slot] : p->masks[slot];
   const size_t bytes = need_pack ? nb * e->C : nb * (comb ? e->CB : 1);
-  D2D_CUDA(cudaMemcpyAsync(dst, actions_host, bytes, cudaMemcpyHostToDevice, p->h2d));
+  D2D_CUDA(cudaMemcpyAsync(dst, src_host, bytes, cudaMemcpyHostToDevice, p->h2d));
   D2D_CUDA(cudaEventRecord(p->in_ready[slot], p->h2d));
   // 2. pack + step on the caller's stream
   D2D_CUDA(cudaStreamWaitEvent(s, p->in_ready[slot], 0));

@@ -66,8 +66,9 @@ static View make_view(float* p, long long t_stride, int t_off, int N, int feat_p
 enum { kSwGruTc = D2D_SWITCH_GRU_WINDOW_TC, kSwBwdTc = D2D_SWITCH_GRU_BPTT_TC, kSwDenseTc = D2D_SWITCH_DENSE_TC,
        kSwWgradTc = D2D_SWITCH_WGRAD_TC, kSwFusedHead = D2D_SWITCH_FUSED_HEAD, kSwAllTc = D2D_SWITCH_ALL_TC,
        kSwBpttRecompute = D2D_SWITCH_BPTT_RECOMPUTE, kSwWindowHead = D2D_SWITCH_WINDOW_HEAD,
-       kSwWindowWide = D2D_SWITCH_WINDOW_WIDE, kSwEnvMultistep = D2D_SWITCH_ENV_MULTISTEP, kSwCount };
-static int g_switch_off[kSwCount] = {0, 0, 0, 0, 0, 0, 0, 0, 1, 0};   // the 32-warp window variant is opt-in (measured slower)
+       kSwWindowWide = D2D_SWITCH_WINDOW_WIDE, kSwEnvMultistep = D2D_SWITCH_ENV_MULTISTEP,
+       kSwHostPack = D2D_SWITCH_HOST_PACK, kSwCount };
+static int g_switch_off[kSwCount] = {0, 0, 0, 0, 0, 0, 0, 0, 1, 0, 0};   // the 32-warp window variant is opt-in (measured slower)
 static bool switched_off(int which) { return g_switch_off[which] != 0; }
 static bool tc_enabled() { return g_switch_off[kSwAllTc] == 0; }
 

@@ -176,12 +176,22 @@ int d2d_pack_actions(const uint8_t* actions_bnc, void* packed, int n_envs, int n
  * after `stream`: a caller that fills actions_host with asynchronous work must synchronise that work first) and
  * must stay untouched until the call's step ran (d2d_env_host_wait of the same ticket suffices).
  * *ticket (may be NULL) identifies the call; d2d_env_host_wait(env, ticket) blocks the host thread until
- * reward_host / done_host of that call are valid. */
+ * reward_host / done_host of that call are valid.
+ * With D2D_ACT_HOST_REFERENCE and at least 12 host threads (d2d_get_host_threads) the library packs the [B][N][C] bytes
+ * into the [N][B] channel bitmasks ON THE HOST (AVX2, thread pool) and copies 1/C of the bytes; the call then blocks for
+ * the packing (actions_host may be reused as soon as it returns), the copy and the step stay asynchronous. */
 #define D2D_ACT_HOST_REFERENCE 0
 #define D2D_ACT_HOST_DEVICE_LAYOUT 1
 int d2d_env_step_host(d2d_env* env, const void* actions_host, int layout, float* obs, float* state,
                       int32_t* reward_host, uint8_t* done_host, void* ack, void* stream, uint64_t* ticket);
 int d2d_env_host_wait(d2d_env* env, uint64_t ticket);
+
+/* Host-side helpers of the host-buffer step (csrc/host_pack.cpp, no CUDA involved).
+ * d2d_set_host_threads(n): size of the library's host thread pool (0 = default: the CPUs of the process's affinity
+ * mask, at most 16); d2d_pack_actions_host: d2d_pack_actions on HOST pointers (u8 [B][N][C] -> bitmasks [N][B]). */
+int d2d_set_host_threads(int n);
+int d2d_get_host_threads(void);
+int d2d_pack_actions_host(const uint8_t* actions_bnc, void* packed, int n_envs, int n_agents, int n_channels);
 
 /* Counters and raw state, env-minor: buffers u8 [N][Dmax][B]... exported as
  *   buffers  u8  [N][B][rec]   rec = d2d_env_record_bytes() (8/16/32), byte d = packets with d slots left
@@ -292,6 +302,8 @@ int d2d_net_check_inputs(const d2d_net* net, const float* x, int x_lead, int t0,
 #define D2D_SWITCH_BPTT_RECOMPUTE 6   /* 0: the BPTT kernel reads stored activations instead of recomputing the gates */
 #define D2D_SWITCH_ENV_MULTISTEP 9    /* 0: d2d_env_run_random_access launches one step kernel per step even where the
                                          register-resident multi-step kernel applies (single-channel env, N <= 4) */
+#define D2D_SWITCH_HOST_PACK 10       /* 0: d2d_env_step_host always copies the reference-layout actions as they are and
+                                         packs them on the device (default: packed on the host when >= 12 host threads) */
 int d2d_set_kernel_switch(int which, int enabled);
 int d2d_get_kernel_switch(int which);
 

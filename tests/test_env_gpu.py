@@ -171,10 +171,26 @@ def test_fused_random_access_policy(cuda_device):
     assert np.array_equal(to_np(env.discarded_packets), orc.discarded)
 
 
-@pytest.mark.parametrize("layout", ["reference", "device"])
+@pytest.mark.parametrize("layout", ["reference", "reference-device-pack", "device"])
 def test_host_buffer_step_matches_oracle(layout, cuda_device):
     """step_host (d2d_env_step_host: pinned host actions in, pinned host rewards out, pipelined copies) against the
-    oracle on Philox streams; the host reads step i - 1 after issuing step i, as bench.py's e2e loop does."""
+    oracle on Philox streams; the host reads step i - 1 after issuing step i, as bench.py's e2e loop does.
+    "reference": the [B, N, C] bytes are packed on the host (12 pool threads) before the copy; "reference-device-pack":
+    D2D_SWITCH_HOST_PACK = 0, they are copied as they are and packed by a kernel."""
+    import torch
+    from d2d_ppo_b200 import _lib as L
+    from oracle.envs_np import PhiloxSource
+    saved = L.lib().d2d_get_host_threads()
+    L.check(L.lib().d2d_set_host_threads(12))
+    L.set_kernel_switch(L.SWITCH_HOST_PACK, layout != "reference-device-pack")
+    try:
+        _host_buffer_step_case("reference" if layout.startswith("reference") else layout, cuda_device)
+    finally:
+        L.set_kernel_switch(L.SWITCH_HOST_PACK, True)
+        L.check(L.lib().d2d_set_host_threads(saved))
+
+
+def _host_buffer_step_case(layout, cuda_device):
     import torch
     from oracle.envs_np import PhiloxSource
     g = load_env_case("comb_c3_load0.33")
