@@ -545,7 +545,8 @@ def bench_env_configs(dev, hbm_peak, steps=200):
         run(f"c2 D2DEnv N=4 deadlines 7, {B} envs, fused random access", D2DEnv(n_envs=B, device=dev, seed=2, **c2),
             env_alg_bytes(7, 1, 4, 9, 5, 0), tp=TP)
     # c2 through RandomAccess.run's call (rewards accumulated, no observation rows): the steps of an episode run in ONE
-    # register-resident kernel (sc_run_kernel); the same call with one launch per step is timed beside it
+    # register-resident kernel (sc_run_kernel; four lanes per env, sc_run_lanes_kernel, up to 32,768 envs); the same call
+    # with one launch per step is timed beside it
     from d2d_ppo_b200 import _lib
     for B in (4096, 1 << 22):
         env = D2DEnv(n_envs=B, device=dev, seed=2, **c2)

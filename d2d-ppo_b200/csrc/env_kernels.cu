@@ -332,6 +332,85 @@ __global__ void __launch_bounds__(256) sc_run_kernel(const StepArgs a, const Run
   if (a.done) a.done[b] = (uint8_t)a.done_flag;
 }
 
+// The same episode-in-one-launch loop with FOUR LANES PER ENV (lane = device) for small batches, where sc_run_kernel is
+// bound by the dependent-issue chain of its few warps (4,096 envs = 128 warps on 148 SMs): every lane keeps ONE device's
+// record and counters, lanes 0 / 1 / 2 of a quad compute the policy / switch / arrival Philox call (one call per lane
+// and step instead of three per thread) and hand the words round with shuffles, the attempt bits meet in a ballot.
+// Same Philox counters and update order: trajectories are bit-identical to sc_run_kernel / sc_step_kernel.
+template <int W>
+__global__ void __launch_bounds__(128) sc_run_lanes_kernel(const StepArgs a, const RunArgs ra) {
+  extern __shared__ __align__(16) uint8_t smem[];
+  const EnvParamsHdr* P = stage_params(a, smem);
+  const uint32_t* cdf = reinterpret_cast<const uint32_t*>(smem + P->off_cdf);
+  const uint32_t* swthr = reinterpret_cast<const uint32_t*>(smem + P->off_sw);
+  const int N = P->N;
+  const size_t B = (size_t)a.B;
+  uint8_t* chan = reinterpret_cast<uint8_t*>(a.chan);
+  const int gid = blockIdx.x * blockDim.x + threadIdx.x;
+  const int k = gid & 3, lane = threadIdx.x & 31, quad0 = lane & ~3;
+  int b = gid >> 2;
+  const bool env_ok = b < a.B;                       // whole quads are in or out; out-of-range quads still shuffle
+  if (!env_ok) b = a.B - 1;
+  const bool live = env_ok && k < N;
+  const int kk = min(k, N - 1);
+  const size_t idx = (size_t)kk * B + b;
+  const uint32_t env = a.env_offset + (uint32_t)b;
+  Rec<W> rec = rec_load<W>(a.buf, idx);
+  uint32_t chv = chan[idx] & 1u, discv = a.disc[idx], recvv = a.recv[idx];
+  const uint32_t thr_sw = swthr[kk];
+  const int dl = P->deadline[kk];
+  uint32_t st0 = a.stats[b], st1 = a.stats[B + b];
+  int32_t rew = a.reward_accum ? a.reward[b] : 0;
+#pragma unroll 1
+  for (int i = 0; i < ra.n_inner; ++i) {
+    const uint32_t t = a.t + (uint32_t)i;
+    const uint64_t active = ra.active[ra.t_plain + i];
+    // lane 0: policy words, lane 1: switch words, lane 2: arrival words (only when a device is active this step)
+    uint4 r = make_uint4(0u, 0u, 0u, 0u);
+    if (k < 2 || (k == 2 && active)) r = philox_rk(a, env, t, (k == 0 ? kPurposePolicy : (k == 1 ? kPurposeSwitch : kPurposeArrival)) << 16, 0u);
+    // 16-bit policy / switch lanes of device k live in word k >> 1 (x or y for k < 4); the arrival word is word k
+    const uint32_t px = __shfl_sync(0xFFFFFFFFu, r.x, quad0), py = __shfl_sync(0xFFFFFFFFu, r.y, quad0);
+    const uint32_t sx = __shfl_sync(0xFFFFFFFFu, r.x, quad0 + 1), sy = __shfl_sync(0xFFFFFFFFu, r.y, quad0 + 1);
+    const uint32_t ax = __shfl_sync(0xFFFFFFFFu, r.x, quad0 + 2), ay = __shfl_sync(0xFFFFFFFFu, r.y, quad0 + 2);
+    const uint32_t az = __shfl_sync(0xFFFFFFFFu, r.z, quad0 + 2), aw = __shfl_sync(0xFFFFFFFFu, r.w, quad0 + 2);
+    const uint32_t pw = (k >> 1) ? py : px, sw = (k >> 1) ? sy : sx;
+    const uint32_t pol16 = (k & 1) ? (pw >> 16) : (pw & 0xFFFFu);
+    const uint32_t sw16 = (k & 1) ? (sw >> 16) : (sw & 0xFFFFu);
+    const uint32_t arw = k == 0 ? ax : (k == 1 ? ay : (k == 2 ? az : aw));
+    const bool at = live && pol16 < a.tp_thr && rec_any<W>(rec);          // env.py:125-127
+    const uint32_t att = (__ballot_sync(0xFFFFFFFFu, at) >> quad0) & 0xFu;
+    const uint32_t good = (__ballot_sync(0xFFFFFFFFu, at && chv) >> quad0) & 0xFu;
+    const int n_att = __popc(att);                                        // :130-152
+    const bool lone = n_att == 1;
+    const bool decoded = lone && good != 0;
+    const int ack = n_att > 1 ? -1 : (decoded ? 1 : 0);
+    st0 += (lone && !decoded) ? 1u : 0u;
+    st1 += n_att > 1 ? 1u : 0u;
+    if (live) {
+      rec_pop_earliest<W>(rec, decoded && at);                            // :137-144
+      discv += rec_age<W>(rec);                                           // :157-158
+      chv ^= sw16 < thr_sw ? 1u : 0u;                                     // :107-109
+      if ((active >> k) & 1ull) {                                         // :162-180
+        const uint32_t arrived = arrival_from_u(P, cdf, k, arw);
+        rec_set_byte<W>(rec, dl - 1, arrived);
+        recvv += arrived;
+      }
+    }
+    if (a.reward_accum) rew += ack;                                       // :191
+    else if (k == 0 && env_ok) a.reward[(size_t)i * ra.reward_stride + b] = ack;
+  }
+  if (live) {
+    rec_store<W>(a.buf, idx, rec);
+    chan[idx] = (uint8_t)chv;
+    a.disc[idx] = discv, a.recv[idx] = recvv;
+  }
+  if (k == 0 && env_ok) {
+    a.stats[b] = st0, a.stats[B + b] = st1;
+    if (a.reward_accum) a.reward[b] = rew;
+    if (a.done) a.done[b] = (uint8_t)a.done_flag;
+  }
+}
+
 template <int W>
 __global__ void __launch_bounds__(256) sc_reset_kernel(const StepArgs a) {
   extern __shared__ __align__(16) uint8_t smem[];
@@ -679,6 +758,7 @@ int host_threads();
 // fewer threads than this pack no faster than PCIe moves the unpacked bytes (measured: 16 threads 82 GB/s of action
 // bytes, 8 threads about the 50 - 55 GB/s of the link)
 constexpr int kHostPackMinThreads = 12;
+constexpr int kRunLanesMaxEnvs = 32768;   // up to here the multi-step env kernel runs four lanes per env
 
 static void pipe_free(HostPipe* p) {
   if (!p) return;
@@ -1034,10 +1114,17 @@ extern "C" int d2d_env_run_random_access(d2d_env* e, double tp, int n_steps, int
       a.done_flag = e->t + n_inner >= e->T;
       RunArgs ra;
       ra.active = e->active_dev, ra.t_plain = e->t + 1, ra.n_inner = n_inner, ra.reward_stride = reward_step_stride;
-      // few envs: 64-thread blocks spread the warps over the SMs (each warp is one dependent-issue chain)
-      const int block = e->B >= 148 * 256 ? 256 : 64, grid = (e->B + block - 1) / block;
-      if (e->W == 2) sc_run_kernel<2, 4><<<grid, block, e->params_bytes, as_stream(stream)>>>(a, ra);
-      else sc_run_kernel<4, 4><<<grid, block, e->params_bytes, as_stream(stream)>>>(a, ra);
+      if (e->B <= kRunLanesMaxEnvs) {
+        // small batches: four lanes per env (sc_run_lanes_kernel), 64-thread blocks = 16 envs spread over the SMs
+        const int block = 64, grid = (int)(((long long)e->B * 4 + block - 1) / block);
+        if (e->W == 2) sc_run_lanes_kernel<2><<<grid, block, e->params_bytes, as_stream(stream)>>>(a, ra);
+        else sc_run_lanes_kernel<4><<<grid, block, e->params_bytes, as_stream(stream)>>>(a, ra);
+      } else {
+        // few envs: 64-thread blocks spread the warps over the SMs (each warp is one dependent-issue chain)
+        const int block = e->B >= 148 * 256 ? 256 : 64, grid = (e->B + block - 1) / block;
+        if (e->W == 2) sc_run_kernel<2, 4><<<grid, block, e->params_bytes, as_stream(stream)>>>(a, ra);
+        else sc_run_kernel<4, 4><<<grid, block, e->params_bytes, as_stream(stream)>>>(a, ra);
+      }
       D2D_LAUNCHED();
       e->t += n_inner;
       i += n_inner - 1;

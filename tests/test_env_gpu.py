@@ -483,16 +483,17 @@ def test_selection_env_fused_random_access_matches_oracle(cuda_device):
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("B", [333, 40000])      # four lanes per env (sc_run_lanes_kernel) / one thread per env
 @pytest.mark.parametrize("deadline,traffic", [(7, "aperiodic"), (14, "aperiodic"), (5, "periodic"), (7, "mixed")])
-def test_multistep_kernel_equals_step_kernels(deadline, traffic, cuda_device):
+def test_multistep_kernel_equals_step_kernels(deadline, traffic, B, cuda_device):
     """D2DEnv, N <= 4, no per-step observation rows: d2d_env_run_random_access runs the steps of an episode inside ONE
-    kernel with the env state in registers (sc_run_kernel).  Bit-identical to the same call with the multi-step kernel
+    kernel with the env state in registers (sc_run_kernel, or sc_run_lanes_kernel up to 32,768 envs).  Bit-identical to the same call with the multi-step kernel
     switched off (one sc_step_kernel launch per step): per-step rewards, done flags, buffers, channel bits, packet
     counters, error / collision counters, across two automatic resets, and for the accumulating reward form."""
     import torch
     from d2d_ppo_b200 import _lib as L
     from d2d_ppo_b200.envs import D2DEnv
-    N, T, B, tp = (3 if traffic == "periodic" else 4), 11, 333, 0.35
+    N, T, tp = (3 if traffic == "periodic" else 4), 11, 0.35
     kw = dict(n_agents=N, deadlines=np.array([deadline] * N), lbdas=np.array([1 / 4] * N), episode_length=T,
               traffic_model="aperiodic" if traffic == "aperiodic" else "heterogeneous" if traffic == "mixed" else "periodic",
               channel_switch=0.2)
