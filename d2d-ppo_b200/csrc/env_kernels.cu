@@ -753,6 +753,7 @@ struct HostPipe {
 // host_pack.cpp
 namespace d2d {
 void host_pack_actions(const uint8_t* src, void* dst, long long B, int N, int C, int mask_bytes);
+bool host_pack_is_fast(int C, int mask_bytes);
 int host_threads();
 }  // namespace d2d
 // fewer threads than this pack no faster than PCIe moves the unpacked bytes (measured: 16 threads 82 GB/s of action
@@ -1205,7 +1206,8 @@ extern "C" int d2d_env_step_host(d2d_env* e, const void* actions_host, int layou
   //    so that 1/C of the bytes cross PCIe.  The call blocks for the packing; the copy and the step stay asynchronous,
   //    so the host packs call k + 1 while the device runs call k.
   const void* src_host = actions_host;
-  if (need_pack && d2d_get_kernel_switch(D2D_SWITCH_HOST_PACK) == 1 && d2d::host_threads() >= kHostPackMinThreads) {
+  if (need_pack && d2d_get_kernel_switch(D2D_SWITCH_HOST_PACK) == 1 && d2d::host_threads() >= kHostPackMinThreads &&
+      d2d::host_pack_is_fast(e->C, e->CB)) {
     if (!p->hpacked[slot]) D2D_CUDA(cudaHostAlloc((void**)&p->hpacked[slot], nb * e->CB, cudaHostAllocDefault));
     if (reused) D2D_CUDA(cudaEventSynchronize(p->in_ready[slot]));   // the copy of call k - 2 has left this buffer
     d2d::host_pack_actions(reinterpret_cast<const uint8_t*>(actions_host), p->hpacked[slot], e->B, e->N, e->C, e->CB);

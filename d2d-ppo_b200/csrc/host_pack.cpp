@@ -140,13 +140,21 @@ __attribute__((target("avx2"))) void pack8_avx2(const uint8_t* src, uint8_t* dst
 
 }  // namespace
 
+// true where the vector kernel applies (8 channels, one mask byte, AVX2): only there does packing on the host outrun the
+// PCIe copy of the unpacked bytes, so d2d_env_step_host takes the host path only then
+bool host_pack_is_fast(int C, int mask_bytes) {
+#ifdef D2D_X86
+  return C == 8 && mask_bytes == 1 && __builtin_cpu_supports("avx2");
+#else
+  (void)C, (void)mask_bytes;
+  return false;
+#endif
+}
+
 // src u8 [B][N][C] -> dst masks [N][B] of mask_bytes (1 / 2 / 4) each; all threads of the pool, split by env ranges
 void host_pack_actions(const uint8_t* src, void* dst, long long B, int N, int C, int mask_bytes) {
   HostPool* pl = pool();
-  bool avx2 = false;
-#ifdef D2D_X86
-  avx2 = C == 8 && mask_bytes == 1 && __builtin_cpu_supports("avx2");
-#endif
+  const bool avx2 = host_pack_is_fast(C, mask_bytes);
   const std::function<void(int, int)> job = [&](int part, int parts) {
     // whole cache lines of every output row per thread: env ranges in multiples of 64
     const long long per = ((B + parts - 1) / parts + 63) / 64 * 64;

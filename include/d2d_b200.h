@@ -177,9 +177,10 @@ int d2d_pack_actions(const uint8_t* actions_bnc, void* packed, int n_envs, int n
  * must stay untouched until the call's step ran (d2d_env_host_wait of the same ticket suffices).
  * *ticket (may be NULL) identifies the call; d2d_env_host_wait(env, ticket) blocks the host thread until
  * reward_host / done_host of that call are valid.
- * With D2D_ACT_HOST_REFERENCE and at least 12 host threads (d2d_get_host_threads) the library packs the [B][N][C] bytes
- * into the [N][B] channel bitmasks ON THE HOST (AVX2, thread pool) and copies 1/C of the bytes; the call then blocks for
- * the packing (actions_host may be reused as soon as it returns), the copy and the step stay asynchronous. */
+ * With D2D_ACT_HOST_REFERENCE, 8 channels, an AVX2 host and at least 12 host threads (d2d_get_host_threads) the library
+ * packs the [B][N][C] bytes into the [N][B] channel bitmasks ON THE HOST (thread pool) and copies 1/8 of the bytes; the
+ * call then blocks for the packing (actions_host may be reused as soon as it returns), the copy and the step stay
+ * asynchronous. */
 #define D2D_ACT_HOST_REFERENCE 0
 #define D2D_ACT_HOST_DEVICE_LAYOUT 1
 int d2d_env_step_host(d2d_env* env, const void* actions_host, int layout, float* obs, float* state,
