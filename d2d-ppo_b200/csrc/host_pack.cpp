@@ -84,6 +84,8 @@ int default_threads() {
   if (sched_getaffinity(0, sizeof(set), &set) == 0) hw = (unsigned)CPU_COUNT(&set);   // respects a rank's NUMA binding
 #endif
   if (hw == 0) hw = 1;
+  // all CPUs, at most 16: packing alone is fastest with 12 of a 16-CPU box's CPUs (profiles/r02_u_time_host_pack.log),
+  // but inside the host-buffer step 16 threads win (0.69 against 0.76 ms per step, profiles/r02_u_ab_host_pack.log)
   return (int)(hw > 16 ? 16 : hw);
 }
 
