@@ -80,3 +80,57 @@ def test_rollout_matches_oracle_env():
         assert np.array_equal(g["buf_rewards"][rows], np.asarray(reward, dtype=np.float32))
         cur = nxt
     assert np.allclose(env.compute_urllc(), g["train_scores"], atol=1e-12)
+
+
+def _reference_or_skip():
+    from oracle import ref_harness
+    if not ref_harness.reference_available():
+        pytest.skip("reference tree not mounted (GPU box / driver container)")
+    return ref_harness.import_reference("algorithms.irdqn")
+
+
+def test_q_forward_and_sample_chunk_against_live_reference():
+    """Direct checks against the imported reference module where it is mounted: RNN.forward on full and short windows,
+    ReplayBuffer.sample_chunk on a buffer that spans several episodes, DQN.update_epsilon."""
+    mod = _reference_or_skip()
+    torch.manual_seed(3)
+    net = mod.RNN(9, 5, hidden_size=24)
+    p = {k: v.detach().clone() for k, v in net.state_dict().items()}
+    assert list(p) == Q.Q_KEYS
+    for Lw in (1, 3, 6):
+        x = torch.randn(7, Lw, 9)
+        assert torch.allclose(Q.q_forward(p, x), net(x).detach(), atol=2e-6, rtol=1e-5)
+    # 2-D input = one window (irdqn.py:79-80)
+    x2 = torch.randn(4, 9)
+    assert torch.allclose(Q.q_forward(p, x2[None]), net(x2).detach(), atol=2e-6, rtol=1e-5)
+
+    rng = np.random.default_rng(0)
+    T, K, N, I, L, mb = 6, 5, 3, 4, 4, 16
+    buf = mod.ReplayBuffer(10 ** 4, "cpu")
+    states = rng.standard_normal((K * T, N, I)).astype(np.float32)
+    nxt = rng.standard_normal((K * T, N, I)).astype(np.float32)
+    acts = rng.integers(0, 5, (K * T, N))
+    rews = rng.integers(0, 3, (K * T, N)).astype(np.float32)
+    dones = np.arange(K * T) % T == T - 1
+    for i in range(K * T):
+        buf.add((torch.tensor(states[i]), acts[i], rews[i], torch.tensor(nxt[i]), bool(dones[i])))
+    start = rng.integers(0, K * T - L, mb)
+    real = np.random.randint
+    np.random.randint = lambda lo, hi=None, size=None: start
+    try:
+        s, a, r, sn, d = buf.sample_chunk(mb, L)
+    finally:
+        np.random.randint = real
+    ms, ma, mr, msn, md = Q.sample_chunk(states, nxt, acts, rews, dones, start, L)
+    assert np.array_equal(s.numpy(), ms) and np.array_equal(sn.numpy(), msn)
+    # the reference returns whole chunks of actions / rewards / dones; train() keeps the last transition (:293-296)
+    assert np.array_equal(a[:, -1].numpy(), ma) and np.array_equal(r[:, -1].numpy(), mr)
+    assert np.array_equal(d[:, -1, 0].numpy(), md.astype(np.float32))
+
+    class _Env:                                     # DQN.__init__ only reads the two spaces
+        observation_space = [type("S", (), {"shape": (9,)})()]
+        action_space = [type("A", (), {"n": 5})()]
+    dqn = mod.DQN(_Env())
+    for ep in (0, 1, 250, 999, 1000, 5000):
+        dqn.update_epsilon(ep)
+        assert abs(dqn.epsilon - Q.epsilon_at(ep)) < 1e-12
