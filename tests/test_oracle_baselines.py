@@ -45,3 +45,30 @@ def test_edf_act_with_channel_mask_matches_reference_step_by_step():
         env.step(ref_acts[t])                                             # teacher-forced: random picks included
     ref_rew, ref_recv, ref_disc, ref_jains, ref_errs = g["channel/per_episode"]
     assert np.array_equal(env.channel_errors, ref_errs) and np.array_equal(env.discarded.sum(1), ref_disc)
+
+
+def test_edf_act_against_live_reference():
+    """Where the reference tree is mounted: its own EarliestDeadlineFirstScheduler.act / preprocess_state and
+    GFAccess.act on random buffers against the restatement (GFAccess: the empty-buffer mask; its draws are random)."""
+    import pytest
+    from oracle import ref_harness
+    if not ref_harness.reference_available():
+        pytest.skip("reference tree not mounted (GPU box / driver container)")
+    base = ref_harness.import_reference("algorithms.baselines")
+
+    class _Env:
+        n_agents = 5
+    edf = base.EarliestDeadlineFirstScheduler(_Env())
+    gf = base.GFAccess(_Env(), transmission_prob=1.0)
+    rng = np.random.default_rng(1)
+    n_checked = 0
+    for _ in range(300):
+        buf = (rng.integers(0, 3, (5, 6)) * (rng.random((5, 6)) < 0.25)).astype(np.float64)
+        mine, anyp = baselines_np.edf_act(buf[None])
+        agg = edf.preprocess_state(buf)
+        assert np.array_equal(agg >= 0, buf.sum(1) > 0)
+        if anyp[0]:
+            assert np.array_equal(edf.act(buf), mine[0])
+            n_checked += 1
+        assert np.array_equal(gf.act(buf) != 0, buf.sum(1) > 0)       # tp = 1: every device with a packet transmits
+    assert n_checked > 200
