@@ -813,10 +813,15 @@ def run_native(args):
                                          "as they are and are packed on the device (PCIe bound)"},
                 "h2d_gbs_per_rank": h2d_gbs_rank, "h2d_gbs_all_ranks": h2d_gbs_rank * world,
                 "numa_binding": None if numa is None else {"node": numa[0], "cpus": numa[1]},
-                "limiter": "host -> device copy of the u8 [B,N,C] actions (50.3 MB per step and rank) over each GPU's "
-                           "PCIe link; with N ranks the N concurrent pinned-memory copies share the host's memory / "
-                           "root-complex bandwidth, so the per-rank rate drops as N grows (no collective is involved); "
-                           "packed_actions moves 8x fewer bytes through the same call",
+                "limiter": ("the host: packing 50.3 MB of u8 [B,N,C] actions per step and rank into 6.3 MB of "
+                            "bitmasks (host memory bandwidth and the pool's fork-join per call); unpacked_copy is the "
+                            "PCIe-bound alternative, packed_actions the same call when the caller hands in bitmasks")
+                           if host_packed else
+                           ("host -> device copy of the u8 [B,N,C] actions (50.3 MB per step and rank) over each GPU's "
+                            "PCIe link; with N ranks the N concurrent pinned-memory copies share the host's memory / "
+                            "root-complex bandwidth, so the per-rank rate drops as N grows (no collective is "
+                            "involved); packed_actions moves 8x fewer bytes through the same call; this rank has too "
+                            "few host threads for host-side packing"),
                 "packed_actions": {"value": e2e_masks, "unit": "agent-steps/s", "h2d_bytes_per_step": B * N_AGENTS,
                                    "d2h_bytes_per_step": B * 4,
                                    "api": "same call with the device action layout (u8 channel bitmask [N,B])"}},
