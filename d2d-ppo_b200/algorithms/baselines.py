@@ -158,7 +158,7 @@ def _finish_run(tot, verbose):
     if verbose:
         print(f"Number of received packets: {recv}")
         print(f"Number of channel_losses: {errors}")
-    return 1 - disc / recv, jains / n, int(errors), rew / n
+    return (1 - disc / recv) if recv else float("nan"), jains / n, int(errors), rew / n   # no packet: numpy's 0 / 0
 
 
 class EarliestDeadlineFirstScheduler:

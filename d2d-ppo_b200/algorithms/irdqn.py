@@ -259,7 +259,7 @@ class iRDQN:
             left -= n
         _dist.all_reduce_sum_(stats)
         d, r, s, n = stats.tolist()
-        return 1 - d / r, s / max(n, 1.0)
+        return (1 - d / r) if r else float("nan"), s / max(n, 1.0)      # no packet at all: numpy's 0 / 0
 
     # ------------------------------------------------------------------ checkpoints (not in the reference's iRDQN;
     # same agent_{i}.pth convention as the PPO learners, state_dict keys of irdqn.RNN)
