@@ -225,9 +225,10 @@ static void launch_wgrad_t(const WgradArgs& a, dim3 grid, cudaStream_t s) {
 
 // dW (+ db) of `w` from dy [out_dim] and x [K]; accumulated into grads
 static int launch_wgrad(d2d_net* n, const View& dy, const View& x, const Wt& w, bool zero_in, float* grads, int t0,
-                        int t1, cudaStream_t s) {
+                        int t1, cudaStream_t s, bool x_is_input = false) {
   WgradArgs a;
   memset(&a, 0, sizeof(a));
+  a.x_planes = (x_is_input && n->x_exact) ? 1 : 0;   // x = the observations, exact in bf16 by the caller's promise
   a.dy = dy, a.x = x, a.partial = n->partial, a.part_stride = n->part_stride;
   a.out_dim = w.out_dim, a.B = n->B, a.t0 = t0, a.t1 = t1, a.with_bias = w.b_off != nullptr;
   int maxK = 0;
@@ -255,7 +256,7 @@ static int launch_wgrad(d2d_net* n, const View& dy, const View& x, const Wt& w, 
       }
       wb.w_off = &woff;
       wb.b_off = w.b_off ? &boff : nullptr;
-      const int rc = launch_wgrad(n, dyb, x, wb, zero_in, grads, t0, t1, s);
+      const int rc = launch_wgrad(n, dyb, x, wb, zero_in, grads, t0, t1, s, x_is_input);
       if (rc) return rc;
     }
     return D2D_OK;
@@ -737,7 +738,7 @@ static int backward_chunk(d2d_net* n, const float* params, const float* x, int x
   }
   if (n->arch == D2D_NET_MLP) {
     w1.in_dim = &n->in_dim;
-    return launch_wgrad(n, dy1, xin, w1, false, grads, c0, c1, s);
+    return launch_wgrad(n, dy1, xin, w1, false, grads, c0, c1, s, true);
   }
   const int L = n->L, halo = c.halo;
   const View hlast = make_view(hs_ptr(n, c, true, L - 1), H * NB, -c0, N, H, B);
@@ -851,7 +852,7 @@ static int backward_chunk(d2d_net* n, const float* params, const float* x, int x
   }
   // dW_ih = d(gi)^T x over every observation the chunk touched (zero observations before t = 0 feed b_ih only)
   Wt wih{&n->o_wih, &n->o_bih, &n->in_dim, 0, 3 * H};
-  return launch_wgrad(n, dgi, xin, wih, false, grads, c0 - halo, c1, s);
+  return launch_wgrad(n, dgi, xin, wih, false, grads, c0 - halo, c1, s, true);
 }
 
 // ================================================================================================

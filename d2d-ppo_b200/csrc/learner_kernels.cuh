@@ -413,6 +413,8 @@ struct WgradArgs {
   int out_dim;
   int B, t0, t1;
   int with_bias;
+  int x_planes;                // tensor-core path: bf16 planes of x that can be non-zero (0 = all three; 1 when x is
+                               // exactly representable in bf16 -- integer observations -- so only p0 carries data)
 };
 
 constexpr int kWgRows = 32;  // rows staged per iteration

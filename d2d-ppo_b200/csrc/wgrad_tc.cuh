@@ -83,6 +83,7 @@ __global__ void __launch_bounds__(tcw::kThreads, 2) wgrad_tc_kernel(const WgradA
     if (lane == 0 && my_chunks > 0) {
       const uint32_t idesc = idesc_bf16_m128(NB);
       const uint32_t sbo = (kRows >> 3) * 128;   // bytes between 8-row groups of a [.][32] tile
+      const int bp = a.x_planes > 0 ? a.x_planes : 3;   // x exact in bf16: planes 1, 2 of B are zero, their products too
       bool first = true;
       for (int i = 0; i < my_chunks; ++i) {
         const int st = i & 1;
@@ -94,7 +95,7 @@ __global__ void __launch_bounds__(tcw::kThreads, 2) wgrad_tc_kernel(const WgradA
         for (int pi = 0; pi < 3; ++pi)
 #pragma unroll
           for (int pj = 0; pj < 3; ++pj) {
-            if (pi + pj > 2) continue;
+            if (pi + pj > 2 || pj >= bp) continue;
             const uint32_t aa = smem_u32(sa + pi * kAPlane);
             const uint32_t bb = smem_u32(sb + pj * NB * kRows);
 #pragma unroll
@@ -162,6 +163,7 @@ __global__ void __launch_bounds__(tcw::kThreads, 2) wgrad_tc_kernel(const WgradA
           for (int j = 0; j < 8; ++j) split3_trunc(v[j], q0[j], q1[j], q2[j]);
           *reinterpret_cast<uint4*>(dst) =
               make_uint4(pack_hi(q0[0], q0[1]), pack_hi(q0[2], q0[3]), pack_hi(q0[4], q0[5]), pack_hi(q0[6], q0[7]));
+          if (f >= O && a.x_planes == 1) continue;     // exact x: the lower planes stay at the zeros of the initial fill
           *reinterpret_cast<uint4*>(dst + plane_stride) =
               make_uint4(pack_hi(q1[0], q1[1]), pack_hi(q1[2], q1[3]), pack_hi(q1[4], q1[5]), pack_hi(q1[6], q1[7]));
           *reinterpret_cast<uint4*>(dst + 2 * plane_stride) =
