@@ -741,6 +741,8 @@ def run_native(args):
     host_packed = host_threads >= 12
     e2e_value = e2e_time(host_actions, "reference")
     secs_default = e2e_secs["reference"]
+    pack_state = env.host_pack_state              # 0: the library timed its first calls and fell back to the copy
+    host_packed = host_packed and pack_state == 1
     _L.set_kernel_switch(_L.SWITCH_HOST_PACK, False)
     e2e_unpacked = e2e_time(host_actions, "reference")
     secs_unpacked = e2e_secs["reference"]
@@ -801,7 +803,7 @@ def run_native(args):
                 "api": "CombinatorialEnv.step_host (C ABI d2d_env_step_host): actions u8 [B,N,C] 0/1, the reference's "
                        "(N,C) array per env, in pinned host memory -> i32 [B] rewards in pinned host memory, read by "
                        "the host every step; two calls in flight",
-                "host_packed": host_packed, "host_threads": host_threads,
+                "host_packed": host_packed, "host_threads": host_threads, "host_pack_state": pack_state,
                 "host_bytes_read_per_step": B * N_AGENTS * N_CHANNELS,
                 "host_pack_gbs_per_rank": (B * N_AGENTS * N_CHANNELS * Ke / secs_default / 1e9) if host_packed else None,
                 "bound": ("host: the library packs the 48 B of actions per env-step into 6 B of channel bitmasks on "

@@ -80,6 +80,7 @@ _SIGNATURES = {
                                             C.c_int, _P, _P, C.POINTER(C.c_int)]),
     "d2d_env_step_host": (C.c_int, [_P, _P, C.c_int, _P, _P, _P, _P, _P, _P, C.POINTER(C.c_uint64)]),
     "d2d_env_host_wait": (C.c_int, [_P, C.c_uint64]),
+    "d2d_env_host_pack_state": (C.c_int, [_P]),
     "d2d_pack_actions": (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_int, _P]),
     "d2d_set_host_threads": (C.c_int, [C.c_int]),
     "d2d_get_host_threads": (C.c_int, []),

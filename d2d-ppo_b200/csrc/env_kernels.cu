@@ -18,6 +18,7 @@
 //   * grid-stride persistent launch sized in whole waves of the SM count; per-env parameters are staged
 //     once per block in shared memory and read by broadcast.
 #include <algorithm>
+#include <chrono>
 #include <cmath>
 #include <cstring>
 #include <new>
@@ -741,6 +742,11 @@ struct HostPipe {
   cudaStream_t h2d = nullptr, d2h = nullptr;
   uint8_t* stage[kSlots] = {nullptr, nullptr};    // device copy of the host actions, as the host laid them out
   uint8_t* hpacked[kSlots] = {nullptr, nullptr};  // pinned host buffers: the actions packed to bitmasks on the host
+  // host packing pays only while the host packs faster than PCIe would move the unpacked bytes; the first calls are
+  // timed and a host that is too slow (a loaded box: 37 GB/s measured instead of ~80) falls back for good
+  int pack_samples = 0;
+  double pack_ms_sum = 0.0;
+  int host_pack_state = -1;                       // -1 not used yet, 1 active, 0 switched off after the timed calls
   void* masks[kSlots] = {nullptr, nullptr};       // device-layout actions [N][B] (packed from `stage` if needed)
   int32_t* reward[kSlots] = {nullptr, nullptr};
   uint8_t* done[kSlots] = {nullptr, nullptr};
@@ -759,6 +765,7 @@ int host_threads();
 // fewer threads than this pack no faster than PCIe moves the unpacked bytes (measured: 16 threads 82 GB/s of action
 // bytes, 8 threads about the 50 - 55 GB/s of the link)
 constexpr int kHostPackMinThreads = 12;
+constexpr int kHostPackSamples = 8;
 constexpr int kRunLanesMaxEnvs = 32768;   // up to here the multi-step env kernel runs four lanes per env
 
 static void pipe_free(HostPipe* p) {
@@ -1207,12 +1214,23 @@ extern "C" int d2d_env_step_host(d2d_env* e, const void* actions_host, int layou
   //    so the host packs call k + 1 while the device runs call k.
   const void* src_host = actions_host;
   if (need_pack && d2d_get_kernel_switch(D2D_SWITCH_HOST_PACK) == 1 && d2d::host_threads() >= kHostPackMinThreads &&
-      d2d::host_pack_is_fast(e->C, e->CB)) {
+      d2d::host_pack_is_fast(e->C, e->CB) && p->host_pack_state != 0) {
     if (!p->hpacked[slot]) D2D_CUDA(cudaHostAlloc((void**)&p->hpacked[slot], nb * e->CB, cudaHostAllocDefault));
     if (reused) D2D_CUDA(cudaEventSynchronize(p->in_ready[slot]));   // the copy of call k - 2 has left this buffer
+    const auto t0 = std::chrono::steady_clock::now();
     d2d::host_pack_actions(reinterpret_cast<const uint8_t*>(actions_host), p->hpacked[slot], e->B, e->N, e->C, e->CB);
+    const double ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
     src_host = p->hpacked[slot];
     need_pack = false;
+    p->host_pack_state = 1;
+    // calls 2 .. 9 are timed (the first two fault the buffers in): slower on average than the unpacked bytes at
+    // 40 GB/s of PCIe -> the following calls copy them as they are and pack on the device
+    if (p->calls >= 2 && p->pack_samples < kHostPackSamples) {
+      p->pack_ms_sum += ms;
+      if (++p->pack_samples == kHostPackSamples &&
+          p->pack_ms_sum / kHostPackSamples > (double)(nb * e->C) / 40.0e6)
+        p->host_pack_state = 0;
+    }
   }
   // 1. host -> device on the copy-in stream, once the step of call k - 2 has consumed this slot.  The copy is NOT
   //    ordered after the caller's stream (that would serialise it behind the previous call's step and lose the
@@ -1240,6 +1258,10 @@ extern "C" int d2d_env_step_host(d2d_env* e, const void* actions_host, int layou
   if (ticket) *ticket = p->calls;
   p->calls += 1;
   return D2D_OK;
+}
+
+extern "C" int d2d_env_host_pack_state(const d2d_env* e) {
+  return (e && e->pipe) ? e->pipe->host_pack_state : -1;
 }
 
 extern "C" int d2d_env_host_wait(d2d_env* e, uint64_t ticket) {

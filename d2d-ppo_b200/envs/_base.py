@@ -304,6 +304,12 @@ class LockstepEnv:
         self.obs_rows_tensor, self.state_rows_tensor = obs, state
         return int(ticket.value)
 
+    @property
+    def host_pack_state(self):
+        """-1: host-side action packing not used by step_host (so far); 1: active; 0: switched off after the timed
+        first calls because this host packs slower than PCIe moves the unpacked bytes (d2d_env_host_pack_state)."""
+        return int(self._lib.d2d_env_host_pack_state(self._h))
+
     def host_wait(self, ticket):
         """Block until the host buffers of the step_host call `ticket` are valid."""
         L.check(self._lib.d2d_env_host_wait(self._h, int(ticket)))

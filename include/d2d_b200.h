@@ -186,6 +186,9 @@ int d2d_pack_actions(const uint8_t* actions_bnc, void* packed, int n_envs, int n
 int d2d_env_step_host(d2d_env* env, const void* actions_host, int layout, float* obs, float* state,
                       int32_t* reward_host, uint8_t* done_host, void* ack, void* stream, uint64_t* ticket);
 int d2d_env_host_wait(d2d_env* env, uint64_t ticket);
+/* Host-side packing of this env's host-buffer steps: -1 not used (so far), 1 active, 0 switched off -- calls 2 .. 9 are
+ * timed, and a host that packs slower than 40 GB/s of PCIe would move the unpacked bytes keeps the unpacked copy. */
+int d2d_env_host_pack_state(const d2d_env* env);
 
 /* Host-side helpers of the host-buffer step (csrc/host_pack.cpp, no CUDA involved).
  * d2d_set_host_threads(n): size of the library's host thread pool (0 = default: the CPUs of the process's affinity
